@@ -1,0 +1,155 @@
+/*
+ * uivr.h -- C-ABI of the B200-native differential volumetric path tracer (libuivr.so).
+ *
+ * Drop-in boundary for the hot path of rgl-epfl/unbiased-inverse-volume-rendering:
+ * everything `mi.render(scene, params, integrator='volpathsimple', ...)` + `dr.backward(loss)`
+ * execute on the device for one sensor (python/optimize.py:345-350), i.e.
+ *   RBIntegrator.render / render_backward   (restated in python/batched.py:134-197, 212-326)
+ *   VolpathSimpleIntegrator.sample          (python/integrators/volpathsimple.py:38-290)
+ *   Medium::sample_interaction(_drt), GridVolume lookup/adjoint, majorant supergrid,
+ *   PCG32 `independent` sampler, perspective sensor, box hdrfilm   (un-vendored Mitsuba 3
+ *   branch; call sites python/integrators/volpathsimple.py:348,469,550,375,141,...).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types; every call returns 0 on success,
+ *    a negative uivr_status otherwise (uivr_last_error(ctx) gives the message).  No C++
+ *    exception crosses the boundary.
+ *  - "d_" pointers are DEVICE pointers owned by the caller (e.g. torch tensors); the library
+ *    never frees them.  Tensors are contiguous float32: sigma_t (Z,Y,X[,1]), albedo (Z,Y,X,3),
+ *    image / grad_image (H,W,3).  "h_" pointers are HOST pointers (the *_host entry points
+ *    stage them through context-owned device buffers, copies on `stream`).
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream unless
+ *    stated otherwise.  A context is bound to one device and is not thread-safe; multi-GPU =
+ *    one context per rank (pixel sharding via uivr_shard, gradients summed by the caller,
+ *    e.g. ncclAllReduce).
+ */
+#ifndef UIVR_H
+#define UIVR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uivr_ctx uivr_ctx;
+
+typedef enum {
+    UIVR_OK = 0,
+    UIVR_ERR_INVALID = -1,    /* bad argument / precondition (reference: Python assert / raise) */
+    UIVR_ERR_CUDA = -2,       /* CUDA runtime error */
+    UIVR_ERR_STATE = -3,      /* call order (scene / medium not set) */
+    UIVR_ERR_NOMEM = -4
+} uivr_status;
+
+/* Scene: one medium box + perspective sensor + constant emitter.
+ * Replaces the Mitsuba scene dict of tests/test_integrators.py:19-116 (cube_test_scene). */
+typedef struct {
+    int32_t res[3];          /* grid resolution X, Y, Z */
+    float   to_local[12];    /* world->local affine (row-major 3x4); medium = local [0,1]^3 */
+    float   scale;           /* medium 'scale' (tests/test_integrators.py:83) */
+    int32_t majorant_factor; /* supergrid factor (scene_config.py:36; optimize.py:182-199); <=1: global */
+    float   cam_origin[3], cam_left[3], cam_up[3], cam_dir[3]; /* look_at frame (:46-53) */
+    float   tan_x, tan_y;    /* tan(fov_x/2), tan_x*H/W */
+    float   near_clip;
+    int32_t width, height;   /* box-filter hdrfilm (:58-66) */
+    float   radiance[3];     /* constant emitter (:73-77) */
+} uivr_scene_desc;
+
+/* Integrator properties: python/integrators/volpathsimple.py:19-34 (+ max_depth of the base
+ * class; rr_depth is always > max_depth, python/opt_config.py:105-106). */
+typedef struct {
+    int32_t max_depth;
+    int32_t hide_emitters;
+    int32_t use_nee;
+    int32_t use_drt;
+    int32_t use_drt_subsampling;
+    int32_t use_drt_mis;
+} uivr_integrator_props;
+
+/* Pixel p is rendered by this call iff (p / block) % count == rank.  count<=1: all pixels.
+ * RNG streams are keyed by the GLOBAL sample index, so results do not depend on the split. */
+typedef struct {
+    int32_t rank, count, block;
+} uivr_shard;
+
+enum {
+    UIVR_CNT_SIGMA_TAPS = 0,  /* trilinear sigma_t lookups                 (32 B each)   */
+    UIVR_CNT_ALBEDO_TAPS,     /* trilinear albedo lookups                  (96 B each)   */
+    UIVR_CNT_MAJORANT_READS,  /* supergrid cell reads                      (4 B each)    */
+    UIVR_CNT_SIGMA_SCATTERS,  /* gradient scatters into d sigma_t          (64 B each)   */
+    UIVR_CNT_ALBEDO_SCATTERS, /* gradient scatters into d albedo           (192 B each)  */
+    UIVR_CNT_CAMERA_HITS,
+    UIVR_CNT_REAL_COLLISIONS,
+    UIVR_CNT_RNG_DRAWS,
+    UIVR_CNT_SAMPLES,
+    UIVR_NUM_COUNTERS
+};
+
+/* ---- lifetime ---- */
+int         uivr_create(int device, uivr_ctx** out);
+int         uivr_destroy(uivr_ctx* ctx);
+const char* uivr_last_error(const uivr_ctx* ctx);
+int         uivr_version(void);
+
+/* ---- configuration (host side, cheap) ---- */
+int uivr_set_scene(uivr_ctx* ctx, const uivr_scene_desc* scene);              /* mi.load_dict(scene) */
+int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props);   /* IntegratorConfig.create, opt_config.py:97-108 */
+
+/* params.update(): rebuild the device-side lookup structures derived from sigma_t -- the
+ * corner-octet tap layout and the majorant supergrid (upstream does the latter on
+ * params.update(), triggered at optimize.py:165, :251, :354).  Must be called after every
+ * change of sigma_t and before rendering. */
+int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream);
+
+/* ---- the path ---- */
+/* mi.render(...) primal: image[H,W,3] = box-film mean over spp of sample(Primal) (optimize.py:345).
+ * d_sample_L (optional, may be NULL): per-sample radiance [W*H*spp,3] for bit-level parity tests. */
+int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int32_t spp,
+                        const uivr_shard* shard, float* d_image, float* d_sample_L, void* stream);
+
+/* dr.backward(loss) -> RBIntegrator.render_backward (batched.py:212-326): primal replay at
+ * seed_grad, then the path-replay adjoint with the three gradient estimators + DRT.
+ * d_dsigma_t [Z,Y,X] and d_dalbedo [Z,Y,X,3] are OVERWRITTEN with this call's gradients. */
+int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_grad_image,
+                         uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard,
+                         float* d_dsigma_t, float* d_dalbedo, float* d_sample_L, void* stream);
+
+/* Host-buffer variants (end-to-end path: H2D of the parameters / grad_image, D2H of the
+ * results inside the call; synchronises `stream` before returning). */
+int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo,
+                             uint32_t seed, int32_t spp, const uivr_shard* shard,
+                             float* h_image, void* stream);
+int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo,
+                              const float* h_grad_image, uint32_t seed_grad, int32_t spp_grad,
+                              const uivr_shard* shard, float* h_dsigma_t, float* h_dalbedo,
+                              void* stream);
+
+/* ---- instrumentation ---- */
+/* Event counters (SURVEY §8d algorithmic bytes).  Counting kernels are separate template
+ * instances; enable only for accounting passes, not for timing. */
+int uivr_set_counting(uivr_ctx* ctx, int enable);
+int uivr_reset_counters(uivr_ctx* ctx, void* stream);
+int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stream); /* synchronises */
+/* number of kernel launches issued by this context so far */
+int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
+/* kernel variant: 0 = persistent lane-refill megakernel (default), 1 = one-sample-per-lane */
+int uivr_set_variant(uivr_ctx* ctx, int variant);
+
+/* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */
+/* out[0:n] = -ln(1-u);  s,c = sin/cos(2 pi x);  sampler floats of stream (seed, idx) */
+int uivr_test_neg_log1m(uivr_ctx* ctx, const float* d_u, int n, float* d_out, void* stream);
+int uivr_test_sincos2pi(uivr_ctx* ctx, const float* d_x, int n, float* d_s, float* d_c, void* stream);
+int uivr_test_sampler(uivr_ctx* ctx, uint32_t seed, uint32_t idx0, int nstreams, int ndraws,
+                      float* d_out, void* stream);
+/* sigma_t(p) through the octet layout (after uivr_update_medium), p = n x 3 local points */
+int uivr_test_sigma_lookup(uivr_ctx* ctx, const float* d_p, int n, float* d_out, void* stream);
+/* copy the current majorant supergrid to d_out (mres[0]*mres[1]*mres[2] floats) */
+int uivr_get_majorant(uivr_ctx* ctx, int32_t mres[3], float* d_out, void* stream);
+uint32_t uivr_tea32(uint32_t v0, uint32_t v1);          /* mi.sample_tea_32(v0, v1)[0] */
+uint32_t uivr_alt_seed(uint32_t seed_grad);             /* volpathsimple.py:99-107 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,225 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- not the product).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED at the upstream (Mitsuba 3 / Dr.Jit) boundary: see
+oracle/uivr_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+COUNTER_NAMES = ["sigma_taps", "albedo_taps", "majorant_reads", "sigma_scatters",
+                 "albedo_scatters", "camera_hits", "real_collisions", "rng_draws", "samples"]
+
+
+class _Scene(C.Structure):
+    _fields_ = [
+        ("res", C.c_int32 * 3), ("to_local", C.c_float * 12), ("scale", C.c_float),
+        ("majorant_factor", C.c_int32),
+        ("cam_origin", C.c_float * 3), ("cam_left", C.c_float * 3), ("cam_up", C.c_float * 3),
+        ("cam_dir", C.c_float * 3), ("tan_x", C.c_float), ("tan_y", C.c_float),
+        ("near_clip", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+        ("radiance", C.c_float * 3),
+        ("max_depth", C.c_int32), ("hide_emitters", C.c_int32), ("use_nee", C.c_int32),
+        ("use_drt", C.c_int32), ("use_drt_subsampling", C.c_int32), ("use_drt_mis", C.c_int32),
+    ]
+
+
+class _Shard(C.Structure):
+    _fields_ = [("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("shard_block", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc, oracle/Makefile) -> oracle/_build/*.so."""
+    so = os.path.join(_BUILD, "libuivr_oracle.so")
+    src = os.path.join(_HERE, "uivr_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def _has_fma() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    name = "libuivr_oracle.so" if _has_fma() else "libuivr_oracle_nofma.so"
+    path = os.path.join(_BUILD, name)
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    fp, dp, u64p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    L.uivr_oracle_render_forward.argtypes = [C.POINTER(_Scene), fp, fp, C.c_uint32, C.c_int32,
+                                             C.POINTER(_Shard), C.c_int, fp, fp, u64p]
+    L.uivr_oracle_render_forward.restype = C.c_int
+    L.uivr_oracle_render_backward.argtypes = [C.POINTER(_Scene), fp, fp, fp, C.c_uint32, C.c_int32,
+                                              C.POINTER(_Shard), C.c_int, dp, dp, fp, u64p]
+    L.uivr_oracle_render_backward.restype = C.c_int
+    L.uivr_oracle_alt_seed.argtypes = [C.c_uint32]
+    L.uivr_oracle_alt_seed.restype = C.c_uint32
+    _lib = L
+    return L
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _ptr(a: Optional[np.ndarray], t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def make_scene(desc: Dict, props: Dict) -> _Scene:
+    """desc: VolumeScene.as_dict(); props: integrator properties (volpathsimple.py:19-34)."""
+    s = _Scene()
+    s.res[:] = [int(v) for v in desc["res"]]
+    s.to_local[:] = [float(v) for v in np.asarray(desc["to_local"]).reshape(-1)]
+    s.scale = float(desc["scale"])
+    s.majorant_factor = int(desc["majorant_factor"])
+    for k in ("cam_origin", "cam_left", "cam_up", "cam_dir", "radiance"):
+        getattr(s, k)[:] = [float(v) for v in desc[k]]
+    s.tan_x, s.tan_y, s.near_clip = float(desc["tan_x"]), float(desc["tan_y"]), float(desc["near_clip"])
+    s.width, s.height = int(desc["width"]), int(desc["height"])
+    s.max_depth = int(props["max_depth"])
+    s.hide_emitters = int(bool(props.get("hide_emitters", False)))
+    s.use_nee = int(bool(props.get("use_nee", True)))
+    s.use_drt = int(bool(props.get("use_drt", True)))
+    s.use_drt_subsampling = int(bool(props.get("use_drt_subsampling", True)))
+    s.use_drt_mis = int(bool(props.get("use_drt_mis", True)))
+    return s
+
+
+def _shard(shard):
+    if shard is None:
+        return None
+    s = _Shard()
+    s.shard_rank, s.shard_count, s.shard_block = (int(v) for v in shard)
+    return C.byref(s)
+
+
+def _check_grids(desc, sigma_t, albedo):
+    x, y, z = desc["res"]
+    sigma_t = _f32(sigma_t).reshape(z, y, x)
+    albedo = _f32(albedo).reshape(z, y, x, 3)
+    return sigma_t, albedo
+
+
+def render_forward(desc, props, sigma_t, albedo, seed: int, spp: int, shard=None,
+                   nthreads: Optional[int] = None, want_samples: bool = False):
+    """-> (image (H,W,3) f32, per-sample L (S,3) or None, counters dict)."""
+    L = lib()
+    sc = make_scene(desc, props)
+    sigma_t, albedo = _check_grids(desc, sigma_t, albedo)
+    h, w = sc.height, sc.width
+    image = np.zeros((h, w, 3), dtype=np.float32)
+    samples = np.zeros((h * w * spp, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = L.uivr_oracle_render_forward(C.byref(sc), _ptr(sigma_t, C.c_float), _ptr(albedo, C.c_float),
+                                      seed & 0xFFFFFFFF, spp, _shard(shard),
+                                      nthreads or os.cpu_count() or 1,
+                                      _ptr(image, C.c_float), _ptr(samples, C.c_float),
+                                      _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_render_forward failed ({rc})")
+    return image, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def render_backward(desc, props, sigma_t, albedo, grad_image, seed_grad: int, spp_grad: int,
+                    shard=None, nthreads: Optional[int] = None, want_samples: bool = False):
+    """-> (d sigma_t (Z,Y,X,1) f64, d albedo (Z,Y,X,3) f64, per-sample primal L or None, counters)."""
+    L = lib()
+    sc = make_scene(desc, props)
+    sigma_t, albedo = _check_grids(desc, sigma_t, albedo)
+    x, y, z = desc["res"]
+    h, w = sc.height, sc.width
+    grad_image = _f32(grad_image).reshape(h, w, 3)
+    dsig = np.zeros((z, y, x, 1), dtype=np.float64)
+    dalb = np.zeros((z, y, x, 3), dtype=np.float64)
+    samples = np.zeros((h * w * spp_grad, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = L.uivr_oracle_render_backward(C.byref(sc), _ptr(sigma_t, C.c_float), _ptr(albedo, C.c_float),
+                                       _ptr(grad_image, C.c_float), seed_grad & 0xFFFFFFFF, spp_grad,
+                                       _shard(shard), nthreads or os.cpu_count() or 1,
+                                       _ptr(dsig, C.c_double), _ptr(dalb, C.c_double),
+                                       _ptr(samples, C.c_float), _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_render_backward failed ({rc})")
+    return dsig, dalb, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+# ---- primitives ----
+
+def tea(v0: int, v1: int):
+    out = (C.c_uint32 * 2)()
+    lib().uivr_oracle_tea(C.c_uint32(v0 & 0xFFFFFFFF), C.c_uint32(v1 & 0xFFFFFFFF), out)
+    return int(out[0]), int(out[1])
+
+
+def pcg32_stream(initstate: int, initseq: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint32)
+    lib().uivr_oracle_pcg32_stream(C.c_uint64(initstate), C.c_uint64(initseq), n, _ptr(out, C.c_uint32))
+    return out
+
+
+def sampler_floats(seed: int, idx: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.float32)
+    lib().uivr_oracle_sampler_floats(C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(idx), n, _ptr(out, C.c_float))
+    return out
+
+
+def neg_log1m(u) -> np.ndarray:
+    u = _f32(u)
+    out = np.zeros_like(u)
+    lib().uivr_oracle_neg_log1m(_ptr(u, C.c_float), u.size, _ptr(out, C.c_float))
+    return out
+
+
+def sincos2pi(x):
+    x = _f32(x)
+    s, c = np.zeros_like(x), np.zeros_like(x)
+    lib().uivr_oracle_sincos2pi(_ptr(x, C.c_float), x.size, _ptr(s, C.c_float), _ptr(c, C.c_float))
+    return s, c
+
+
+def alt_seed(seed_grad: int) -> int:
+    return int(lib().uivr_oracle_alt_seed(seed_grad & 0xFFFFFFFF))
+
+
+def trilinear(grid, p) -> np.ndarray:
+    grid = _f32(grid)
+    z, y, x, ch = grid.shape
+    p = _f32(p).reshape(-1, 3)
+    out = np.zeros((p.shape[0], ch), dtype=np.float32)
+    res = (C.c_int32 * 3)(x, y, z)
+    lib().uivr_oracle_trilinear(_ptr(grid, C.c_float), res, ch, _ptr(p, C.c_float), p.shape[0], _ptr(out, C.c_float))
+    return out
+
+
+def build_majorant(sigma_t, scale: float, factor: int) -> np.ndarray:
+    sigma_t = _f32(sigma_t)
+    z, y, x = sigma_t.shape[:3]
+    res = (C.c_int32 * 3)(x, y, z)
+    mres = (C.c_int32 * 3)()
+    m = [max(1, r // factor) if factor > 1 else 1 for r in (x, y, z)]
+    out = np.zeros((m[2], m[1], m[0]), dtype=np.float32)
+    lib().uivr_oracle_build_majorant(_ptr(sigma_t, C.c_float), res, C.c_float(scale), factor, mres, _ptr(out, C.c_float))
+    assert list(mres) == m
+    return out

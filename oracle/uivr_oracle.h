@@ -1,0 +1,106 @@
+/*
+ * uivr_oracle.h -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * Plain-C restatement of the hot path of rgl-epfl/unbiased-inverse-volume-rendering:
+ * the `volpathsimple` integrator (python/integrators/volpathsimple.py) driven the way
+ * RBIntegrator.render / render_backward drive it (restated in python/batched.py:134-326).
+ *
+ * PARITY UNPINNED at the third-party boundary: the arithmetic of the path (Medium::
+ * sample_interaction, GridVolume lookup, PCG32 sampler, perspective sensor ...) lives in an
+ * un-vendored, un-pinned Mitsuba 3 branch + Dr.Jit (README.md:97-104) which cannot be
+ * imported or built here, and the reference's own tests hold no golden vectors for this
+ * path (tests/test_integrators.py:343-347 is disabled).  This oracle therefore follows the
+ * reference's control flow line by line (citations at each function) and DEFINES the
+ * upstream arithmetic itself (DESIGN.md "Arithmetic contract").  It is pinned by:
+ * PCG32 public known-answer vectors, analytic known answers (KA1-KA3) and finite
+ * differences (KA4, the reference's own methodology, python/fd.py) -- see tests/.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (csrc/) never links or calls it.
+ */
+#ifndef UIVR_ORACLE_H
+#define UIVR_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Scene + integrator description (all host memory). */
+typedef struct {
+    int32_t res[3];          /* grid resolution X, Y, Z; tensors are (Z,Y,X,C), x fastest     */
+    float   to_local[12];    /* world->local affine, row-major 3x4; medium = local [0,1]^3    */
+    float   scale;           /* medium 'scale' (tests/test_integrators.py:83)                 */
+    int32_t majorant_factor; /* supergrid resolution factor; <=1 -> one global majorant       */
+    float   cam_origin[3];   /* perspective sensor (tests/test_integrators.py:46-53)          */
+    float   cam_left[3];
+    float   cam_up[3];
+    float   cam_dir[3];
+    float   tan_x, tan_y;    /* tan(fov_x/2), tan_x*H/W                                       */
+    float   near_clip;
+    int32_t width, height;   /* box-filter hdrfilm                                            */
+    float   radiance[3];     /* constant emitter (tests/test_integrators.py:73-77)            */
+    int32_t max_depth;       /* integrator props (volpathsimple.py:19-34)                     */
+    int32_t hide_emitters;
+    int32_t use_nee;
+    int32_t use_drt;
+    int32_t use_drt_subsampling;
+    int32_t use_drt_mis;
+} uivr_oracle_scene;
+
+/* Pixel sharding: pixel p belongs to this call iff (p / shard_block) % shard_count == shard_rank. */
+typedef struct {
+    int32_t shard_rank, shard_count, shard_block;
+} uivr_oracle_shard;
+
+enum {
+    UIVR_ORC_SIGMA_TAPS = 0,   /* trilinear sigma_t lookups (8 voxels each)          */
+    UIVR_ORC_ALBEDO_TAPS,      /* trilinear albedo lookups (8 voxels x 3 ch)         */
+    UIVR_ORC_MAJORANT_READS,   /* supergrid cell reads                               */
+    UIVR_ORC_SIGMA_SCATTERS,   /* gradient scatter events into d sigma_t (8 voxels)  */
+    UIVR_ORC_ALBEDO_SCATTERS,  /* gradient scatter events into d albedo (8 x 3)      */
+    UIVR_ORC_CAMERA_HITS,      /* primary rays entering the medium                   */
+    UIVR_ORC_REAL_COLLISIONS,  /* real scattering events (all path kinds)            */
+    UIVR_ORC_RNG_DRAWS,        /* PCG32 outputs consumed (primary + alt streams)     */
+    UIVR_ORC_SAMPLES,          /* samples processed                                  */
+    UIVR_ORC_NUM_COUNTERS
+};
+
+/* ---- primitives (KA5 + bitwise GPU-vs-oracle checks) ---- */
+void  uivr_oracle_tea(uint32_t v0, uint32_t v1, uint32_t out[2]);
+void  uivr_oracle_pcg32_stream(uint64_t initstate, uint64_t initseq, int n, uint32_t* out);
+void  uivr_oracle_sampler_floats(uint32_t seed, uint32_t idx, int n, float* out);
+void  uivr_oracle_neg_log1m(const float* u, int n, float* out);
+void  uivr_oracle_sincos2pi(const float* x, int n, float* s, float* c);
+uint32_t uivr_oracle_alt_seed(uint32_t seed_grad);
+/* trilinear lookup at local points p (n x 3); grid (Z,Y,X,C) */
+void  uivr_oracle_trilinear(const float* grid, const int32_t res[3], int channels,
+                            const float* p, int n, float* out);
+
+/* supergrid of local majorants; out has M[0]*M[1]*M[2] floats, M written to mres */
+void  uivr_oracle_build_majorant(const float* sigma_t, const int32_t res[3], float scale,
+                                 int32_t factor, int32_t mres[3], float* out);
+
+/* ---- the path ---- */
+/* image_out: H*W*3 (overwritten; pixels outside the shard are zero).
+ * sample_L_out: optional (NULL) S*3 per-sample radiance, S = W*H*spp.
+ * counters: optional, UIVR_ORC_NUM_COUNTERS uint64 (accumulated into). */
+int uivr_oracle_render_forward(const uivr_oracle_scene* scene, const float* sigma_t,
+                               const float* albedo, uint32_t seed, int32_t spp,
+                               const uivr_oracle_shard* shard, int nthreads,
+                               float* image_out, float* sample_L_out, uint64_t* counters);
+
+/* grad_image: H*W*3.  dsigma_out: Z*Y*X doubles, dalbedo_out: Z*Y*X*3 doubles (overwritten).
+ * sample_L_out: optional per-sample primal radiance of the seed_grad pass. */
+int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sigma_t,
+                                const float* albedo, const float* grad_image,
+                                uint32_t seed_grad, int32_t spp_grad,
+                                const uivr_oracle_shard* shard, int nthreads,
+                                double* dsigma_out, double* dalbedo_out,
+                                float* sample_L_out, uint64_t* counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,31 @@
+"""Test configuration.
+
+`-m "not gpu"`: oracle vs known answers / golden vectors, host logic, C-ABI symbol exports.
+`-m gpu`: parity of the CUDA path (through the C-ABI) against the oracle on a real B200.
+"""
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def uivr():
+    """The product package (directory name carries a hyphen, hence importlib)."""
+    return importlib.import_module("uivr_b200")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.build()
+    return O

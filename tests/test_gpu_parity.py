@@ -1,0 +1,329 @@
+"""GPU parity: the CUDA path (through the C-ABI) vs the CPU oracle at matched RNG seeds.
+
+Bars: per-sample radiance and event counters BIT-EXACT (every branch decision of every path is
+identical); image L-inf < 1e-5; gradient relative L-inf < 1e-3 (north_star tolerance; only the
+atomic summation order differs, observed ~1e-6).
+"""
+import numpy as np
+import pytest
+
+from helpers import FLAG_COMBOS, hetero_grids, loss_grad, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+IMAGE_TOL = 1e-5
+GRAD_TOL = 1e-3  # north_star: gradient L-inf < 1e-3 (relative to max |g_ref|)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _run_forward(uivr, vol, props, sig, alb, seed, spp, dev, variant, shard=None, counting=True):
+    scene = uivr.Scene(vol, device=0)
+    scene.ctx.set_variant(variant)
+    scene.ctx.set_counting(counting)
+    scene.ctx.reset_counters()
+    integ = uivr.VolpathSimpleIntegrator(props)
+    params = {"m.sigma_t.data": _gpu(sig, dev), "m.albedo.data": _gpu(alb, dev)}
+    d = vol.as_dict()
+    samples = torch.zeros((d["width"] * d["height"] * spp, 3), device=dev)
+    img = integ.render(scene, params, seed=seed, spp=spp, shard=shard, sample_out=samples)
+    torch.cuda.synchronize()
+    cnt = scene.ctx.get_counters() if counting else None
+    return img.cpu().numpy(), samples.cpu().numpy(), cnt
+
+
+def _run_backward(uivr, vol, props, sig, alb, gimg, seed, spp, dev, variant, shard=None, counting=True):
+    scene = uivr.Scene(vol, device=0)
+    scene.ctx.set_variant(variant)
+    scene.ctx.set_counting(counting)
+    scene.ctx.reset_counters()
+    integ = uivr.VolpathSimpleIntegrator(props)
+    params = {"m.sigma_t.data": _gpu(sig, dev), "m.albedo.data": _gpu(alb, dev)}
+    d = vol.as_dict()
+    samples = torch.zeros((d["width"] * d["height"] * spp, 3), device=dev)
+    ds, da = integ.render_backward(scene, params, _gpu(gimg, dev), seed=seed, spp=spp, shard=shard,
+                                   sample_out=samples)
+    torch.cuda.synchronize()
+    cnt = scene.ctx.get_counters() if counting else None
+    return ds.cpu().numpy(), da.cpu().numpy(), samples.cpu().numpy(), cnt
+
+
+VARIANTS = [1]
+
+
+# ---------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------
+
+def test_primitives_bit_exact(uivr, oracle, dev):
+    ctx = uivr._native.Context(0)
+    rng = np.random.default_rng(0)
+    u = (rng.integers(0, 1 << 23, size=1 << 20).astype(np.float32) / np.float32(1 << 23))
+    u[:4] = [0.0, 1.0 - 2.0 ** -23, 0.5, 2.0 ** -23]
+    du = _gpu(u, dev)
+    out = torch.empty_like(du)
+    ctx.test_neg_log1m(du.data_ptr(), u.size, out.data_ptr())
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), oracle.neg_log1m(u).view(np.uint32))
+    s, c = torch.empty_like(du), torch.empty_like(du)
+    ctx.test_sincos2pi(du.data_ptr(), u.size, s.data_ptr(), c.data_ptr())
+    so, co = oracle.sincos2pi(u)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), so.view(np.uint32))
+    assert np.array_equal(c.cpu().numpy().view(np.uint32), co.view(np.uint32))
+    # sampler streams (TEA + PCG32 + u32->float)
+    fl = torch.empty((64, 16), device=dev)
+    ctx.test_sampler(1234, 1000, 64, 16, fl.data_ptr())
+    ref = np.stack([oracle.sampler_floats(1234, 1000 + i, 16) for i in range(64)])
+    assert np.array_equal(fl.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    assert uivr._native.lib().uivr_alt_seed(0x38fc4d3a) == oracle.alt_seed(0x38fc4d3a)
+
+
+@pytest.mark.parametrize("n,factor", [(3, 0), (16, 4), (33, 8), (32, 8)])
+def test_lookup_and_majorant_bit_exact(uivr, oracle, dev, n, factor):
+    sig, alb = hetero_grids(n, seed=n)
+    vol = uivr.cube_test_scene(8, 8, density_scale=3.0, res=(n, n, n))
+    vol.majorant_resolution_factor = factor
+    scene = uivr.Scene(vol, device=0)
+    scene.bind(None, dict(max_depth=4))
+    dsig = _gpu(sig, dev)
+    scene.update_medium(dsig)
+    rng = np.random.default_rng(1)
+    p = rng.random((20000, 3)).astype(np.float32)
+    p[:64] = rng.integers(0, 2, size=(64, 3)).astype(np.float32)  # corners / faces
+    p[64:96] = p[64:96] * 1.2 - 0.1                                # some outside
+    dp = _gpu(p, dev)
+    out = torch.empty(p.shape[0], device=dev)
+    scene.ctx.test_sigma_lookup(dp.data_ptr(), p.shape[0], out.data_ptr())
+    ref = (np.float32(3.0) * oracle.trilinear(sig, p)[:, 0]).astype(np.float32)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    f = vol.effective_majorant_factor()
+    mref = oracle.build_majorant(sig, 3.0, f)
+    mres = scene.ctx.get_majorant()
+    dm = torch.empty(int(np.prod(mres)), device=dev)
+    scene.ctx.get_majorant(dm.data_ptr())
+    assert tuple(mref.shape[::-1]) == mres
+    assert np.array_equal(dm.cpu().numpy().view(np.uint32), mref.reshape(-1).view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------
+# forward
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_forward_config1_homogeneous(uivr, oracle, dev, variant):
+    """BASELINE.json configs[0]: 64^3 homogeneous, 128x128x4 spp."""
+    n = 64
+    sig = np.ones((n, n, n, 1), np.float32)
+    alb = np.full((n, n, n, 3), 0.8, np.float32)
+    vol = uivr.cube_test_scene(128, 128, density_scale=2.0, res=(n, n, n))
+    props = dict(max_depth=64)
+    img_o, smp_o, cnt_o = oracle.render_forward(vol.as_dict(), props, sig, alb, 1234, 4, want_samples=True)
+    img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, 1234, 4, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert np.max(np.abs(img_g - img_o)) < IMAGE_TOL
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,factor,spp", [(24, 0, 8), (32, 8, 8), (40, 4, 5)])
+def test_forward_heterogeneous(uivr, oracle, dev, variant, n, factor, spp):
+    sig, alb = hetero_grids(n)
+    vol = uivr.benchmark_scene(n, 96, 64, scale=8.0, majorant_resolution_factor=factor)
+    props = dict(max_depth=64)
+    img_o, smp_o, cnt_o = oracle.render_forward(vol.as_dict(), props, sig, alb, 99, spp, want_samples=True)
+    img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, 99, spp, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert np.max(np.abs(img_g - img_o)) < IMAGE_TOL
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("props", [dict(max_depth=0), dict(max_depth=1), dict(max_depth=3, use_nee=False),
+                                   dict(max_depth=5, hide_emitters=True)])
+def test_forward_prop_edge_cases(uivr, oracle, dev, variant, props):
+    sig, alb = uivr.cube_test_grids()
+    vol = uivr.cube_test_scene(48, 48, density_scale=2.0)
+    img_o, smp_o, cnt_o = oracle.render_forward(vol.as_dict(), props, sig, alb, 5, 16, want_samples=True)
+    img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, 5, 16, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_forward_empty_and_opaque_media(uivr, oracle, dev, variant):
+    vol = uivr.benchmark_scene(8, 32, 32, scale=50.0, majorant_resolution_factor=2)
+    props = dict(max_depth=8)
+    for fill in (0.0, 1.0):
+        sig = np.full((8, 8, 8, 1), fill, np.float32)
+        alb = np.full((8, 8, 8, 3), 0.5, np.float32)
+        alb[..., 1] = 0.0  # zero albedo channel (throughput partially zero)
+        img_o, smp_o, cnt_o = oracle.render_forward(vol.as_dict(), props, sig, alb, 3, 4, want_samples=True)
+        img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, 3, 4, dev, variant)
+        assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+        assert cnt_g == cnt_o
+
+
+# ---------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("combo", sorted(FLAG_COMBOS))
+def test_backward_fixture_all_flag_combos(uivr, oracle, dev, variant, combo):
+    """3^3 fixture of tests/test_integrators.py:19-116, density_scale=2 (tests:265)."""
+    sig, alb = uivr.cube_test_grids()
+    vol = uivr.cube_test_scene(40, 40, density_scale=2.0)
+    props = dict(max_depth=64, **FLAG_COMBOS[combo])
+    spp = 16
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 1234, spp)
+    gimg = loss_grad(img)
+    sg = uivr.tea32(1234, 1)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, spp, want_samples=True)
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, sg, spp, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,factor", [(16, 0), (32, 8)])
+def test_backward_heterogeneous(uivr, oracle, dev, variant, n, factor):
+    sig, alb = hetero_grids(n)
+    vol = uivr.benchmark_scene(n, 64, 48, scale=8.0, majorant_resolution_factor=factor)
+    props = dict(max_depth=64)
+    spp = 8
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 77, spp)
+    gimg = loss_grad(img)
+    sg = uivr.tea32(77, 1)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, spp, want_samples=True)
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, sg, spp, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_backward_config1_homogeneous(uivr, oracle, dev, variant):
+    """BASELINE.json configs[0] verbatim: 64^3 homogeneous, 128x128x4 spp, DRT fwd+bwd."""
+    n = 64
+    sig = np.ones((n, n, n, 1), np.float32)
+    alb = np.full((n, n, n, 3), 0.8, np.float32)
+    vol = uivr.cube_test_scene(128, 128, density_scale=2.0, res=(n, n, n))
+    props = dict(max_depth=64)
+    img_o, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 1234, 4)
+    gimg = loss_grad(img_o)
+    sg = uivr.tea32(1234, 1)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, 4, want_samples=True)
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, sg, 4, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------
+# sharding, autograd plumbing, host entry points, errors
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_pixel_sharding_is_invariant(uivr, oracle, dev, variant):
+    sig, alb = hetero_grids(16)
+    vol = uivr.benchmark_scene(16, 50, 30, scale=6.0, majorant_resolution_factor=4)
+    props = dict(max_depth=32)
+    img_full, smp_full, _ = _run_forward(uivr, vol, props, sig, alb, 11, 6, dev, variant, counting=False)
+    acc = np.zeros_like(img_full)
+    smp = np.zeros_like(smp_full)
+    for r in range(3):
+        img_r, smp_r, _ = _run_forward(uivr, vol, props, sig, alb, 11, 6, dev, variant, shard=(r, 3, 64), counting=False)
+        img_or, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 11, 6, shard=(r, 3, 64))
+        assert np.max(np.abs(img_r - img_or)) < IMAGE_TOL
+        acc += img_r
+        smp += smp_r
+    assert np.array_equal(smp.view(np.uint32), smp_full.view(np.uint32))
+    assert np.max(np.abs(acc - img_full)) < IMAGE_TOL
+    gimg = loss_grad(img_full)
+    ds_full, da_full, _, _ = _run_backward(uivr, vol, props, sig, alb, gimg, 12, 6, dev, variant, counting=False)
+    ds_acc, da_acc = np.zeros_like(ds_full), np.zeros_like(da_full)
+    for r in range(3):
+        ds_r, da_r, _, _ = _run_backward(uivr, vol, props, sig, alb, gimg, 12, 6, dev, variant, shard=(r, 3, 64), counting=False)
+        ds_acc += ds_r
+        da_acc += da_r
+    assert rel_linf(ds_acc, ds_full) < 1e-4
+    assert rel_linf(da_acc, da_full) < 1e-4
+
+
+def test_autograd_render_matches_oracle(uivr, oracle, dev):
+    """mi.render + dr.backward flow of optimize.py:345-350 through torch autograd."""
+    sig, alb = uivr.cube_test_grids()
+    vol = uivr.cube_test_scene(32, 32, density_scale=2.0)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.get_int_config("volpathsimple-drt").create(max_depth=64)
+    p_sig = _gpu(sig, dev).requires_grad_(True)
+    p_alb = _gpu(alb, dev).requires_grad_(True)
+    params = {"cube.interior_medium.sigma_t.data": p_sig, "cube.interior_medium.albedo.data": p_alb}
+    img = uivr.render(scene, params, integ, spp=32, seed=1234)
+    loss = torch.mean((img - 0.5) ** 2)
+    loss.backward()
+    props = integ.props()
+    img_o, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 1234, 32)
+    assert np.max(np.abs(img.detach().cpu().numpy() - img_o)) < IMAGE_TOL
+    ds_o, da_o, _, _ = oracle.render_backward(vol.as_dict(), props, sig, alb, loss_grad(img_o),
+                                              uivr.tea32(1234, 1), 32)
+    assert rel_linf(p_sig.grad.cpu().numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(p_alb.grad.cpu().numpy(), da_o) < GRAD_TOL
+    with pytest.raises(Exception, match="primal and differential seed"):
+        uivr.render(scene, params, integ, spp=4, seed=7, seed_grad=7)
+
+
+def test_host_entry_points(uivr, oracle, dev):
+    sig, alb = hetero_grids(12)
+    vol = uivr.benchmark_scene(12, 40, 24, scale=5.0, majorant_resolution_factor=0)
+    props = dict(max_depth=16)
+    scene = uivr.Scene(vol, device=0)
+    scene.bind(None, props)
+    h_sig = torch.from_numpy(sig).pin_memory()
+    h_alb = torch.from_numpy(alb).pin_memory()
+    h_img = torch.empty((24, 40, 3)).pin_memory()
+    scene.ctx.render_forward_host(h_sig.data_ptr(), h_alb.data_ptr(), 21, 8, h_img.data_ptr())
+    img_o, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 21, 8)
+    assert np.max(np.abs(h_img.numpy() - img_o)) < IMAGE_TOL
+    gimg = loss_grad(img_o)
+    h_g = torch.from_numpy(gimg).pin_memory()
+    h_ds, h_da = torch.empty_like(h_sig).pin_memory(), torch.empty_like(h_alb).pin_memory()
+    scene.ctx.render_backward_host(h_sig.data_ptr(), h_alb.data_ptr(), h_g.data_ptr(), 22, 8,
+                                   h_ds.data_ptr(), h_da.data_ptr())
+    ds_o, da_o, _, _ = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 22, 8)
+    assert rel_linf(h_ds.numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(h_da.numpy(), da_o) < GRAD_TOL
+
+
+def test_error_behaviour(uivr, dev):
+    vol = uivr.cube_test_scene(8, 8)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.VolpathSimpleIntegrator(dict(max_depth=4))
+    sig, alb = uivr.cube_test_grids()
+    good = {"m.sigma_t.data": _gpu(sig, dev), "m.albedo.data": _gpu(alb, dev)}
+    with pytest.raises(ValueError):
+        integ.render(scene, {"m.sigma_t.data": _gpu(sig[:2], dev), "m.albedo.data": good["m.albedo.data"]}, spp=1)
+    with pytest.raises(ValueError):
+        integ.render(scene, {"m.sigma_t.data": good["m.sigma_t.data"]}, spp=1)
+    with pytest.raises(Exception):
+        integ.render(scene, good, spp=1, develop=False)
+    ctx = uivr._native.Context(0)
+    with pytest.raises(uivr.NativeError, match="uivr_set_scene"):
+        ctx.update_medium(good["m.sigma_t.data"].data_ptr())
+    big = uivr.cube_test_scene(8192, 8192)
+    scene2 = uivr.Scene(big, device=0)
+    with pytest.raises(uivr.NativeError, match="wavefront too large"):
+        integ.render(scene2, good, spp=128)

@@ -1,0 +1,16 @@
+"""B200-native differential volumetric path tracer behind the reference's IntegratorConfig /
+integrator-plugin surface (hot path of rgl-epfl/unbiased-inverse-volume-rendering)."""
+from . import _native
+from ._native import NativeError, tea32
+from .integrator import (INTEGRATORS, Scene, VolpathSimpleIntegrator, load_dict,
+                         register_integrator, render)
+from .opt_config import IntegratorConfig, add_int_config, get_int_config
+from .scene import (Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_test_grids,
+                    cube_test_scene, look_at, synthetic_grids)
+
+__all__ = [
+    "NativeError", "tea32", "INTEGRATORS", "Scene", "VolpathSimpleIntegrator", "load_dict",
+    "register_integrator", "render", "IntegratorConfig", "add_int_config", "get_int_config",
+    "Sensor", "VolumeScene", "benchmark_scene", "circle_sensors", "cube_test_grids",
+    "cube_test_scene", "look_at", "synthetic_grids",
+]

@@ -1,0 +1,473 @@
+// uivr_api.cu -- C-ABI of libuivr.so (see include/uivr.h).  Host side: context, launch
+// configuration, derived-layout management.  No torch types, no exceptions across the ABI.
+#include "../../include/uivr.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "uivr_kernels.cuh"
+#include "uivr_mega.cuh"
+
+using namespace uivr;
+
+struct uivr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    bool have_scene = false, have_props = false, have_medium = false;
+    uivr_scene_desc scene{};
+    uivr_integrator_props props{};
+    int mres[3] = {1, 1, 1};
+    float4* oct = nullptr;
+    size_t oct_cells = 0;
+    float* maj = nullptr;
+    size_t maj_cells = 0;
+    unsigned long long* counters = nullptr;
+    unsigned int* work_counter = nullptr;
+    int variant = 1;
+    int counting = 0;
+    uint64_t launches = 0;
+    // staging for the *_host entry points
+    float* st_sigma = nullptr;
+    float* st_albedo = nullptr;
+    float* st_image = nullptr;
+    float* st_gimage = nullptr;
+    float* st_dsigma = nullptr;
+    float* st_dalbedo = nullptr;
+    size_t st_vox = 0, st_pix = 0;
+};
+
+namespace {
+
+int fail(uivr_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define UIVR_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(ctx, UIVR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int check_ready(uivr_ctx* ctx) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    if (!ctx->have_props) return fail(ctx, UIVR_ERR_STATE, "uivr_set_integrator has not been called");
+    if (!ctx->have_medium) return fail(ctx, UIVR_ERR_STATE, "uivr_update_medium has not been called");
+    return UIVR_OK;
+}
+
+int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed, int32_t spp) {
+    const uivr_scene_desc& s = ctx->scene;
+    const uivr_integrator_props& ip = ctx->props;
+    if (spp < 1) return fail(ctx, UIVR_ERR_INVALID, "spp must be >= 1");
+    const uint64_t npix = (uint64_t) s.width * (uint64_t) s.height;
+    if (npix * (uint64_t) spp >= (1ull << 32))
+        return fail(ctx, UIVR_ERR_INVALID, "wavefront too large: W*H*spp must be < 2^32 (batched.py:378-388)");
+    memset(&P, 0, sizeof(P));
+    for (int a = 0; a < 3; ++a) {
+        P.res[a] = s.res[a];
+        P.ores[a] = s.res[a] + 1;
+        P.fres[a] = (float) s.res[a];
+        P.mres[a] = ctx->mres[a];
+        P.fmres[a] = (float) ctx->mres[a];
+        P.mcs[a] = 1.0f / (float) ctx->mres[a];
+        P.cam_origin[a] = s.cam_origin[a];
+        P.cam_left[a] = s.cam_left[a];
+        P.cam_up[a] = s.cam_up[a];
+        P.cam_dir[a] = s.cam_dir[a];
+        P.radiance[a] = s.radiance[a];
+        P.half_le[a] = 0.5f * s.radiance[a];
+    }
+    memcpy(P.to_local, s.to_local, sizeof(P.to_local));
+    P.oct = ctx->oct;
+    P.maj = ctx->maj;
+    P.scale = s.scale;
+    P.tan_x = s.tan_x;
+    P.tan_y = s.tan_y;
+    P.near_clip = s.near_clip;
+    P.width = s.width;
+    P.height = s.height;
+    P.inv_w = 1.0f / (float) s.width;
+    P.inv_h = 1.0f / (float) s.height;
+    P.max_depth = ip.max_depth;
+    P.hide_emitters = ip.hide_emitters;
+    P.use_nee = ip.use_nee;
+    P.use_drt = ip.use_drt;
+    P.use_drt_subsampling = ip.use_drt_subsampling;
+    P.use_drt_mis = ip.use_drt_mis;
+    P.seed = seed;
+    P.spp = (uint32_t) spp;
+    P.inv_spp = 1.0f / (float) spp;
+    P.npix = (uint32_t) npix;
+    if (shard && shard->count > 1) {
+        if (shard->rank < 0 || shard->rank >= shard->count || shard->block < 1)
+            return fail(ctx, UIVR_ERR_INVALID, "invalid shard (need 0 <= rank < count, block >= 1)");
+        P.shard_rank = shard->rank;
+        P.shard_count = shard->count;
+        P.shard_block = shard->block;
+        const uint64_t nblocks = (npix + shard->block - 1) / shard->block;
+        const uint64_t mine = nblocks > (uint64_t) shard->rank
+                                  ? (nblocks - shard->rank + shard->count - 1) / shard->count : 0;
+        P.n_slots = (uint32_t) (mine * shard->block);
+    } else {
+        P.shard_rank = 0;
+        P.shard_count = 1;
+        P.shard_block = 1;
+        P.n_slots = (uint32_t) npix;
+    }
+    P.counters = ctx->counters;
+    P.work_counter = ctx->work_counter;
+    return UIVR_OK;
+}
+
+template <typename K>
+int persistent_grid(uivr_ctx* ctx, K kernel, int block, int* grid) {
+    int per_sm = 0;
+    UIVR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    if (per_sm < 1) per_sm = 1;
+    *grid = ctx->num_sms * per_sm;
+    return UIVR_OK;
+}
+
+int ensure_staging(uivr_ctx* ctx) {
+    const uivr_scene_desc& s = ctx->scene;
+    const size_t vox = (size_t) s.res[0] * s.res[1] * s.res[2];
+    const size_t pix = (size_t) s.width * s.height;
+    if (vox != ctx->st_vox) {
+        cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
+        ctx->st_sigma = ctx->st_albedo = ctx->st_dsigma = ctx->st_dalbedo = nullptr;
+        ctx->st_vox = 0;
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_sigma, vox * sizeof(float)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_albedo, vox * 3 * sizeof(float)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_dsigma, vox * sizeof(float)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_dalbedo, vox * 3 * sizeof(float)));
+        ctx->st_vox = vox;
+    }
+    if (pix != ctx->st_pix) {
+        cudaFree(ctx->st_image); cudaFree(ctx->st_gimage);
+        ctx->st_image = ctx->st_gimage = nullptr;
+        ctx->st_pix = 0;
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_image, pix * 3 * sizeof(float)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->st_gimage, pix * 3 * sizeof(float)));
+        ctx->st_pix = pix;
+    }
+    return UIVR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uivr_version(void) { return 100; }
+
+int uivr_create(int device, uivr_ctx** out) {
+    if (!out) return UIVR_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return UIVR_ERR_CUDA;
+    uivr_ctx* ctx = new (std::nothrow) uivr_ctx();
+    if (!ctx) return UIVR_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaMalloc(&ctx->counters, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess ||
+        cudaMalloc(&ctx->work_counter, sizeof(unsigned int) * 4) != cudaSuccess ||
+        cudaMemset(ctx->counters, 0, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess) {
+        delete ctx;
+        return UIVR_ERR_CUDA;
+    }
+    *out = ctx;
+    return UIVR_OK;
+}
+
+int uivr_destroy(uivr_ctx* ctx) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter);
+    cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
+    cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
+    delete ctx;
+    return UIVR_OK;
+}
+
+const char* uivr_last_error(const uivr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int uivr_set_scene(uivr_ctx* ctx, const uivr_scene_desc* scene) {
+    if (!ctx || !scene) return UIVR_ERR_INVALID;
+    for (int a = 0; a < 3; ++a)
+        if (scene->res[a] < 1 || scene->res[a] > 2047)
+            return fail(ctx, UIVR_ERR_INVALID, "grid resolution must be in [1, 2047] per axis");
+    if (scene->width < 1 || scene->height < 1) return fail(ctx, UIVR_ERR_INVALID, "film size must be positive");
+    if (!(scene->scale >= 0.0f)) return fail(ctx, UIVR_ERR_INVALID, "medium scale must be >= 0");
+    const bool res_changed = !ctx->have_scene || memcmp(ctx->scene.res, scene->res, sizeof(scene->res)) != 0 ||
+                             ctx->scene.majorant_factor != scene->majorant_factor ||
+                             ctx->scene.scale != scene->scale;
+    ctx->scene = *scene;
+    ctx->have_scene = true;
+    if (res_changed) ctx->have_medium = false;  // derived layouts are stale
+    return UIVR_OK;
+}
+
+int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props) {
+    if (!ctx || !props) return UIVR_ERR_INVALID;
+    if (props->max_depth < 0) return fail(ctx, UIVR_ERR_INVALID, "max_depth must be >= 0 (opt_config.py:102)");
+    ctx->props = *props;
+    ctx->have_props = true;
+    return UIVR_OK;
+}
+
+int uivr_set_counting(uivr_ctx* ctx, int enable) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    ctx->counting = enable ? 1 : 0;
+    return UIVR_OK;
+}
+
+int uivr_set_variant(uivr_ctx* ctx, int variant) {
+    if (!ctx || variant < 0 || variant > 1) return UIVR_ERR_INVALID;
+    ctx->variant = variant;
+    return UIVR_OK;
+}
+
+int uivr_reset_counters(uivr_ctx* ctx, void* stream) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * UIVR_NUM_COUNTERS, (cudaStream_t) stream));
+    return UIVR_OK;
+}
+
+int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stream) {
+    if (!ctx || !out) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(out, ctx->counters, sizeof(uint64_t) * UIVR_NUM_COUNTERS, cudaMemcpyDeviceToHost,
+                                   (cudaStream_t) stream));
+    UIVR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t) stream));
+    return UIVR_OK;
+}
+
+int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return UIVR_ERR_INVALID;
+    *out = ctx->launches;
+    return UIVR_OK;
+}
+
+int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream) {
+    if (!ctx || !d_sigma_t) return UIVR_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    const uivr_scene_desc& s = ctx->scene;
+    const size_t cells = (size_t) (s.res[0] + 1) * (s.res[1] + 1) * (s.res[2] + 1);
+    if (cells != ctx->oct_cells) {
+        cudaFree(ctx->oct);
+        ctx->oct = nullptr;
+        ctx->oct_cells = 0;
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->oct, cells * 2 * sizeof(float4)));
+        ctx->oct_cells = cells;
+    }
+    for (int a = 0; a < 3; ++a) {
+        ctx->mres[a] = (s.majorant_factor > 1) ? s.res[a] / s.majorant_factor : 1;
+        if (ctx->mres[a] < 1) ctx->mres[a] = 1;
+    }
+    const size_t mcells = (size_t) ctx->mres[0] * ctx->mres[1] * ctx->mres[2];
+    if (mcells != ctx->maj_cells) {
+        cudaFree(ctx->maj);
+        ctx->maj = nullptr;
+        ctx->maj_cells = 0;
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->maj, mcells * sizeof(float)));
+        ctx->maj_cells = mcells;
+    }
+    const int grid = ctx->num_sms * 8;
+    k_build_octets<<<grid, kBlock, 0, st>>>(d_sigma_t, ctx->oct, s.res[0], s.res[1], s.res[2]);
+    k_build_majorant<<<grid, kBlock, 0, st>>>(d_sigma_t, ctx->maj, s.res[0], s.res[1], s.res[2], ctx->mres[0],
+                                               ctx->mres[1], ctx->mres[2], s.scale);
+    ctx->launches += 2;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    ctx->have_medium = true;
+    return UIVR_OK;
+}
+
+int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int32_t spp, const uivr_shard* shard,
+                        float* d_image, float* d_sample_L, void* stream) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!d_albedo || !d_image) return fail(ctx, UIVR_ERR_INVALID, "null device pointer");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    Params P;
+    if ((rc = fill_params(ctx, P, shard, seed, spp))) return rc;
+    P.albedo = d_albedo;
+    P.image = d_image;
+    P.sample_L = d_sample_L;
+    const size_t nimg = (size_t) P.npix * 3;
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_image, 0, nimg * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
+    int grid = 0;
+    if (ctx->variant == 1) {
+        if (ctx->counting) {
+            if ((rc = persistent_grid(ctx, k_forward_v1<true>, kBlock, &grid))) return rc;
+            k_forward_v1<true><<<grid, kBlock, 0, st>>>(P);
+        } else {
+            if ((rc = persistent_grid(ctx, k_forward_v1<false>, kBlock, &grid))) return rc;
+            k_forward_v1<false><<<grid, kBlock, 0, st>>>(P);
+        }
+    } else {
+        if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
+    }
+    k_scale<<<ctx->num_sms * 4, kBlock, 0, st>>>(d_image, nimg, P.inv_spp);
+    ctx->launches += 2;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_grad_image, uint32_t seed_grad,
+                         int32_t spp_grad, const uivr_shard* shard, float* d_dsigma_t, float* d_dalbedo,
+                         float* d_sample_L, void* stream) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!d_albedo || !d_grad_image || !d_dsigma_t || !d_dalbedo) return fail(ctx, UIVR_ERR_INVALID, "null device pointer");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    Params P;
+    if ((rc = fill_params(ctx, P, shard, seed_grad, spp_grad))) return rc;
+    P.alt_seed = uivr_alt_seed(seed_grad);
+    P.albedo = d_albedo;
+    P.grad_image = d_grad_image;
+    P.dsigma = d_dsigma_t;
+    P.dalbedo = d_dalbedo;
+    P.sample_L = d_sample_L;
+    const size_t vox = (size_t) P.res[0] * P.res[1] * P.res[2];
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_dsigma_t, 0, vox * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_dalbedo, 0, vox * 3 * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
+    int grid = 0;
+    if (ctx->variant == 1) {
+        if (ctx->counting) {
+            if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
+            k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);
+        } else {
+            if ((rc = persistent_grid(ctx, k_backward_v1<false>, kBlock, &grid))) return rc;
+            k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
+        }
+    } else {
+        if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
+    }
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo, uint32_t seed, int32_t spp,
+                             const uivr_shard* shard, float* h_image, void* stream) {
+    if (!ctx || !h_sigma_t || !h_albedo || !h_image) return UIVR_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    int rc = ensure_staging(ctx);
+    if (rc) return rc;
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
+    if ((rc = uivr_render_forward(ctx, ctx->st_albedo, seed, spp, shard, ctx->st_image, nullptr, stream))) return rc;
+    UIVR_CUDA(ctx, cudaMemcpyAsync(h_image, ctx->st_image, ctx->st_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    UIVR_CUDA(ctx, cudaStreamSynchronize(st));
+    return UIVR_OK;
+}
+
+int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo, const float* h_grad_image,
+                              uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard, float* h_dsigma_t,
+                              float* h_dalbedo, void* stream) {
+    if (!ctx || !h_sigma_t || !h_albedo || !h_grad_image || !h_dsigma_t || !h_dalbedo) return UIVR_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    int rc = ensure_staging(ctx);
+    if (rc) return rc;
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_gimage, h_grad_image, ctx->st_pix * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
+    if ((rc = uivr_render_backward(ctx, ctx->st_albedo, ctx->st_gimage, seed_grad, spp_grad, shard, ctx->st_dsigma,
+                                   ctx->st_dalbedo, nullptr, stream)))
+        return rc;
+    UIVR_CUDA(ctx, cudaMemcpyAsync(h_dsigma_t, ctx->st_dsigma, ctx->st_vox * sizeof(float), cudaMemcpyDeviceToHost, st));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(h_dalbedo, ctx->st_dalbedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    UIVR_CUDA(ctx, cudaStreamSynchronize(st));
+    return UIVR_OK;
+}
+
+// ---- primitives ----
+
+uint32_t uivr_tea32(uint32_t v0, uint32_t v1) {
+    uint32_t a, b;
+    tea(v0, v1, a, b);
+    return a;
+}
+
+uint32_t uivr_alt_seed(uint32_t seed_grad) {
+    // volpathsimple.py:99-107: bits of lane 0's 4th sampler float, scrambled by TEA(.,1)
+    Rng r;
+    r.seed_sampler(seed_grad, 0);
+    r.next(); r.next(); r.next();
+    const uint32_t x = r.next();
+    union { uint32_t u; float f; } c;
+    c.u = (x >> 9) | 0x3f800000u;
+    c.f = c.f - 1.0f;
+    return uivr_tea32(c.u, 1);
+}
+
+int uivr_test_neg_log1m(uivr_ctx* ctx, const float* d_u, int n, float* d_out, void* stream) {
+    if (!ctx || !d_u || !d_out || n < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n) k_test_neg_log1m<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(d_u, n, d_out);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_test_sincos2pi(uivr_ctx* ctx, const float* d_x, int n, float* d_s, float* d_c, void* stream) {
+    if (!ctx || !d_x || !d_s || !d_c || n < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n) k_test_sincos2pi<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(d_x, n, d_s, d_c);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_test_sampler(uivr_ctx* ctx, uint32_t seed, uint32_t idx0, int nstreams, int ndraws, float* d_out, void* stream) {
+    if (!ctx || !d_out || nstreams < 0 || ndraws < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nstreams) k_test_sampler<<<(nstreams + 255) / 256, 256, 0, (cudaStream_t) stream>>>(seed, idx0, nstreams, ndraws, d_out);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_test_sigma_lookup(uivr_ctx* ctx, const float* d_p, int n, float* d_out, void* stream) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!d_p || !d_out || n < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    Params P;
+    if ((rc = fill_params(ctx, P, nullptr, 0, 1))) return rc;
+    if (n) k_test_sigma_lookup<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(P, d_p, n, d_out);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_get_majorant(uivr_ctx* ctx, int32_t mres[3], float* d_out, void* stream) {
+    if (!ctx || !mres) return UIVR_ERR_INVALID;
+    if (!ctx->have_medium) return fail(ctx, UIVR_ERR_STATE, "uivr_update_medium has not been called");
+    for (int a = 0; a < 3; ++a) mres[a] = ctx->mres[a];
+    if (d_out)
+        UIVR_CUDA(ctx, cudaMemcpyAsync(d_out, ctx->maj, ctx->maj_cells * sizeof(float), cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t) stream));
+    return UIVR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,453 @@
+// uivr_device.cuh -- device-side primitives of the volpathsimple hot path (sm_100a).
+//
+// Arithmetic contract: only IEEE + - * / sqrt, explicit fmaf and integer ops;
+// the translation unit is compiled with -fmad=false so nvcc never fuses a*b+c on its own.
+// The CPU oracle follows the same operation order, which makes every branch decision of a
+// path (collision accept/reject, escape tests, reservoir swaps) reproducible bit for bit.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uivr {
+
+#define UIVR_DEV __device__ __forceinline__
+#define UIVR_INF __int_as_float(0x7f800000)
+#define UIVR_ENTRY_EPS 1e-4f
+
+// --------------------------------------------------------------------------------------
+// Parameters shared by all kernels (passed by value -> constant bank)
+// --------------------------------------------------------------------------------------
+struct Params {
+    // medium
+    int   res[3];            // X, Y, Z
+    int   ores[3];           // octet grid dims = res + 1
+    float fres[3];           // (float) res
+    const float4* __restrict__ oct;     // corner octets: 2 x float4 per cell, ((z*OY+y)*OX+x)
+    const float*  __restrict__ albedo;  // (Z,Y,X,3)
+    const float*  __restrict__ maj;     // supergrid (MZ,MY,MX)
+    int   mres[3];
+    float fmres[3];          // (float) mres
+    float mcs[3];            // 1 / mres
+    float scale;
+    float to_local[12];
+    // sensor / film / emitter
+    float cam_origin[3], cam_left[3], cam_up[3], cam_dir[3];
+    float tan_x, tan_y, near_clip;
+    int   width, height;
+    float inv_w, inv_h;
+    float radiance[3], half_le[3];
+    // integrator
+    int max_depth, hide_emitters, use_nee, use_drt, use_drt_subsampling, use_drt_mis;
+    // launch
+    uint32_t seed, alt_seed, spp;
+    float inv_spp;
+    int shard_rank, shard_count, shard_block;
+    uint32_t npix;            // W*H
+    uint32_t n_slots;         // local pixel slots of this shard
+    // buffers
+    float* image;             // [H,W,3] accumulated sums (forward)
+    float* sample_L;          // optional [S,3]
+    const float* __restrict__ grad_image;
+    float* dsigma;            // [Z,Y,X]
+    float* dalbedo;           // [Z,Y,X,3]
+    unsigned long long* counters;
+    unsigned int* work_counter;
+};
+
+// --------------------------------------------------------------------------------------
+// RNG: TEA + PCG32 `independent` sampler  
+// --------------------------------------------------------------------------------------
+__host__ __device__ inline void tea(uint32_t v0, uint32_t v1, uint32_t& o0, uint32_t& o1) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    o0 = v0;
+    o1 = v1;
+}
+
+struct Rng {
+    uint64_t state, inc;
+
+    __host__ __device__ inline uint32_t next() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dull + inc;
+        uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t) (old >> 59u);
+        return (xs >> rot) | (xs << ((0u - rot) & 31u));
+    }
+    __host__ __device__ inline void seed_stream(uint64_t initstate, uint64_t initseq) {
+        state = 0;
+        inc = (initseq << 1u) | 1u;
+        next();
+        state += initstate;
+        next();
+    }
+    // sampler.seed(seed, wavefront): lane idx gets PCG32(TEA(seed, idx))
+    __host__ __device__ inline void seed_sampler(uint32_t seed, uint32_t idx) {
+        uint32_t v0, v1;
+        tea(seed, idx, v0, v1);
+        seed_stream(v0, v1);
+    }
+    UIVR_DEV float f() { return __uint_as_float((next() >> 9) | 0x3f800000u) - 1.0f; }
+};
+
+// --------------------------------------------------------------------------------------
+// exact-op transcendental replacements (same coefficients / order as the oracle)
+// --------------------------------------------------------------------------------------
+UIVR_DEV float neg_log1m(float u) {
+    float x = 1.0f - u;
+    uint32_t ix = __float_as_uint(x) + (0x3f800000u - 0x3f3504f3u);
+    int e = (int) (ix >> 23) - 127;
+    float f = __uint_as_float((ix & 0x007fffffu) + 0x3f3504f3u) - 1.0f;
+    float q = -0x1.2d9544p-4f;
+    q = fmaf(q, f, 0x1.0276dcp-3f);
+    q = fmaf(q, f, -0x1.0e610cp-3f);
+    q = fmaf(q, f, 0x1.235f0ep-3f);
+    q = fmaf(q, f, -0x1.5467dap-3f);
+    q = fmaf(q, f, 0x1.9998b0p-3f);
+    q = fmaf(q, f, -0x1.00023cp-2f);
+    q = fmaf(q, f, 0x1.555564p-2f);
+    float f2 = f * f;
+    float lm = fmaf(f2 * f, q, fmaf(-0.5f, f2, f));
+    float l = fmaf((float) e, 0x1.62e430p-1f, lm);
+    return -l;
+}
+
+UIVR_DEV void sincos2pi(float x, float& s, float& c) {
+    float y = 4.0f * x;
+    int k = (int) (y + 0.5f);
+    float r = y - (float) k;
+    float z = r * r;
+    float ps = -0x1.2d9b78p-8f;
+    ps = fmaf(ps, z, 0x1.465ec4p-4f);
+    ps = fmaf(ps, z, -0x1.4abbbap-1f);
+    ps = fmaf(ps, z, 0x1.921fb6p+0f);
+    ps = ps * r;
+    float pc = 0x1.d9c322p-11f;
+    pc = fmaf(pc, z, -0x1.55c57ap-6f);
+    pc = fmaf(pc, z, 0x1.03c1dcp-2f);
+    pc = fmaf(pc, z, -0x1.3bd3ccp+0f);
+    pc = fmaf(pc, z, 1.0f);
+    float ss = (k & 1) ? pc : ps;
+    float cc = (k & 1) ? ps : pc;
+    s = (k & 2) ? -ss : ss;
+    c = (((k + 1) & 2) ? -cc : cc);
+}
+
+// warp::square_to_uniform_sphere
+UIVR_DEV void uniform_sphere(float xi1, float xi2, float& wx, float& wy, float& wz) {
+    float z = fmaf(-2.0f, xi2, 1.0f);
+    float r2 = fmaf(-z, z, 1.0f);
+    float r = sqrtf(r2 > 0.0f ? r2 : 0.0f);
+    float s, c;
+    sincos2pi(xi1, s, c);
+    wx = r * c;
+    wy = r * s;
+    wz = z;
+}
+
+UIVR_DEV float lerpf(float a, float b, float w) { return fmaf(w, b - a, a); }
+UIVR_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// --------------------------------------------------------------------------------------
+// event counters (only touched by COUNT template instances)
+// --------------------------------------------------------------------------------------
+enum { C_SIGMA = 0, C_ALBEDO, C_MAJ, C_SSCAT, C_ASCAT, C_HITS, C_REAL, C_DRAWS, C_SAMPLES, C_NUM };
+
+template <bool COUNT>
+struct Counters;
+template <>
+struct Counters<false> {
+    UIVR_DEV void add(int, unsigned) {}
+    UIVR_DEV void flush(unsigned long long*) {}
+};
+template <>
+struct Counters<true> {
+    unsigned v[C_NUM];
+    UIVR_DEV Counters() {
+#pragma unroll
+        for (int i = 0; i < C_NUM; ++i) v[i] = 0;
+    }
+    UIVR_DEV void add(int k, unsigned n) { v[k] += n; }
+    UIVR_DEV void flush(unsigned long long* g) {
+#pragma unroll
+        for (int i = 0; i < C_NUM; ++i) {
+            unsigned s = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&g[i], (unsigned long long) s);
+            v[i] = 0;
+        }
+    }
+};
+
+// RNG wrapper that optionally counts draws
+template <bool COUNT>
+UIVR_DEV float draw(Rng& r, Counters<COUNT>& K) {
+    K.add(C_DRAWS, 1);
+    return r.f();
+}
+
+// --------------------------------------------------------------------------------------
+// grid lookups
+// --------------------------------------------------------------------------------------
+UIVR_DEV bool inside_unit(float x, float y, float z) {
+    return x >= 0.0f && x <= 1.0f && y >= 0.0f && y <= 1.0f && z >= 0.0f && z <= 1.0f;
+}
+
+// sigma_t(p) = scale * trilinear(grid, p) through the corner-octet layout: one 32-byte
+// sector (2 x LDG.128) per tap, border clamping baked into the layout.
+UIVR_DEV float sigma_tap(const Params& P, float px, float py, float pz) {
+    if (!inside_unit(px, py, pz)) return 0.0f;
+    float qx = fmaf(px, P.fres[0], -0.5f), qy = fmaf(py, P.fres[1], -0.5f), qz = fmaf(pz, P.fres[2], -0.5f);
+    float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+    float wx = qx - fx, wy = qy - fy, wz = qz - fz;
+    int ix = (int) fx + 1, iy = (int) fy + 1, iz = (int) fz + 1;
+    size_t cell = ((size_t) iz * P.ores[1] + iy) * P.ores[0] + ix;
+    const float4 a = __ldg(P.oct + 2 * cell);
+    const float4 b = __ldg(P.oct + 2 * cell + 1);
+    float c00 = lerpf(a.x, a.y, wx), c10 = lerpf(a.z, a.w, wx);
+    float c01 = lerpf(b.x, b.y, wx), c11 = lerpf(b.z, b.w, wx);
+    float c0 = lerpf(c00, c10, wy), c1 = lerpf(c01, c11, wy);
+    return P.scale * lerpf(c0, c1, wz);
+}
+
+struct GridCell {
+    int x0, x1, y0, y1, z0, z1;
+    float wx, wy, wz;
+};
+
+UIVR_DEV bool grid_cell(const Params& P, float px, float py, float pz, GridCell& g) {
+    if (!inside_unit(px, py, pz)) return false;
+    float qx = fmaf(px, P.fres[0], -0.5f), qy = fmaf(py, P.fres[1], -0.5f), qz = fmaf(pz, P.fres[2], -0.5f);
+    float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+    g.wx = qx - fx; g.wy = qy - fy; g.wz = qz - fz;
+    int ix = (int) fx, iy = (int) fy, iz = (int) fz;
+    g.x0 = max(ix, 0); g.x1 = min(ix + 1, P.res[0] - 1);
+    g.y0 = max(iy, 0); g.y1 = min(iy + 1, P.res[1] - 1);
+    g.z0 = max(iz, 0); g.z1 = min(iz + 1, P.res[2] - 1);
+    return true;
+}
+
+UIVR_DEV void albedo_tap(const Params& P, float px, float py, float pz, float a[3]) {
+    GridCell g;
+    if (!grid_cell(P, px, py, pz, g)) { a[0] = a[1] = a[2] = 0.0f; return; }
+    const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
+    const float* b000 = P.albedo + 3 * (g.z0 * sz + g.y0 * sy + g.x0);
+    const float* b100 = P.albedo + 3 * (g.z0 * sz + g.y0 * sy + g.x1);
+    const float* b010 = P.albedo + 3 * (g.z0 * sz + g.y1 * sy + g.x0);
+    const float* b110 = P.albedo + 3 * (g.z0 * sz + g.y1 * sy + g.x1);
+    const float* b001 = P.albedo + 3 * (g.z1 * sz + g.y0 * sy + g.x0);
+    const float* b101 = P.albedo + 3 * (g.z1 * sz + g.y0 * sy + g.x1);
+    const float* b011 = P.albedo + 3 * (g.z1 * sz + g.y1 * sy + g.x0);
+    const float* b111 = P.albedo + 3 * (g.z1 * sz + g.y1 * sy + g.x1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float c00 = lerpf(__ldg(b000 + c), __ldg(b100 + c), g.wx);
+        float c10 = lerpf(__ldg(b010 + c), __ldg(b110 + c), g.wx);
+        float c01 = lerpf(__ldg(b001 + c), __ldg(b101 + c), g.wx);
+        float c11 = lerpf(__ldg(b011 + c), __ldg(b111 + c), g.wx);
+        a[c] = lerpf(lerpf(c00, c10, g.wy), lerpf(c01, c11, g.wy), g.wz);
+    }
+}
+
+// adjoint of the lookups: scatter-add g*w_k into the 8 voxels
+UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float g) {
+    GridCell c;
+    if (!grid_cell(P, px, py, pz, c)) return;
+    const float gs = P.scale * g;
+    const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
+    const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
+    atomicAdd(P.dsigma + c.z0 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * uz));
+    atomicAdd(P.dsigma + c.z0 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * uz));
+    atomicAdd(P.dsigma + c.z0 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * uz));
+    atomicAdd(P.dsigma + c.z0 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * uz));
+    atomicAdd(P.dsigma + c.z1 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * c.wz));
+    atomicAdd(P.dsigma + c.z1 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * c.wz));
+    atomicAdd(P.dsigma + c.z1 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * c.wz));
+    atomicAdd(P.dsigma + c.z1 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * c.wz));
+}
+
+UIVR_DEV void scatter_albedo(const Params& P, float px, float py, float pz, const float g[3]) {
+    GridCell c;
+    if (!grid_cell(P, px, py, pz, c)) return;
+    const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
+    const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int x = (k & 1) ? c.x1 : c.x0, y = (k & 2) ? c.y1 : c.y0, z = (k & 4) ? c.z1 : c.z0;
+        const float w = (((k & 1) ? c.wx : ux) * ((k & 2) ? c.wy : uy)) * ((k & 4) ? c.wz : uz);
+        float* dst = P.dalbedo + 3 * (z * sz + y * sy + x);
+        atomicAdd(dst + 0, g[0] * w);
+        atomicAdd(dst + 1, g[1] * w);
+        atomicAdd(dst + 2, g[2] * w);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// segments (local-space origin / direction, t in world units)
+// --------------------------------------------------------------------------------------
+struct Seg {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmax;
+};
+
+UIVR_DEV void dir_to_local(const Params& P, float wx, float wy, float wz, float& dx, float& dy, float& dz) {
+    const float* M = P.to_local;
+    dx = fmaf(M[0], wx, fmaf(M[1], wy, M[2] * wz));
+    dy = fmaf(M[4], wx, fmaf(M[5], wy, M[6] * wz));
+    dz = fmaf(M[8], wx, fmaf(M[9], wy, M[10] * wz));
+}
+
+UIVR_DEV float exit_axis(float o, float d, float& inv) {
+    if (d != 0.0f) {
+        inv = 1.0f / d;
+        return ((d > 0.0f ? 1.0f : 0.0f) - o) * inv;
+    }
+    inv = UIVR_INF;
+    return UIVR_INF;
+}
+
+// distance to the box boundary from a point inside local [0,1]^3; fills inv_d
+UIVR_DEV float exit_distance(Seg& s) {
+    float t = exit_axis(s.ox, s.dx, s.ix);
+    t = fminf(t, exit_axis(s.oy, s.dy, s.iy));
+    t = fminf(t, exit_axis(s.oz, s.dz, s.iz));
+    return t;
+}
+
+// new segment leaving local point p along world direction w; false on accidental escape
+UIVR_DEV bool make_segment(const Params& P, float px, float py, float pz, float wx, float wy, float wz, Seg& s) {
+    s.ox = px; s.oy = py; s.oz = pz;
+    dir_to_local(P, wx, wy, wz, s.dx, s.dy, s.dz);
+    s.tmax = exit_distance(s);
+    return s.tmax > 0.0f && s.tmax < UIVR_INF;
+}
+
+// perspective sensor + reach_medium.  0 = missed (escaped), 1 = entered, 2 = dead
+UIVR_DEV int camera_segment(const Params& P, uint32_t pix, float jx, float jy, Seg& s) {
+    uint32_t px = pix % (uint32_t) P.width, py = pix / (uint32_t) P.width;
+    float u = ((float) px + jx) * P.inv_w;
+    float v = ((float) py + jy) * P.inv_h;
+    float cx = P.tan_x * fmaf(-2.0f, u, 1.0f);
+    float cy = P.tan_y * fmaf(-2.0f, v, 1.0f);
+    float d0 = fmaf(cx, P.cam_left[0], fmaf(cy, P.cam_up[0], P.cam_dir[0]));
+    float d1 = fmaf(cx, P.cam_left[1], fmaf(cy, P.cam_up[1], P.cam_dir[1]));
+    float d2 = fmaf(cx, P.cam_left[2], fmaf(cy, P.cam_up[2], P.cam_dir[2]));
+    float len = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+    float inv_len = 1.0f / len;
+    float near_t = P.near_clip * len;
+    d0 *= inv_len; d1 *= inv_len; d2 *= inv_len;
+    float o0 = fmaf(near_t, d0, P.cam_origin[0]);
+    float o1 = fmaf(near_t, d1, P.cam_origin[1]);
+    float o2 = fmaf(near_t, d2, P.cam_origin[2]);
+    const float* M = P.to_local;
+    float ol[3], dl[3];
+    ol[0] = fmaf(M[0], o0, fmaf(M[1], o1, fmaf(M[2], o2, M[3])));
+    ol[1] = fmaf(M[4], o0, fmaf(M[5], o1, fmaf(M[6], o2, M[7])));
+    ol[2] = fmaf(M[8], o0, fmaf(M[9], o1, fmaf(M[10], o2, M[11])));
+    dir_to_local(P, d0, d1, d2, dl[0], dl[1], dl[2]);
+    float tn = -UIVR_INF, tf = UIVR_INF;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (dl[a] != 0.0f) {
+            float inv = 1.0f / dl[a];
+            float t0 = (0.0f - ol[a]) * inv, t1 = (1.0f - ol[a]) * inv;
+            float lo = t0 < t1 ? t0 : t1, hi = t0 < t1 ? t1 : t0;
+            if (lo > tn) tn = lo;
+            if (hi < tf) tf = hi;
+        } else if (ol[a] < 0.0f || ol[a] > 1.0f) {
+            return 0;
+        }
+    }
+    if (!(tn <= tf) || !(tf > 0.0f)) return 0;
+    if (!(tn > 0.0f)) return 2;
+    float e0 = fmaf(tn, dl[0], ol[0]), e1 = fmaf(tn, dl[1], ol[1]), e2 = fmaf(tn, dl[2], ol[2]);
+    const float lo = UIVR_ENTRY_EPS, hi = 1.0f - UIVR_ENTRY_EPS;
+    s.ox = e0 < lo ? lo : (e0 > hi ? hi : e0);
+    s.oy = e1 < lo ? lo : (e1 > hi ? hi : e1);
+    s.oz = e2 < lo ? lo : (e2 > hi ? hi : e2);
+    s.dx = dl[0]; s.dy = dl[1]; s.dz = dl[2];
+    s.tmax = exit_distance(s);
+    return (s.tmax > 0.0f && s.tmax < UIVR_INF) ? 1 : 2;
+}
+
+// --------------------------------------------------------------------------------------
+// free-flight walk over the majorant supergrid (Medium::sample_interaction, App. B.5)
+// --------------------------------------------------------------------------------------
+struct Walk {
+    float t, tmax;
+    float tnx, tny, tnz;
+    int cx, cy, cz;
+    float sb;
+};
+
+template <bool COUNT>
+UIVR_DEV float majorant_at(const Params& P, int cx, int cy, int cz, Counters<COUNT>& K) {
+    K.add(C_MAJ, 1);
+    return __ldg(P.maj + ((size_t) cz * P.mres[1] + cy) * P.mres[0] + cx);
+}
+
+UIVR_DEV void walk_axis_init(float o, float d, float inv, float fm, float cs, int m, int& c, float& tn) {
+    c = clampi((int) floorf(o * fm), 0, m - 1);
+    if (d > 0.0f) tn = ((float) (c + 1) * cs - o) * inv;
+    else if (d < 0.0f) tn = ((float) c * cs - o) * inv;
+    else tn = UIVR_INF;
+}
+
+template <bool COUNT>
+UIVR_DEV void walk_init(const Params& P, const Seg& s, Walk& w, Counters<COUNT>& K) {
+    w.t = 0.0f;
+    w.tmax = s.tmax;
+    walk_axis_init(s.ox, s.dx, s.ix, P.fmres[0], P.mcs[0], P.mres[0], w.cx, w.tnx);
+    walk_axis_init(s.oy, s.dy, s.iy, P.fmres[1], P.mcs[1], P.mres[1], w.cy, w.tny);
+    walk_axis_init(s.oz, s.dz, s.iz, P.fmres[2], P.mcs[2], P.mres[2], w.cz, w.tnz);
+    w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, K);
+}
+
+// advance to the next tentative collision; false when the segment end is reached
+template <bool COUNT>
+UIVR_DEV bool walk_next(const Params& P, const Seg& s, Walk& w, float u, Counters<COUNT>& K) {
+    float tau = neg_log1m(u);
+    for (;;) {
+        int ax = 0;
+        float tn = w.tnx;
+        if (w.tny < tn) { ax = 1; tn = w.tny; }
+        if (w.tnz < tn) { ax = 2; tn = w.tnz; }
+        const float t_end = tn < w.tmax ? tn : w.tmax;
+        float len = t_end - w.t;
+        if (len < 0.0f) len = 0.0f;
+        if (w.sb > 0.0f) {
+            const float dtau = w.sb * len;
+            if (tau < dtau) {
+                float t = w.t + tau / w.sb;
+                if (t > t_end) t = t_end;
+                w.t = t;
+                return true;
+            }
+            tau -= dtau;
+        }
+        if (t_end > w.t) w.t = t_end;
+        if (!(tn < w.tmax)) return false;
+        if (ax == 0) {
+            w.cx += s.dx > 0.0f ? 1 : -1;
+            if (w.cx < 0 || w.cx >= P.mres[0]) return false;
+            w.tnx += fabsf(P.mcs[0] * s.ix);
+        } else if (ax == 1) {
+            w.cy += s.dy > 0.0f ? 1 : -1;
+            if (w.cy < 0 || w.cy >= P.mres[1]) return false;
+            w.tny += fabsf(P.mcs[1] * s.iy);
+        } else {
+            w.cz += s.dz > 0.0f ? 1 : -1;
+            if (w.cz < 0 || w.cz >= P.mres[2]) return false;
+            w.tnz += fabsf(P.mcs[2] * s.iz);
+        }
+        w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, K);
+    }
+}
+
+}  // namespace uivr

@@ -1,0 +1,186 @@
+// uivr_kernels.cuh -- __global__ entry points (sm_100a).
+#pragma once
+
+#include "uivr_path.cuh"
+
+namespace uivr {
+
+constexpr int kBlock = 256;
+
+// ---------------------------------------------------------------------------------------
+// K4a: corner-octet tap layout.  Cell (ix,iy,iz) in [0,res]^3 holds the 8 voxels a
+// trilinear lookup with floor(q)+1 == (ix,iy,iz) needs, border clamping applied, as two
+// float4: {v(x0,y0,z0), v(x1,y0,z0), v(x0,y1,z0), v(x1,y1,z0)}, {.. z1 ..}.  One tap = one
+// aligned 32-byte sector.  Costs 8x the memory of sigma_t (HBM is 180 GB; 512^3 -> 4.3 GB).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_build_octets(const float* __restrict__ sigma_t, float4* __restrict__ oct,
+                                                         int rx, int ry, int rz) {
+    const int ox = rx + 1, oy = ry + 1, oz = rz + 1;
+    const size_t n = (size_t) ox * oy * oz;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int ix = (int) (i % ox), iy = (int) ((i / ox) % oy), iz = (int) (i / ((size_t) ox * oy));
+        const int x0 = max(ix - 1, 0), x1 = min(ix, rx - 1);
+        const int y0 = max(iy - 1, 0), y1 = min(iy, ry - 1);
+        const int z0 = max(iz - 1, 0), z1 = min(iz, rz - 1);
+        const size_t sy = (size_t) rx, sz = (size_t) rx * ry;
+        float4 a, b;
+        a.x = __ldg(sigma_t + z0 * sz + y0 * sy + x0);
+        a.y = __ldg(sigma_t + z0 * sz + y0 * sy + x1);
+        a.z = __ldg(sigma_t + z0 * sz + y1 * sy + x0);
+        a.w = __ldg(sigma_t + z0 * sz + y1 * sy + x1);
+        b.x = __ldg(sigma_t + z1 * sz + y0 * sy + x0);
+        b.y = __ldg(sigma_t + z1 * sz + y0 * sy + x1);
+        b.z = __ldg(sigma_t + z1 * sz + y1 * sy + x0);
+        b.w = __ldg(sigma_t + z1 * sz + y1 * sy + x1);
+        oct[2 * i] = a;
+        oct[2 * i + 1] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4b: majorant supergrid: cell value = scale * max over the voxels whose
+// trilinear footprint touches the cell.  One warp per cell.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int floordiv_pos(int a, int b) {
+    int q = a / b;
+    if ((a % b) != 0 && a < 0) --q;
+    return q;
+}
+
+__global__ void __launch_bounds__(kBlock) k_build_majorant(const float* __restrict__ sigma_t, float* __restrict__ maj,
+                                                           int rx, int ry, int rz, int mx, int my, int mz, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int ncell = mx * my * mz;
+    for (int cell = warp; cell < ncell; cell += nwarps) {
+        const int cx = cell % mx, cy = (cell / mx) % my, cz = cell / (mx * my);
+        const int lx = clampi(floordiv_pos(2 * cx * rx - mx, 2 * mx), 0, rx - 1);
+        const int hx = clampi(floordiv_pos(2 * (cx + 1) * rx - mx, 2 * mx) + 1, 0, rx - 1);
+        const int ly = clampi(floordiv_pos(2 * cy * ry - my, 2 * my), 0, ry - 1);
+        const int hy = clampi(floordiv_pos(2 * (cy + 1) * ry - my, 2 * my) + 1, 0, ry - 1);
+        const int lz = clampi(floordiv_pos(2 * cz * rz - mz, 2 * mz), 0, rz - 1);
+        const int hz = clampi(floordiv_pos(2 * (cz + 1) * rz - mz, 2 * mz) + 1, 0, rz - 1);
+        const int nx = hx - lx + 1, ny = hy - ly + 1, nz = hz - lz + 1;
+        const int total = nx * ny * nz;
+        float m = 0.0f;
+        for (int i = lane; i < total; i += 32) {
+            const int x = lx + i % nx, y = ly + (i / nx) % ny, z = lz + i / (nx * ny);
+            m = fmaxf(m, __ldg(sigma_t + ((size_t) z * ry + y) * rx + x));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) maj[cell] = scale * m;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_scale(float* __restrict__ x, size_t n, float s) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        x[i] = x[i] * s;
+}
+
+// ---------------------------------------------------------------------------------------
+// variant 1: one sample per lane, warps pull 32-sample chunks from a global counter
+// ---------------------------------------------------------------------------------------
+UIVR_DEV bool next_chunk(const Params& P, uint64_t total, uint32_t& item) {
+    unsigned base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(P.work_counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((uint64_t) base >= total) return false;
+    item = base + (threadIdx.x & 31);
+    return true;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_forward_v1(const Params P) {
+    Counters<COUNT> K;
+    const uint64_t total = (uint64_t) P.n_slots * P.spp;
+    uint32_t item;
+    while (next_chunk(P, total, item)) {
+        uint32_t pix = 0;
+        const bool live = (uint64_t) item < total && slot_to_pixel(P, item / P.spp, pix);
+        float L[3] = {0.0f, 0.0f, 0.0f};
+        if (live) {
+            const uint32_t idx = pix * P.spp + item % P.spp;
+            sample_from_camera<false, COUNT>(P, idx, nullptr, L, K);
+            K.add(C_SAMPLES, 1);
+            if (P.sample_L) {
+                P.sample_L[3 * (size_t) idx + 0] = L[0];
+                P.sample_L[3 * (size_t) idx + 1] = L[1];
+                P.sample_L[3 * (size_t) idx + 2] = L[2];
+            }
+        }
+        __syncwarp();
+        if ((P.spp & 31u) == 0) {  // the whole chunk belongs to one pixel
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = L[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0 && live) atomicAdd(P.image + 3 * (size_t) pix + c, v);
+            }
+        } else if (live) {
+            atomicAdd(P.image + 3 * (size_t) pix + 0, L[0]);
+            atomicAdd(P.image + 3 * (size_t) pix + 1, L[1]);
+            atomicAdd(P.image + 3 * (size_t) pix + 2, L[2]);
+        }
+    }
+    K.flush(P.counters);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_backward_v1(const Params P) {
+    Counters<COUNT> K;
+    const uint64_t total = (uint64_t) P.n_slots * P.spp;
+    uint32_t item;
+    while (next_chunk(P, total, item)) {
+        uint32_t pix = 0;
+        const bool live = (uint64_t) item < total && slot_to_pixel(P, item / P.spp, pix);
+        if (live) {
+            const uint32_t idx = pix * P.spp + item % P.spp;
+            float L[3] = {0.0f, 0.0f, 0.0f};
+            // batched.py:255-264: detached primal pass at seed_grad -> state_in
+            sample_from_camera<false, COUNT>(P, idx, nullptr, L, K);
+            K.add(C_SAMPLES, 1);
+            if (P.sample_L) {
+                P.sample_L[3 * (size_t) idx + 0] = L[0];
+                P.sample_L[3 * (size_t) idx + 1] = L[1];
+                P.sample_L[3 * (size_t) idx + 2] = L[2];
+            }
+            // batched.py:272-306: box film => dL = grad_image[pixel] / spp
+            float dL[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dL[c] = __ldg(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp;
+            // batched.py:309-318: sample(Backward, state_in = L)
+            sample_from_camera<true, COUNT>(P, idx, dL, L, K);
+        }
+        __syncwarp();
+    }
+    K.flush(P.counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// primitive test kernels (bit-exactness checks against the oracle)
+// ---------------------------------------------------------------------------------------
+__global__ void k_test_neg_log1m(const float* u, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = neg_log1m(u[i]);
+}
+__global__ void k_test_sincos2pi(const float* x, int n, float* s, float* c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincos2pi(x[i], s[i], c[i]);
+}
+__global__ void k_test_sampler(uint32_t seed, uint32_t idx0, int nstreams, int ndraws, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nstreams) {
+        Rng r;
+        r.seed_sampler(seed, idx0 + (uint32_t) i);
+        for (int k = 0; k < ndraws; ++k) out[(size_t) i * ndraws + k] = r.f();
+    }
+}
+__global__ void k_test_sigma_lookup(const Params P, const float* p, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sigma_tap(P, p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+}
+
+}  // namespace uivr

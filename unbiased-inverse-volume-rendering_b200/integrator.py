@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's integrator plugin surface for the volpathsimple path.
+
+Reference interface                                  -> here
+  mi.register_integrator("volpathsimple", ...)  (volpathsimple.py:769)   -> INTEGRATORS registry
+  VolpathSimpleIntegrator(props)                 (volpathsimple.py:19-34) -> VolpathSimpleIntegrator
+  RBIntegrator.render / render_backward          (batched.py:134-326)     -> .render / .render_backward
+  mi.render(scene, params, integrator, sensor, spp, spp_grad, seed, seed_grad)
+                                                 (optimize.py:345-347)    -> render(...)
+  dr.backward(loss) -> dr.grad(params[k])        (optimize.py:350)        -> torch autograd
+
+PyTorch only holds device memory and streams; all arithmetic runs in libuivr.so (C-ABI,
+include/uivr.h).  There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+from .scene import Sensor, VolumeScene
+
+SIGMA_T_SUFFIX = "sigma_t.data"
+ALBEDO_SUFFIX = "albedo.data"
+
+
+def _find_key(params: Dict[str, torch.Tensor], suffix: str) -> str:
+    keys = [k for k in params.keys() if k.endswith(suffix)]
+    if len(keys) != 1:
+        # util.get_single_medium (util.py:75-86): exactly one medium / one grid of each kind
+        raise ValueError(f"expected exactly one parameter ending in '{suffix}', found {keys}")
+    return keys[0]
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class Scene:
+    """Runtime scene: a VolumeScene bound to one CUDA device through a native context."""
+
+    def __init__(self, volume: VolumeScene, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _native.NativeError("CUDA device required: the volpathsimple path has no CPU fallback")
+        self.volume = volume
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.ctx = _native.Context(self.device)
+        self._medium_key = None
+        self._scene_key = None
+        self._props_key = None
+
+    # mi.traverse(scene) equivalent for the two optimised grids
+    def check_params(self, params: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        x, y, z = self.volume.res
+        sig = params[_find_key(params, SIGMA_T_SUFFIX)]
+        alb = params[_find_key(params, ALBEDO_SUFFIX)]
+        for name, t, shape in (("sigma_t", sig, (z, y, x, 1)), ("albedo", alb, (z, y, x, 3))):
+            if tuple(t.shape) != shape and not (name == "sigma_t" and tuple(t.shape) == (z, y, x)):
+                raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+            if t.dtype != torch.float32 or not t.is_cuda or t.device.index != self.device:
+                raise ValueError(f"{name} must be a float32 CUDA tensor on device {self.device}")
+            if not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous")
+        return sig, alb
+
+    def bind(self, sensor: Optional[Sensor], props: dict):
+        vol = self.volume if sensor is None else self.volume.with_sensor(sensor)
+        desc = vol.as_dict()
+        key = tuple((k, tuple(map(float, v.reshape(-1))) if hasattr(v, "reshape") else v) for k, v in sorted(desc.items()))
+        if key != self._scene_key:
+            old_medium_inputs = None if self._scene_key is None else self._medium_inputs
+            self.ctx.set_scene(desc)
+            self._scene_key = key
+            self._medium_inputs = (desc["res"], float(desc["scale"]), desc["majorant_factor"])
+            if old_medium_inputs != self._medium_inputs:
+                self._medium_key = None
+        pkey = tuple(sorted(props.items()))
+        if pkey != self._props_key:
+            self.ctx.set_integrator(props)
+            self._props_key = pkey
+        return desc
+
+    def update_medium(self, sigma_t: torch.Tensor, force: bool = False):
+        """params.update(): rebuild octets + majorant supergrid if sigma_t changed."""
+        key = (sigma_t.data_ptr(), sigma_t._version)
+        if force or key != self._medium_key:
+            self.ctx.update_medium(sigma_t.data_ptr(), _stream())
+            self._medium_key = key
+
+
+class VolpathSimpleIntegrator:
+    """Same property names / defaults as python/integrators/volpathsimple.py:19-34."""
+
+    def __init__(self, props: Optional[dict] = None):
+        props = dict(props or {})
+        props.pop("type", None)
+        self.max_depth = int(props.pop("max_depth", 64))
+        self.rr_depth = int(props.pop("rr_depth", self.max_depth + 1000))
+        self.hide_emitters = bool(props.pop("hide_emitters", False))
+        self.use_nee = bool(props.pop("use_nee", True))
+        self.use_drt = bool(props.pop("use_drt", True))
+        self.use_drt_subsampling = bool(props.pop("use_drt_subsampling", True))
+        self.use_drt_mis = bool(props.pop("use_drt_mis", True))
+        if props:
+            raise ValueError(f"unknown integrator properties: {sorted(props)}")
+        if self.max_depth < 0:
+            raise ValueError("max_depth must be >= 0")
+        if self.rr_depth <= self.max_depth:
+            # volpathsimple.py:36 "TODO: support Russian Roulette"; opt_config.py:103-106
+            raise NotImplementedError("Russian roulette is not supported (rr_depth must exceed max_depth)")
+
+    def props(self) -> dict:
+        return {"max_depth": self.max_depth, "hide_emitters": self.hide_emitters,
+                "use_nee": self.use_nee, "use_drt": self.use_drt,
+                "use_drt_subsampling": self.use_drt_subsampling, "use_drt_mis": self.use_drt_mis}
+
+    def aovs(self):
+        return []
+
+    # RBIntegrator.render (batched.py:134-197)
+    def render(self, scene: Scene, params: Dict[str, torch.Tensor], sensor: Optional[Sensor] = None,
+               seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True,
+               shard: Optional[Sequence[int]] = None, sample_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not develop:
+            raise Exception("develop=True must be specified when invoking AD integrators")  # batched.py:145-147
+        if spp <= 0:
+            raise ValueError("spp must be positive")
+        sig, alb = scene.check_params(params)
+        desc = scene.bind(sensor, self.props())
+        scene.update_medium(sig.detach())
+        image = torch.empty((desc["height"], desc["width"], 3), dtype=torch.float32, device=sig.device)
+        scene.ctx.render_forward(alb.detach().data_ptr(), seed, spp, image.data_ptr(),
+                                 None if sample_out is None else sample_out.data_ptr(), shard, _stream())
+        return image
+
+    # RBIntegrator.render_backward (batched.py:212-326)
+    def render_backward(self, scene: Scene, params: Dict[str, torch.Tensor], grad_in: torch.Tensor,
+                        sensor: Optional[Sensor] = None, seed: int = 0, spp: int = 0,
+                        shard: Optional[Sequence[int]] = None, sample_out: Optional[torch.Tensor] = None,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        if spp <= 0:
+            raise ValueError("spp must be positive")
+        sig, alb = scene.check_params(params)
+        desc = scene.bind(sensor, self.props())
+        if tuple(grad_in.shape) != (desc["height"], desc["width"], 3):
+            raise ValueError(f"grad_in must have shape {(desc['height'], desc['width'], 3)}")
+        grad_in = grad_in.to(dtype=torch.float32).contiguous()
+        scene.update_medium(sig.detach())
+        if out is None:
+            dsig = torch.empty_like(sig)
+            dalb = torch.empty_like(alb)
+        else:
+            dsig, dalb = out
+        scene.ctx.render_backward(alb.detach().data_ptr(), grad_in.data_ptr(), seed, spp,
+                                  dsig.data_ptr(), dalb.data_ptr(),
+                                  None if sample_out is None else sample_out.data_ptr(), shard, _stream())
+        return dsig, dalb
+
+
+INTEGRATORS = {"volpathsimple": VolpathSimpleIntegrator}
+
+
+def register_integrator(name: str, factory):
+    """mi.register_integrator (volpathsimple.py:769)."""
+    INTEGRATORS[name] = factory
+
+
+def load_dict(d: dict):
+    """mi.load_dict for integrator dictionaries (opt_config.py:108)."""
+    if "type" not in d:
+        raise ValueError("integrator dictionary needs a 'type'")
+    if d["type"] not in INTEGRATORS:
+        raise NotImplementedError(f"integrator type '{d['type']}' is outside the hot path of this build")
+    return INTEGRATORS[d["type"]](d)
+
+
+class _RenderOp(torch.autograd.Function):
+    """mi.render's _RenderOp: forward = primal render at `seed`/`spp` (detached), backward =
+    render_backward at `seed_grad`/`spp_grad`."""
+
+    @staticmethod
+    def forward(ctx, sigma_t, albedo, scene, integrator, sensor, seed, seed_grad, spp, spp_grad, keys, shard, reducer):
+        params = {keys[0]: sigma_t, keys[1]: albedo}
+        image = integrator.render(scene, params, sensor=sensor, seed=seed, spp=spp, shard=shard)
+        ctx.save_for_backward(sigma_t, albedo)
+        ctx.meta = (scene, integrator, sensor, seed_grad, spp_grad, keys, shard, reducer)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        sigma_t, albedo = ctx.saved_tensors
+        scene, integrator, sensor, seed_grad, spp_grad, keys, shard, reducer = ctx.meta
+        params = {keys[0]: sigma_t, keys[1]: albedo}
+        dsig, dalb = integrator.render_backward(scene, params, grad_image, sensor=sensor, seed=seed_grad,
+                                                spp=spp_grad, shard=shard)
+        if reducer is not None:
+            dsig, dalb = reducer(dsig, dalb)
+        return (dsig, dalb) + (None,) * 10
+
+
+def render(scene: Scene, params: Dict[str, torch.Tensor], integrator: VolpathSimpleIntegrator,
+           sensor: Optional[Sensor] = None, spp: int = 0, spp_grad: int = 0, seed: int = 0,
+           seed_grad: int = 0, shard: Optional[Sequence[int]] = None, reducer=None) -> torch.Tensor:
+    """mi.render(scene, params=..., integrator=..., sensor=..., spp=..., spp_grad=..., seed=...,
+    seed_grad=...) as called at optimize.py:345-347.  Differentiable w.r.t. the two grids."""
+    if spp_grad == 0:
+        spp_grad = spp
+    if seed_grad == 0:
+        # de-correlate the primal and differential phases (batched.py:119-121)
+        seed_grad = _native.tea32(seed, 1)
+    elif seed_grad == seed:
+        raise Exception("The primal and differential seed should be different "
+                        "to ensure unbiased gradient computation!")  # batched.py:122-124
+    k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, ALBEDO_SUFFIX)
+    return _RenderOp.apply(params[k_sig], params[k_alb], scene, integrator, sensor, seed, seed_grad,
+                           spp, spp_grad, (k_sig, k_alb), shard, reducer)
