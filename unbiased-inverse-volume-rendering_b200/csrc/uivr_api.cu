@@ -26,7 +26,7 @@ struct uivr_ctx {
     size_t maj_cells = 0;
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
-    int variant = 1;
+    int variant = 0;
     int counting = 0;
     uint64_t launches = 0;
     // staging for the *_host entry points
@@ -66,7 +66,7 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     const uivr_integrator_props& ip = ctx->props;
     if (spp < 1) return fail(ctx, UIVR_ERR_INVALID, "spp must be >= 1");
     const uint64_t npix = (uint64_t) s.width * (uint64_t) s.height;
-    if (npix * (uint64_t) spp >= (1ull << 32))
+    if (npix * (uint64_t) spp >= (1ull << 32) - (1ull << 24))
         return fail(ctx, UIVR_ERR_INVALID, "wavefront too large: W*H*spp must be < 2^32 (batched.py:378-388)");
     memset(&P, 0, sizeof(P));
     for (int a = 0; a < 3; ++a) {
@@ -345,7 +345,9 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     UIVR_CUDA(ctx, cudaMemsetAsync(d_dalbedo, 0, vox * 3 * sizeof(float), st));
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
-    if (ctx->variant == 1) {
+    // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
+    const bool quadratic = ctx->props.use_drt && !ctx->props.use_drt_subsampling;
+    if (ctx->variant == 1 || quadratic) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);
