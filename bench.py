@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the volpathsimple hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A "step" = one forward render at `seed` + one DRT backward at `seed_grad` (primal replay +
+path-replay adjoint + DRT) of ONE view, i.e. what `mi.render` + `dr.backward(loss)` execute
+per view in the reference (optimize.py:345-350).  Workload at N=1: BASELINE.json configs[2]
+(the configuration the metric is quoted on): 256^3 sigma_t + albedo grids, 512x512x64 spp,
+`volpathsimple-drt` flags, max_depth 64, supergrid factor 8.  At N>1 the pixels are sharded
+across ranks (interleaved blocks), spp grows with N so that per-GPU work stays fixed (weak
+scaling), and the gradients are summed with one NCCL all-reduce inside the timed region.
+
+Own arm prints one JSON line with `value` (inputs resident in HBM), `e2e` (host buffers
+through the C-ABI *_host calls, copies inside the timed region), `roofline` (dominant kernel:
+the backward megakernel; algorithmic bytes from the in-kernel event counters of the same
+steps), `cpu_baseline` (the CPU oracle on a bounded sample, N=1 only) and `clocks`.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, all host
+threads): the reference itself (Dr.Jit/Mitsuba 3) cannot be installed here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/s (fwd+DRT bwd) on 256^3 grid @512^2x64spp"
+UNIT = "Msamples/s"
+GRID_N, FILM_W, FILM_H, SPP = 256, 512, 512, 64
+BASE_SEED = 1234
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def step_seeds(it: int):
+    """optimize.py:327-328: seed, seed_grad = tea32(2 it, base), tea32(2 it + 1, base)."""
+    import uivr_b200 as u
+    return u.tea32(2 * it, BASE_SEED), u.tea32(2 * it + 1, BASE_SEED)
+
+
+def workload_config(n_gpus: int, spp: int, extra=None):
+    cfg = {
+        "workload": f"config3: {GRID_N}^3 sigma_t+albedo, {FILM_W}x{FILM_H}x{spp}spp, DRT fwd+bwd, single view",
+        "integrator": "volpathsimple-drt (nee, drt, subsampling, mis), max_depth 64, majorant factor 8",
+        "samples_per_step": FILM_W * FILM_H * spp,
+        "parallelism": "single GPU" if n_gpus == 1 else
+                       f"pixel-sharded x{n_gpus} (interleaved 64-px blocks), spp={SPP}*{n_gpus}, NCCL grad all-reduce in step",
+        "l2_policy": "inputs larger than L2 (sigma_t octets 537 MB + albedo 192 MB + gradients 256 MB vs 126 MB L2); "
+                     "gradient buffers re-zeroed every step; seeds change every step",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(cnt: dict, hw: int, backward: bool) -> int:
+    """32 N_sigma + 96 N_alb + 4 N_maj + 64 G_sigma + 192 G_alb + 12 HW."""
+    b = (32 * cnt["sigma_taps"] + 96 * cnt["albedo_taps"] + 4 * cnt["majorant_reads"] +
+         64 * cnt["sigma_scatters"] + 192 * cnt["albedo_scatters"])
+    return b + 12 * hw  # image write (fwd) / grad_image read (bwd)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/uivr_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w": statistics.median(power),
+                "n_samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm (oracle)
+# ----------------------------------------------------------------------------------------
+def oracle_step(O, desc, props, sig, alb, it, spp, nthreads):
+    import numpy as np
+    seed, seed_grad = step_seeds(it)
+    img, _, _ = O.render_forward(desc, props, sig, alb, seed, spp, nthreads=nthreads)
+    g = (2.0 * (img.astype(np.float64) - 0.5) / img.size).astype(np.float32)
+    O.render_backward(desc, props, sig, alb, g, seed_grad, spp, nthreads=nthreads)
+
+
+def cpu_baseline(target_s: float = 12.0):
+    """The CPU oracle (kind 'port': C restatement of the reference algorithm, pthreads over all
+    host cores) on a bounded sample of config 3: same grids / camera / flags, reduced spp."""
+    import uivr_b200 as u
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    sig_t, alb_t = u.synthetic_grids(GRID_N)
+    sig, alb = sig_t.numpy(), alb_t.numpy()
+    vol = u.benchmark_scene(GRID_N, FILM_W, FILM_H, scale=8.0, majorant_resolution_factor=8)
+    desc = vol.as_dict()
+    props = u.get_int_config("volpathsimple-drt").create(max_depth=64).props()
+    t0 = time.perf_counter()
+    oracle_step(O, desc, props, sig, alb, 0, 1, cores)  # calibration (also warms the page cache)
+    t1 = time.perf_counter() - t0
+    spp = int(max(1, min(SPP, round(target_s / max(t1, 1e-3)))))
+    t0 = time.perf_counter()
+    oracle_step(O, desc, props, sig, alb, 1, spp, cores)
+    dt = time.perf_counter() - t0
+    return {"value": FILM_W * FILM_H * spp / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"config3 grids/camera/flags at {FILM_W}x{FILM_H}x{spp}spp ({FILM_W * FILM_H * spp} samples, "
+                      f"fwd+bwd, {dt:.1f} s of wall time on {cores} threads)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Mitsuba 3 / Dr.Jit
+    (llvm_ad_rgb) cannot be installed here, so this is the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import uivr_b200 as u
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    sig_t, alb_t = u.synthetic_grids(GRID_N)
+    sig, alb = sig_t.numpy(), alb_t.numpy()
+    vol = u.benchmark_scene(GRID_N, FILM_W, FILM_H, scale=8.0, majorant_resolution_factor=8)
+    desc = vol.as_dict()
+    props = u.get_int_config("volpathsimple-drt").create(max_depth=64).props()
+    t0 = time.perf_counter()
+    oracle_step(O, desc, props, sig, alb, 0, 1, cores)
+    t1 = time.perf_counter() - t0
+    # bounded sample per step so that (K + W) steps end within ~2 minutes
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    spp = int(max(1, min(SPP, budget / max(t1, 1e-3))))
+    for it in range(args.warmup):
+        oracle_step(O, desc, props, sig, alb, it, spp, cores)
+    t0 = time.perf_counter()
+    for it in range(args.warmup, args.warmup + args.steps):
+        oracle_step(O, desc, props, sig, alb, it, spp, cores)
+    dt = time.perf_counter() - t0
+    samples = FILM_W * FILM_H * spp
+    value = samples * args.steps / dt / 1e6
+    sample = (f"each step = config3 grids/camera/flags at {FILM_W}x{FILM_H}x{spp}spp ({samples} samples), fwd+bwd, "
+              f"CPU oracle port on {cores} host threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.gpus, SPP * args.gpus, {"reference_sample": sample}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import uivr_b200 as u
+    from importlib import import_module
+    sharding = import_module("uivr_b200.sharding")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spp = SPP * world
+    shard = sharding.pixel_shard(rank, world)
+    S_total = FILM_W * FILM_H * spp
+    HW = FILM_W * FILM_H
+
+    sig_h, alb_h = u.synthetic_grids(GRID_N)
+    sig, alb = sig_h.to(dev), alb_h.to(dev)
+    vol = u.benchmark_scene(GRID_N, FILM_W, FILM_H, scale=8.0, majorant_resolution_factor=8)
+    scene = u.Scene(vol, device=local_rank)
+    integ = u.get_int_config("volpathsimple-drt").create(max_depth=64)
+    params = {"medium.sigma_t.data": sig, "medium.albedo.data": alb}
+    grads = sharding.GradientBuffer(vol.res, dev)
+    ctx = scene.ctx
+    inv_numel = 1.0 / (HW * 3)
+
+    def step(it):
+        seed, seed_grad = step_seeds(it)
+        img = integ.render(scene, params, seed=seed, spp=spp, shard=shard)
+        g = (img - 0.5) * (2.0 * inv_numel)  # d/d image of mean((image - 0.5)^2), tests:119-120
+        integ.render_backward(scene, params, g, seed=seed_grad, spp=spp, shard=shard, out=grads.views())
+        grads.all_reduce()
+        return img
+
+    # ---- resident-input timing: `value` ----
+    for it in range(args.warmup):
+        step(it)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_fwd_ms, k_bwd_ms = [], []
+    barrier()
+    ev0.record()
+    for it in range(args.warmup, args.warmup + args.steps):
+        step(it)
+        k_fwd_ms.append(ctx.kernel_ms(0))  # waits for the kernels of this step (results are read
+        k_bwd_ms.append(ctx.kernel_ms(1))  # back every step in the reference loop as well)
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = S_total / (ms_step * 1e-3) / 1e6
+
+    # ---- end-to-end through host buffers: `e2e` ----
+    h_sig, h_alb = sig_h.contiguous().pin_memory(), alb_h.contiguous().pin_memory()
+    h_img = torch.empty((FILM_H, FILM_W, 3), dtype=torch.float32).pin_memory()
+    h_g = torch.empty_like(h_img).pin_memory()
+    h_ds, h_da = torch.empty_like(h_sig).pin_memory(), torch.empty_like(h_alb).pin_memory()
+    stream = int(torch.cuda.current_stream().cuda_stream)
+    scene.bind(None, integ.props())
+
+    def e2e_step(it):
+        seed, seed_grad = step_seeds(it)
+        if world == 1:
+            # the C-ABI host entry points: H2D parameters, update_medium, render, D2H image ...
+            ctx.render_forward_host(h_sig.data_ptr(), h_alb.data_ptr(), seed, spp, h_img.data_ptr(), None, stream)
+            torch.sub(h_img, 0.5, out=h_g).mul_(2.0 * inv_numel)  # loss gradient on the host
+            # ... H2D grad_image, backward on the staged parameters, D2H gradients
+            ctx.render_backward_host(None, None, h_g.data_ptr(), seed_grad, spp, h_ds.data_ptr(), h_da.data_ptr(),
+                                     None, stream)
+        else:
+            sig.copy_(h_sig, non_blocking=True)
+            alb.copy_(h_alb, non_blocking=True)
+            scene.update_medium(sig, force=True)
+            img = integ.render(scene, params, seed=seed, spp=spp, shard=shard)
+            h_img.copy_(img, non_blocking=True)
+            g = (img - 0.5) * (2.0 * inv_numel)
+            integ.render_backward(scene, params, g, seed=seed_grad, spp=spp, shard=shard, out=grads.views())
+            grads.all_reduce()
+            h_ds.copy_(grads.dsigma, non_blocking=True)
+            h_da.copy_(grads.dalbedo, non_blocking=True)
+            torch.cuda.synchronize()
+
+    h2d = h_sig.numel() * 4 + h_alb.numel() * 4 + (h_g.numel() * 4 if world == 1 else 0)
+    d2h = h_img.numel() * 4 + h_ds.numel() * 4 + h_da.numel() * 4
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for it in range(1, 1 + e2e_steps):
+        e2e_step(it)
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, e2e_wall_ms)  # host-side loss gradient and synchronous copies count too
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = S_total / (e2e_ms / e2e_steps * 1e-3) / 1e6
+    # restore the device-resident medium for the accounting pass
+    scene.update_medium(sig, force=True)
+
+    # ---- algorithmic bytes of the timed steps (counting instances; untimed) ----
+    ctx.set_counting(True)
+    cnt_f = dict.fromkeys(u._native.COUNTER_NAMES, 0)
+    cnt_b = dict.fromkeys(u._native.COUNTER_NAMES, 0)
+    for it in range(args.warmup, args.warmup + args.steps):
+        seed, seed_grad = step_seeds(it)
+        ctx.reset_counters()
+        img = integ.render(scene, params, seed=seed, spp=spp, shard=shard)
+        for k, v in ctx.get_counters().items():
+            cnt_f[k] += v
+        g = (img - 0.5) * (2.0 * inv_numel)
+        ctx.reset_counters()
+        integ.render_backward(scene, params, g, seed=seed_grad, spp=spp, shard=shard, out=grads.views())
+        for k, v in ctx.get_counters().items():
+            cnt_b[k] += v
+    ctx.set_counting(False)
+    torch.cuda.synchronize()
+    my_hw = int(sharding.owned_pixel_mask(HW, shard).sum().item())
+    bytes_b = algorithmic_bytes(cnt_b, my_hw * args.steps, True) / args.steps
+    bytes_f = algorithmic_bytes(cnt_f, my_hw * args.steps, False) / args.steps
+    bwd_ms = sum(k_bwd_ms) / len(k_bwd_ms)
+    fwd_ms = sum(k_fwd_ms) / len(k_fwd_ms)
+    peak, peak_src = hbm_peak()
+    achieved = bytes_b / (bwd_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("k_mega_bwd_dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        my_samples = my_hw * spp
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, spp),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "uivr_render_forward_host + uivr_render_backward_host (pinned host buffers)" if world == 1
+                           else "pinned H2D + integrator.render/render_backward + NCCL all-reduce + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_mega<BWD> (primal replay + adjoint + DRT megakernel), rank 0",
+                         "kernel_ms": bwd_ms, "algorithmic_bytes_per_launch": bytes_b,
+                         "bytes_per_sample": bytes_b / my_samples,
+                         "forward_kernel": {"kernel_ms": fwd_ms, "algorithmic_bytes_per_launch": bytes_f,
+                                            "achieved": bytes_f / (fwd_ms * 1e-3) / 1e9,
+                                            "bytes_per_sample": bytes_f / my_samples},
+                         "kernel_share_of_step": (bwd_ms + fwd_ms) / ms_step},
+            "events_per_sample": {"forward": {k: v / (my_samples * args.steps) for k, v in cnt_f.items()},
+                                  "backward": {k: v / (my_samples * args.steps) for k, v in cnt_b.items()}},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        print(f"note: warmup {args.warmup} < 3 breaks the timing rules; use only for profiling runs", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch ourselves under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

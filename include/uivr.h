@@ -116,7 +116,10 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
                          float* d_dsigma_t, float* d_dalbedo, float* d_sample_L, void* stream);
 
 /* Host-buffer variants (end-to-end path: H2D of the parameters / grad_image, D2H of the
- * results inside the call; synchronises `stream` before returning). */
+ * results inside the call; synchronises `stream` before returning).  They include
+ * uivr_update_medium.  uivr_render_backward_host accepts h_sigma_t == h_albedo == NULL to
+ * reuse the parameters staged by the previous *_host call (dr.backward follows mi.render on
+ * unchanged parameters, optimize.py:345-350). */
 int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo,
                              uint32_t seed, int32_t spp, const uivr_shard* shard,
                              float* h_image, void* stream);
@@ -131,6 +134,10 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
 int uivr_set_counting(uivr_ctx* ctx, int enable);
 int uivr_reset_counters(uivr_ctx* ctx, void* stream);
 int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stream); /* synchronises */
+/* CUDA-event duration (ms) of the most recent path megakernel launched by this context:
+ * which = 0 forward (sample(Primal) kernel), 1 backward (primal replay + adjoint + DRT kernel).
+ * Events are recorded on the stream the kernel was launched on; synchronises on the end event. */
+int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms);
 /* number of kernel launches issued by this context so far */
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
 /* kernel variant: 0 = persistent lane-refill megakernel (default), 1 = one-sample-per-lane */

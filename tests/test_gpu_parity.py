@@ -308,6 +308,57 @@ def test_host_entry_points(uivr, oracle, dev):
     assert rel_linf(h_da.numpy(), da_o) < GRAD_TOL
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("case", ["hetero12", "cube3"])
+def test_against_committed_golden_fixtures(uivr, dev, variant, case):
+    """CUDA path vs the numbers frozen in tests/golden/*.npz (no oracle build involved)."""
+    import importlib.util
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gdir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(gdir, f"{case}.npz"))
+    sig, alb, vol, spp, max_depth, seed, seed_grad = mg.case_inputs(case)
+    names = uivr._native.COUNTER_NAMES
+    for combo, flags in FLAG_COMBOS.items():
+        props = dict(max_depth=max_depth, use_nee=True, **flags)
+        img, smp, cnt = _run_forward(uivr, vol, props, sig, alb, seed, spp, dev, variant)
+        assert np.array_equal(smp.view(np.uint32), g[f"{combo}/samples"])
+        assert [cnt[k] for k in names] == list(g[f"{combo}/counters_fwd"])
+        assert np.max(np.abs(img - g[f"{combo}/image"])) < IMAGE_TOL
+        ds, da, smp_g, cnt_b = _run_backward(uivr, vol, props, sig, alb, loss_grad(g[f"{combo}/image"]),
+                                             seed_grad, spp, dev, variant)
+        assert np.array_equal(smp_g.view(np.uint32), g[f"{combo}/samples_grad_pass"])
+        assert [cnt_b[k] for k in names] == list(g[f"{combo}/counters_bwd"])
+        assert rel_linf(ds, g[f"{combo}/dsigma"]) < GRAD_TOL
+        assert rel_linf(da, g[f"{combo}/dalbedo"]) < GRAD_TOL
+
+
+def test_host_backward_reuses_staged_parameters_and_kernel_timers(uivr, oracle, dev):
+    sig, alb = hetero_grids(10)
+    vol = uivr.benchmark_scene(10, 24, 20, scale=5.0, majorant_resolution_factor=2)
+    props = dict(max_depth=16)
+    scene = uivr.Scene(vol, device=0)
+    scene.bind(None, props)
+    h_sig, h_alb = torch.from_numpy(sig).pin_memory(), torch.from_numpy(alb).pin_memory()
+    h_img = torch.empty((20, 24, 3)).pin_memory()
+    h_g = torch.empty((20, 24, 3)).pin_memory()
+    h_ds, h_da = torch.empty_like(h_sig).pin_memory(), torch.empty_like(h_alb).pin_memory()
+    with pytest.raises(uivr.NativeError, match="no staged parameters"):
+        scene.ctx.render_backward_host(None, None, h_g.data_ptr(), 22, 4, h_ds.data_ptr(), h_da.data_ptr())
+    with pytest.raises(uivr.NativeError, match="no path kernel"):
+        scene.ctx.kernel_ms(1)
+    scene.ctx.render_forward_host(h_sig.data_ptr(), h_alb.data_ptr(), 21, 4, h_img.data_ptr())
+    assert scene.ctx.kernel_ms(0) > 0.0
+    h_g.copy_(torch.from_numpy(loss_grad(h_img.numpy())))
+    scene.ctx.render_backward_host(None, None, h_g.data_ptr(), 22, 4, h_ds.data_ptr(), h_da.data_ptr())
+    assert scene.ctx.kernel_ms(1) > 0.0
+    ds_o, da_o, _, _ = oracle.render_backward(vol.as_dict(), props, sig, alb, h_g.numpy(), 22, 4)
+    assert rel_linf(h_ds.numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(h_da.numpy(), da_o) < GRAD_TOL
+
+
 def test_error_behaviour(uivr, dev):
     vol = uivr.cube_test_scene(8, 8)
     scene = uivr.Scene(vol, device=0)

@@ -22,7 +22,8 @@ EXPORTS = [
     "uivr_version", "uivr_create", "uivr_destroy", "uivr_last_error", "uivr_set_scene",
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
-    "uivr_reset_counters", "uivr_get_counters", "uivr_get_launch_count", "uivr_set_variant",
+    "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
+    "uivr_set_variant",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
 ]
@@ -88,6 +89,7 @@ def lib():
         "uivr_set_counting": ([vp, C.c_int], C.c_int),
         "uivr_reset_counters": ([vp, vp], C.c_int),
         "uivr_get_counters": ([vp, C.POINTER(C.c_uint64), vp], C.c_int),
+        "uivr_get_kernel_ms": ([vp, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "uivr_get_launch_count": ([vp, C.POINTER(C.c_uint64)], C.c_int),
         "uivr_set_variant": ([vp, C.c_int], C.c_int),
         "uivr_test_neg_log1m": ([vp, fp, C.c_int, fp, vp], C.c_int),
@@ -212,6 +214,12 @@ class Context:
         out = (C.c_uint64 * len(COUNTER_NAMES))()
         self._check(self._L.uivr_get_counters(self._h, out, stream), "uivr_get_counters")
         return dict(zip(COUNTER_NAMES, (int(v) for v in out)))
+
+    def kernel_ms(self, which: int) -> float:
+        """CUDA-event time of the last path megakernel (0 = forward, 1 = backward)."""
+        out = C.c_float()
+        self._check(self._L.uivr_get_kernel_ms(self._h, int(which), C.byref(out)), "uivr_get_kernel_ms")
+        return float(out.value)
 
     def launch_count(self) -> int:
         out = C.c_uint64()

@@ -37,6 +37,10 @@ struct uivr_ctx {
     float* st_dsigma = nullptr;
     float* st_dalbedo = nullptr;
     size_t st_vox = 0, st_pix = 0;
+    bool st_params_valid = false;  // st_sigma / st_albedo hold the parameters of the last *_host call
+    // CUDA events bracketing the most recent path kernel: [0] forward, [1] backward
+    cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool ev_valid[2] = {false, false};
 };
 
 namespace {
@@ -177,7 +181,9 @@ int uivr_create(int device, uivr_ctx** out) {
         cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaMalloc(&ctx->counters, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess ||
         cudaMalloc(&ctx->work_counter, sizeof(unsigned int) * 4) != cudaSuccess ||
-        cudaMemset(ctx->counters, 0, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess) {
+        cudaMemset(ctx->counters, 0, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev[0][0]) != cudaSuccess || cudaEventCreate(&ctx->ev[0][1]) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev[1][0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1][1]) != cudaSuccess) {
         delete ctx;
         return UIVR_ERR_CUDA;
     }
@@ -191,6 +197,9 @@ int uivr_destroy(uivr_ctx* ctx) {
     cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
     delete ctx;
     return UIVR_OK;
 }
@@ -246,6 +255,15 @@ int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stre
     UIVR_CUDA(ctx, cudaMemcpyAsync(out, ctx->counters, sizeof(uint64_t) * UIVR_NUM_COUNTERS, cudaMemcpyDeviceToHost,
                                    (cudaStream_t) stream));
     UIVR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t) stream));
+    return UIVR_OK;
+}
+
+int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms) {
+    if (!ctx || !ms || which < 0 || which > 1) return UIVR_ERR_INVALID;
+    if (!ctx->ev_valid[which]) return fail(ctx, UIVR_ERR_STATE, "no path kernel of that kind has been launched");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    UIVR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which][1]));
+    UIVR_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
     return UIVR_OK;
 }
 
@@ -307,6 +325,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     UIVR_CUDA(ctx, cudaMemsetAsync(d_image, 0, nimg * sizeof(float), st));
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
     if (ctx->variant == 1) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_forward_v1<true>, kBlock, &grid))) return rc;
@@ -318,6 +337,8 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     } else {
         if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
+    ctx->ev_valid[0] = true;
     k_scale<<<ctx->num_sms * 4, kBlock, 0, st>>>(d_image, nimg, P.inv_spp);
     ctx->launches += 2;
     UIVR_CUDA(ctx, cudaGetLastError());
@@ -347,6 +368,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     int grid = 0;
     // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
     const bool quadratic = ctx->props.use_drt && !ctx->props.use_drt_subsampling;
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     if (ctx->variant == 1 || quadratic) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
@@ -358,6 +380,8 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     } else {
         if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
+    ctx->ev_valid[1] = true;
     ctx->launches += 1;
     UIVR_CUDA(ctx, cudaGetLastError());
     return UIVR_OK;
@@ -371,9 +395,11 @@ int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float*
     cudaStream_t st = (cudaStream_t) stream;
     int rc = ensure_staging(ctx);
     if (rc) return rc;
+    ctx->st_params_valid = false;
     UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
     UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
+    ctx->st_params_valid = true;
     if ((rc = uivr_render_forward(ctx, ctx->st_albedo, seed, spp, shard, ctx->st_image, nullptr, stream))) return rc;
     UIVR_CUDA(ctx, cudaMemcpyAsync(h_image, ctx->st_image, ctx->st_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     UIVR_CUDA(ctx, cudaStreamSynchronize(st));
@@ -383,16 +409,23 @@ int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float*
 int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo, const float* h_grad_image,
                               uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard, float* h_dsigma_t,
                               float* h_dalbedo, void* stream) {
-    if (!ctx || !h_sigma_t || !h_albedo || !h_grad_image || !h_dsigma_t || !h_dalbedo) return UIVR_ERR_INVALID;
+    if (!ctx || !h_grad_image || !h_dsigma_t || !h_dalbedo || (!h_sigma_t != !h_albedo)) return UIVR_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
     UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t) stream;
+    const size_t old_vox = ctx->st_vox;
     int rc = ensure_staging(ctx);
     if (rc) return rc;
-    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
-    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (h_sigma_t) {
+        ctx->st_params_valid = false;
+        UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
+        UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
+        ctx->st_params_valid = true;
+    } else if (!ctx->st_params_valid || old_vox != ctx->st_vox || !ctx->have_medium) {
+        return fail(ctx, UIVR_ERR_STATE, "no staged parameters: pass h_sigma_t / h_albedo, or call uivr_render_forward_host first");
+    }
     UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_gimage, h_grad_image, ctx->st_pix * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
     if ((rc = uivr_render_backward(ctx, ctx->st_albedo, ctx->st_gimage, seed_grad, spp_grad, shard, ctx->st_dsigma,
                                    ctx->st_dalbedo, nullptr, stream)))
         return rc;
