@@ -1,67 +1,75 @@
-"""IntegratorConfig surface of the reference (python/opt_config.py:83-169), same names / keys /
-error behaviour; `create()` returns the native-backed integrator instead of `mi.load_dict`."""
+"""Host mirror of the reference's `IntegratorConfig` surface (python/opt_config.py:83-169).
+
+Same field names, registry names, property keys and error behaviour (AssertionError on the
+same preconditions), so that `get_int_config(name).create(max_depth=...)` -- the call made at
+python/optimize.py:290 -- returns the native-backed integrator where the reference returns
+`mi.load_dict(...)`.  Written table-first: the registry below is data, `create` is the only
+logic.
+"""
 from __future__ import annotations
 
-from copy import deepcopy
-from dataclasses import dataclass
-from typing import Dict, Optional
+import copy
+import dataclasses
+from typing import Any, Dict, Optional, Union
 
 from .integrator import load_dict
 
+# rr_depth = max_depth + this: Russian roulette never fires (opt_config.py:103-106)
+_RR_OFFSET = 1000
 
-@dataclass
+
+@dataclasses.dataclass
 class IntegratorConfig:
+    """opt_config.py:83-95.  `params` is the plugin dictionary handed to `load_dict`."""
     name: str
     pretty_name: str
-    params: Dict
-
+    params: Dict[str, Any]
     uses_fd: bool = False
     fd_epsilon: Optional[float] = None
     fd_spp_multiplier: int = 16
 
     def __post_init__(self):
-        if self.uses_fd:
-            assert self.fd_epsilon is not None
+        assert not self.uses_fd or self.fd_epsilon is not None, "finite differences need fd_epsilon"
 
-    def create(self, **kwargs):
-        assert 'max_depth' in kwargs
-        d = deepcopy(self.params)
-        d.update(kwargs)
-
-        assert d['max_depth'] >= 0
-        # Russian roulette is unsupported: it never fires (opt_config.py:103-106)
-        assert 'rr_depth' not in kwargs
-        if 'rr_depth' not in self.params:
-            d['rr_depth'] = d['max_depth'] + 1000
-
-        return load_dict(d)
+    def create(self, **overrides):
+        """opt_config.py:97-108: merge overrides, require max_depth, forbid a caller rr_depth."""
+        assert "max_depth" in overrides, "create() requires max_depth"
+        assert "rr_depth" not in overrides, "rr_depth is not configurable (Russian roulette is unsupported)"
+        plugin = {**copy.deepcopy(self.params), **overrides}
+        assert plugin["max_depth"] >= 0
+        plugin.setdefault("rr_depth", plugin["max_depth"] + _RR_OFFSET)
+        return load_dict(plugin)
 
 
-_INTEGRATOR_CONFIGS: Dict[str, IntegratorConfig] = {}
+_REGISTRY: Dict[str, IntegratorConfig] = {}
 
 
-def add_int_config(name, **kwargs):
-    assert name not in _INTEGRATOR_CONFIGS, f'Duplicate integrator config name: {name}'
-    _INTEGRATOR_CONFIGS[name] = IntegratorConfig(name, **kwargs)
+def add_int_config(name: str, **fields) -> None:
+    """opt_config.py:112-114."""
+    assert name not in _REGISTRY, f"Duplicate integrator config name: {name}"
+    _REGISTRY[name] = IntegratorConfig(name, **fields)
 
 
-def get_int_config(name):
-    if isinstance(name, IntegratorConfig):
-        return deepcopy(name)
-    return deepcopy(_INTEGRATOR_CONFIGS[name])
+def get_int_config(name: Union[str, IntegratorConfig]) -> IntegratorConfig:
+    """opt_config.py:117-120: always hands out a private copy."""
+    src = name if isinstance(name, IntegratorConfig) else _REGISTRY[name]
+    return copy.deepcopy(src)
 
 
-add_int_config('fd-forward', pretty_name='Finite differences',
-               params={'type': 'volpathsimple', 'use_drt': False},
-               uses_fd=True, fd_epsilon=5e-3)
-add_int_config('volpathsimple-drt', pretty_name='Differential Ratio Tracking',
-               params={'type': 'volpathsimple', 'use_drt': True, 'use_drt_subsampling': True,
-                       'use_drt_mis': True})
-add_int_config('volpathsimple-drt-quadratic', pretty_name='Differential Ratio Tracking (quadratic)',
-               params={'type': 'volpathsimple', 'use_drt': True, 'use_drt_subsampling': False,
-                       'use_drt_mis': True})
-add_int_config('volpathsimple-basic', pretty_name='Free-flight based',
-               params={'type': 'volpathsimple', 'use_drt': False})
-# the emission-only ray marcher is a different estimator outside this build's hot path
-add_int_config('nerf', pretty_name='NeRF (grid-backed)',
-               params={'type': 'nerf', 'queries_per_ray': 128})
+def _vps(**flags) -> Dict[str, Any]:
+    return {"type": "volpathsimple", **flags}
+
+
+# opt_config.py:123-169 -- (registry name, pretty name, plugin params, extra fields)
+for _name, _pretty, _params, _extra in (
+    ("fd-forward", "Finite differences", _vps(use_drt=False), {"uses_fd": True, "fd_epsilon": 5e-3}),
+    ("volpathsimple-drt", "Differential Ratio Tracking",
+     _vps(use_drt=True, use_drt_subsampling=True, use_drt_mis=True), {}),
+    ("volpathsimple-drt-quadratic", "Differential Ratio Tracking (quadratic)",
+     _vps(use_drt=True, use_drt_subsampling=False, use_drt_mis=True), {}),
+    ("volpathsimple-basic", "Free-flight based", _vps(use_drt=False), {}),
+    # emission-only ray marcher: a different estimator, outside this build's hot path;
+    # load_dict raises NotImplementedError for it
+    ("nerf", "NeRF (grid-backed)", {"type": "nerf", "queries_per_ray": 128}, {}),
+):
+    add_int_config(_name, pretty_name=_pretty, params=_params, **_extra)
