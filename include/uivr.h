@@ -39,7 +39,8 @@ typedef enum {
     UIVR_ERR_INVALID = -1,    /* bad argument / precondition (reference: Python assert / raise) */
     UIVR_ERR_CUDA = -2,       /* CUDA runtime error */
     UIVR_ERR_STATE = -3,      /* call order (scene / medium not set) */
-    UIVR_ERR_NOMEM = -4
+    UIVR_ERR_NOMEM = -4,
+    UIVR_ERR_WATCHDOG = -5    /* the persistent kernel made no progress and aborted (results invalid) */
 } uivr_status;
 
 /* Scene: one medium box + perspective sensor + constant emitter.
@@ -138,9 +139,14 @@ int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stre
  * which = 0 forward (sample(Primal) kernel), 1 backward (primal replay + adjoint + DRT kernel).
  * Events are recorded on the stream the kernel was launched on; synchronises on the end event. */
 int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms);
+/* Synchronises `stream` and reports whether a persistent path kernel launched by this context
+ * has tripped its progress watchdog since the last check (UIVR_ERR_WATCHDOG; the record is
+ * cleared).  out (optional): 64 raw words of the record.  A healthy run never trips it. */
+int uivr_check_watchdog(uivr_ctx* ctx, uint32_t out[64], void* stream);
 /* number of kernel launches issued by this context so far */
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
-/* kernel variant: 0 = persistent lane-refill megakernel (default), 1 = one-sample-per-lane */
+/* kernel variant: 0 = persistent lane-refill megakernel, 1 = one-sample-per-lane,
+ * 2 = persistent slot-pool megakernel (CTA-wide compaction through shared-memory queues) */
 int uivr_set_variant(uivr_ctx* ctx, int variant);
 
 /* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */

@@ -23,7 +23,7 @@ EXPORTS = [
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
-    "uivr_set_variant",
+    "uivr_set_variant", "uivr_check_watchdog",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
 ]
@@ -92,6 +92,7 @@ def lib():
         "uivr_get_kernel_ms": ([vp, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "uivr_get_launch_count": ([vp, C.POINTER(C.c_uint64)], C.c_int),
         "uivr_set_variant": ([vp, C.c_int], C.c_int),
+        "uivr_check_watchdog": ([vp, C.POINTER(C.c_uint32), vp], C.c_int),
         "uivr_test_neg_log1m": ([vp, fp, C.c_int, fp, vp], C.c_int),
         "uivr_test_sincos2pi": ([vp, fp, C.c_int, fp, fp, vp], C.c_int),
         "uivr_test_sampler": ([vp, u32, u32, C.c_int, C.c_int, fp, vp], C.c_int),
@@ -213,6 +214,7 @@ class Context:
     def get_counters(self, stream: int = 0) -> dict:
         out = (C.c_uint64 * len(COUNTER_NAMES))()
         self._check(self._L.uivr_get_counters(self._h, out, stream), "uivr_get_counters")
+        self.check_watchdog(stream)
         return dict(zip(COUNTER_NAMES, (int(v) for v in out)))
 
     def kernel_ms(self, which: int) -> float:
@@ -220,6 +222,10 @@ class Context:
         out = C.c_float()
         self._check(self._L.uivr_get_kernel_ms(self._h, int(which), C.byref(out)), "uivr_get_kernel_ms")
         return float(out.value)
+
+    def check_watchdog(self, stream: int = 0):
+        """Synchronise and raise NativeError if a persistent kernel aborted on its progress watchdog."""
+        self._check(self._L.uivr_check_watchdog(self._h, None, stream), "uivr_check_watchdog")
 
     def launch_count(self) -> int:
         out = C.c_uint64()

@@ -9,6 +9,7 @@
 
 #include "uivr_kernels.cuh"
 #include "uivr_mega.cuh"
+#include "uivr_pool.cuh"
 
 using namespace uivr;
 
@@ -26,7 +27,8 @@ struct uivr_ctx {
     size_t maj_cells = 0;
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
-    int variant = 0;
+    unsigned int* debug = nullptr;  // [64] watchdog record of the slot-pool kernel
+    int variant = 2;
     int counting = 0;
     uint64_t launches = 0;
     // staging for the *_host entry points
@@ -126,6 +128,7 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     }
     P.counters = ctx->counters;
     P.work_counter = ctx->work_counter;
+    P.debug = ctx->debug;
     return UIVR_OK;
 }
 
@@ -181,6 +184,8 @@ int uivr_create(int device, uivr_ctx** out) {
         cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaMalloc(&ctx->counters, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess ||
         cudaMalloc(&ctx->work_counter, sizeof(unsigned int) * 4) != cudaSuccess ||
+        cudaMalloc(&ctx->debug, sizeof(unsigned int) * 64) != cudaSuccess ||
+        cudaMemset(ctx->debug, 0, sizeof(unsigned int) * 64) != cudaSuccess ||
         cudaMemset(ctx->counters, 0, sizeof(unsigned long long) * UIVR_NUM_COUNTERS) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[0][0]) != cudaSuccess || cudaEventCreate(&ctx->ev[0][1]) != cudaSuccess ||
         cudaEventCreate(&ctx->ev[1][0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1][1]) != cudaSuccess) {
@@ -194,7 +199,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
     for (int i = 0; i < 2; ++i)
@@ -237,7 +242,7 @@ int uivr_set_counting(uivr_ctx* ctx, int enable) {
 }
 
 int uivr_set_variant(uivr_ctx* ctx, int variant) {
-    if (!ctx || variant < 0 || variant > 1) return UIVR_ERR_INVALID;
+    if (!ctx || variant < 0 || variant > 2) return UIVR_ERR_INVALID;
     ctx->variant = variant;
     return UIVR_OK;
 }
@@ -265,6 +270,24 @@ int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms) {
     UIVR_CUDA(ctx, cudaEventSynchronize(ctx->ev[which][1]));
     UIVR_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
     return UIVR_OK;
+}
+
+int uivr_check_watchdog(uivr_ctx* ctx, uint32_t out[64], void* stream) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    uint32_t rec[64];
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(rec, ctx->debug, sizeof(rec), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    UIVR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t) stream));
+    if (out) memcpy(out, rec, sizeof(rec));
+    if (rec[0] == 0u) return UIVR_OK;
+    char msg[512];
+    int n = snprintf(msg, sizeof(msg), "slot-pool kernel watchdog tripped: reason 0x%x, block %u thread %u; queues (head,tail,count):",
+                     rec[0], rec[1], rec[2]);
+    for (int q = 0; q < Q_NUM && n < (int) sizeof(msg) - 40; ++q)
+        n += snprintf(msg + n, sizeof(msg) - n, " q%d(%u,%u,%d)", q, rec[4 + 3 * q], rec[5 + 3 * q], (int) rec[6 + 3 * q]);
+    snprintf(msg + n, sizeof(msg) - n, " live %d exhausted %u", (int) rec[4 + 3 * Q_NUM], rec[5 + 3 * Q_NUM]);
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->debug, 0, sizeof(rec), (cudaStream_t) stream));
+    return fail(ctx, UIVR_ERR_WATCHDOG, msg);
 }
 
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out) {
@@ -334,6 +357,8 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
             if ((rc = persistent_grid(ctx, k_forward_v1<false>, kBlock, &grid))) return rc;
             k_forward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
+    } else if (ctx->variant == 2 && ctx->props.max_depth < 65536) {
+        if ((rc = launch_pool(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
         if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }
@@ -377,6 +402,8 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             if ((rc = persistent_grid(ctx, k_backward_v1<false>, kBlock, &grid))) return rc;
             k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
+    } else if (ctx->variant == 2 && ctx->props.max_depth < 65536) {
+        if ((rc = launch_pool(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
         if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }

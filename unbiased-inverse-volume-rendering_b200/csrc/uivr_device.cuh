@@ -53,6 +53,7 @@ struct Params {
     float* dalbedo;           // [Z,Y,X,3]
     unsigned long long* counters;
     unsigned int* work_counter;
+    unsigned int* debug;      // [64] watchdog record of the slot-pool kernel (word 0 != 0: tripped)
 };
 
 // --------------------------------------------------------------------------------------

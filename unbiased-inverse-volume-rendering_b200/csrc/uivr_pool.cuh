@@ -1,0 +1,854 @@
+// uivr_pool.cuh -- variant 2: persistent SLOT-POOL megakernel (sm_100a).
+//
+// Why: in the lane-refill megakernel (uivr_mega.cuh) every lane keeps its sample in registers,
+// so a warp can only batch the <= 32 samples it owns; ncu shows the transition handlers
+// (vertex / NEE end / path end / fetch) running with ~4 of 32 lanes active and 37 % of the
+// stall samples waiting for instruction fetch (profiles/r01_*).  Here ONE CTA per SM owns a
+// pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA, field-major),
+// and every state of the per-sample state machine has a CTA-wide queue of slot ids:
+//
+//      Q_FREE -> [fetch] -> Q_WALK -> [walk] -> Q_VERTEX -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK ...
+//                                            -> Q_NEE_END / Q_PATH_END -> ... -> Q_FREE
+//
+// Any warp can serve any queue: it pops up to 32 slot ids (normally a FULL batch), loads only
+// the fields that handler needs from the pool, and pushes the slots on to their next queue --
+// compaction of live rays across all 16 warps of the CTA instead of within one warp.  The
+// free-flight walk (the hot loop: branch-free supergrid DDA + batched sigma_t taps) keeps ITS
+// state in registers: every lane of every warp is a walker that is refilled from Q_WALK as soon
+// as kWalkQuantum lanes of the warp have finished.
+//
+// Per-sample arithmetic, RNG draw order and handler logic are exactly those of uivr_mega.cuh /
+// uivr_path.cuh (= volpathsimple.py), so results stay bit-identical per sample.
+#pragma once
+
+#include "uivr_kernels.cuh"
+
+namespace uivr {
+
+constexpr int kPoolBlock = 512;
+constexpr int kPoolRing = 1024;      // ring capacity per queue (>= NSLOT, power of two)
+constexpr int kWalkQuantum = 8;      // the walk loop returns once this many lanes have finished
+constexpr int kPoolTapBatch = 8;     // tentative collisions are evaluated when this many lanes wait
+constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
+constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
+constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
+constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
+
+enum : int { Q_FREE = 0, Q_WALK, Q_VERTEX, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
+enum : int { PM_DELTA = 0, PM_NEE, PM_NEE_ADJ, PM_DRT };
+enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
+
+// pool fields (one 32-bit word per slot each)
+enum : int {
+    F_IDX = 0, F_PIX, F_RNG_LO, F_RNG_HI, F_INC_LO, F_INC_HI,
+    F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TMAX, F_WT,
+    F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_ST, F_T, F_FLAGS, F_DEPTH, F_VPX, F_VPY, F_VPZ,
+    F_NUM_FWD,
+    // adjoint-only state
+    F_ALT_LO = F_NUM_FWD, F_ALT_HI, F_AINC_LO, F_AINC_HI, F_CLONE_LO, F_CLONE_HI,
+    F_DL0, F_DL1, F_DL2, F_ASUM,
+    F_RSW0, F_RSW1, F_RSW2, F_RSC0, F_RSC1, F_RSC2,
+    F_RSOX, F_RSOY, F_RSOZ, F_RSDX, F_RSDY, F_RSDZ, F_RSTMAX,
+    F_DRT_D, F_DRT_T, F_DRT_ST, F_LI0, F_LI1, F_LI2, F_AL0, F_AL1, F_AL2,
+    F_NUM_BWD
+};
+
+// F_FLAGS bits
+enum : unsigned {
+    FL_PASS_MASK = 3u, FL_MODE_SHIFT = 2, FL_MODE_MASK = 3u << 2,
+    FL_DID_SCATTER = 1u << 4, FL_ESCAPED = 1u << 5, FL_HAS_SCATTERED = 1u << 6, FL_ACTIVE = 1u << 7,
+    FL_NEE_VALID = 1u << 8, FL_RS_VALID = 1u << 9, FL_DRT_FOUND = 1u << 10, FL_SPAWN_PHASE = 1u << 11,
+    FL_RESTART = 1u << 12
+};
+
+struct PoolCtl {
+    unsigned head[Q_NUM];
+    unsigned tail[Q_NUM];
+    int count[Q_NUM];
+    int live;        // slots that may still carry work
+    int exhausted;   // the global sample queue is empty
+    int abort;       // watchdog tripped: every warp leaves
+};
+
+template <bool BWD, int NSLOT>
+constexpr size_t pool_smem_bytes() {
+    return 128 + (size_t) Q_NUM * kPoolRing * sizeof(unsigned) +
+           (size_t) (BWD ? F_NUM_BWD : F_NUM_FWD) * NSLOT * sizeof(uint32_t);
+}
+
+template <bool BWD, bool COUNT, int NSLOT>
+__global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
+    static_assert(NSLOT <= kPoolRing && NSLOT < 0xFFFF, "ring too small");
+    static_assert(sizeof(PoolCtl) <= 128, "PoolCtl must fit its 128-byte header");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PoolCtl* const ctl = reinterpret_cast<PoolCtl*>(smem_raw);
+    unsigned* const ring = reinterpret_cast<unsigned*>(smem_raw + 128);  // one mailbox cell per ring position
+    uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * kPoolRing * sizeof(unsigned));
+
+    Counters<COUNT> K;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint64_t total = (uint64_t) P.n_slots * P.spp;
+    const bool use_rsv = BWD && P.use_drt && P.use_drt_subsampling;
+
+#define PU(f, s) pool[(f) * NSLOT + (s)]
+#define PF(f, s) __uint_as_float(pool[(f) * NSLOT + (s)])
+#define PSET(f, s, v) pool[(f) * NSLOT + (s)] = __float_as_uint(v)
+
+    // ---- pool / queue initialisation: every slot starts in Q_FREE ----
+    for (int i = threadIdx.x; i < Q_NUM * kPoolRing; i += kPoolBlock)
+        ring[i] = (i < NSLOT) ? (unsigned) i : kPoolEmpty;   // ring 0 == Q_FREE
+    for (int i = threadIdx.x; i < NSLOT; i += kPoolBlock) PU(F_FLAGS, i) = 0u;
+    if (threadIdx.x < Q_NUM) {
+        ctl->head[threadIdx.x] = 0u;
+        ctl->tail[threadIdx.x] = threadIdx.x == Q_FREE ? (unsigned) NSLOT : 0u;
+        ctl->count[threadIdx.x] = threadIdx.x == Q_FREE ? NSLOT : 0;
+    }
+    if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; }
+    __syncthreads();
+
+    // ---- queue primitives (warp-collective; each is instantiated ONCE to keep the code small) ----
+    // watchdog: a tripped limit records the reason + queue state and makes every warp leave
+    auto trip = [&](unsigned why) {
+        if (atomicExch(&ctl->abort, 1) == 0 && P.debug) {
+            if (atomicExch(&P.debug[0], why) == 0u) {
+                P.debug[1] = blockIdx.x;
+                P.debug[2] = threadIdx.x;
+                for (int q = 0; q < Q_NUM; ++q) {
+                    P.debug[4 + 3 * q] = ctl->head[q];
+                    P.debug[5 + 3 * q] = ctl->tail[q];
+                    P.debug[6 + 3 * q] = (unsigned) ctl->count[q];
+                }
+                P.debug[4 + 3 * Q_NUM] = (unsigned) ctl->live;
+                P.debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
+            }
+        }
+    };
+    // pops up to `want` ids from queue q (all-or-nothing when `exact`); lane i < got receives one
+    auto q_pop = [&](int q, int want, bool exact, unsigned& slot) -> int {
+        int got = 0;
+        unsigned base = 0;
+        if (lane == 0) {
+            const int old = atomicSub(&ctl->count[q], want);
+            got = old >= want ? want : ((exact || old <= 0) ? 0 : old);
+            if (got < want) atomicAdd(&ctl->count[q], want - got);
+            if (got) base = atomicAdd(&ctl->head[q], (unsigned) got);
+        }
+        got = __shfl_sync(FULL, got, 0);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int) lane < got) {
+            unsigned* cell = &ring[q * kPoolRing + ((base + lane) & (kPoolRing - 1))];
+            unsigned v;
+            int spins = 0;
+            // the position is reserved by a producer; its store may still be in flight
+            while ((v = atomicExch(cell, kPoolEmpty)) == kPoolEmpty) {
+                if (++spins > kPoolSpinLimit) { trip(0x200u + (unsigned) q); v = 0; break; }
+            }
+            slot = v;
+        }
+        __threadfence_block();
+        return got;
+    };
+
+    // ---- walker state (registers; one walk job per lane) ----
+    int wslot = -1;            // pool slot this lane walks for, -1 = idle
+    bool walking = false;      // the walk is in progress
+    bool pending = false;      // a tentative collision at `wt` waits for its sigma_t tap
+    unsigned wflags = 0;
+    int mode = PM_DELTA;
+    Rng rng;
+    rng.state = rng.inc = 0;
+    float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f, tmax = 0.0f;
+    float wt = 0.0f, tnx = 0.0f, tny = 0.0f, tnz = 0.0f, sb = 0.0f, tau = 0.0f;
+    float adx = 0.0f, ady = 0.0f, adz = 0.0f;
+    int cx = 0, cy = 0, cz = 0;
+    float T = 1.0f, asum = 0.0f, sigma_t = 0.0f;
+    float drt_D = 0.0f, drt_t = 0.0f, drt_st = 0.0f;
+    bool drt_found = false, did_scatter = false;
+
+    long long t_progress = clock64();
+    for (;;) {
+        if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
+        // per-queue fill levels, one queue per lane
+        const int cnt = (lane < Q_NUM) ? *((volatile int*) &ctl->count[lane]) : 0;
+
+        // ==============================================================================
+        // 1. refill idle walker lanes from Q_WALK
+        // ==============================================================================
+        {
+            const unsigned idle = __ballot_sync(FULL, wslot < 0);
+            if (idle && __shfl_sync(FULL, cnt, Q_WALK) > 0) {
+                unsigned got_slot = 0;
+                const int got = q_pop(Q_WALK, __popc(idle), false, got_slot);
+                if (got) {
+                    const int rank = __popc(idle & lt_mask);
+                    const unsigned s = __shfl_sync(FULL, got_slot, rank & 31);
+                    if (wslot < 0 && rank < got) {
+                        wslot = (int) s;
+                        wflags = PU(F_FLAGS, s);
+                        mode = (int) ((wflags & FL_MODE_MASK) >> FL_MODE_SHIFT);
+                        rng.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
+                        rng.inc = (uint64_t) PU(F_INC_LO, s) | ((uint64_t) PU(F_INC_HI, s) << 32);
+                        ox = PF(F_OX, s); oy = PF(F_OY, s); oz = PF(F_OZ, s);
+                        dx = PF(F_DX, s); dy = PF(F_DY, s); dz = PF(F_DZ, s);
+                        tmax = PF(F_TMAX, s);
+                        T = 1.0f;
+                        drt_D = 0.0f;
+                        drt_found = false;
+                        did_scatter = false;
+                        if (BWD) asum = PF(F_ASUM, s);
+                        // walk_init (Medium::sample_interaction set-up, App. B.5)
+                        const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
+                        const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
+                        const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
+                        wt = 0.0f;
+                        walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
+                        walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
+                        walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
+                        adx = fabsf(P.mcs[0] * ix);
+                        ady = fabsf(P.mcs[1] * iy);
+                        adz = fabsf(P.mcs[2] * iz);
+                        sb = majorant_at<COUNT>(P, cx, cy, cz, K);
+                        tau = neg_log1m(draw(rng, K));
+                        walking = true;
+                        pending = false;
+                    }
+                }
+            }
+        }
+
+        // ==============================================================================
+        // 2. schedule ONE work item: a FULL batch of a transition queue if there is one, else a walk
+        //    quantum, else (only once the global sample queue is exhausted) a partial batch.
+        //    Before exhaustion no slot retires, so "no full queue and nothing to walk anywhere"
+        //    cannot happen: NSLOT > (Q_NUM - 1) * 31 slots cannot all sit in non-full queues.
+        // ==============================================================================
+        const unsigned m_walk = __ballot_sync(FULL, walking);
+        int work = -1;
+        bool exact = true;
+        {
+            const unsigned fullq = __ballot_sync(FULL, cnt >= 32) & ~(1u << Q_WALK);
+            if (fullq) {
+                work = __ffs(fullq) - 1;
+            } else if (m_walk) {
+                work = Q_WALK;
+            } else {
+                const unsigned some = __ballot_sync(FULL, cnt > 0) & ~(1u << Q_WALK);
+                if (some && __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0)) {
+                    work = __ffs(some) - 1;
+                    exact = false;
+                }
+            }
+        }
+        if (work < 0) {
+            if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
+            if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
+            __nanosleep(100);
+            continue;
+        }
+        t_progress = clock64();
+
+        // per-lane result of the work item: slot `s` goes to queue `next` (-1: nothing to route)
+        unsigned s = 0;
+        int next = -1;
+        // gradient scatter request of the handlers (executed at one site below)
+        bool sc_taps = false, sc_ff = false;
+        float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
+        float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
+        float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
+        Rng alt;
+        alt.state = alt.inc = 0;
+
+        if (work == Q_WALK) {
+            // ==========================================================================
+            // 3. walk quantum: free-flight walk over the majorant supergrid (Medium::
+            //    sample_interaction and its ratio-tracking / DRT siblings) until kWalkQuantum
+            //    lanes have finished
+            // ==========================================================================
+            const int n0 = __popc(m_walk);
+            const int n_stop = n0 > kWalkQuantum ? n0 - kWalkQuantum : 0;
+            for (int guard = 0;; ++guard) {
+                if (guard > kPoolWalkLimit) { trip(0x400u); walking = false; pending = false; break; }
+                // ---- one supergrid cell per iteration (branch-free DDA) ----
+                if (walking && !pending) {
+                    const bool yx = tny < tnx;
+                    float tn = yx ? tny : tnx;
+                    const bool zb = tnz < tn;
+                    tn = zb ? tnz : tn;
+                    const float t_end = tn < tmax ? tn : tmax;
+                    float len = t_end - wt;
+                    len = len < 0.0f ? 0.0f : len;
+                    const float dtau = sb * len;
+                    if (sb > 0.0f && tau < dtau) {
+                        float t = wt + tau / sb;
+                        wt = t > t_end ? t_end : t;
+                        pending = true;
+                    } else {
+                        if (sb > 0.0f) tau -= dtau;
+                        wt = t_end > wt ? t_end : wt;
+                        bool end = !(tn < tmax);
+                        const bool a0 = !zb && !yx, a1 = !zb && yx;
+                        const int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1, sz = dz > 0.0f ? 1 : -1;
+                        cx += a0 ? sx : 0;
+                        cy += a1 ? sy : 0;
+                        cz += zb ? sz : 0;
+                        tnx = a0 ? tnx + adx : tnx;
+                        tny = a1 ? tny + ady : tny;
+                        tnz = zb ? tnz + adz : tnz;
+                        end = end || (unsigned) cx >= (unsigned) P.mres[0] || (unsigned) cy >= (unsigned) P.mres[1] ||
+                              (unsigned) cz >= (unsigned) P.mres[2];
+                        if (end) walking = false;  // segment end: no (further) collision
+                        else sb = majorant_at<COUNT>(P, cx, cy, cz, K);
+                    }
+                }
+                const int n_walk = __popc(__ballot_sync(FULL, walking));
+                const int n_pend = __popc(__ballot_sync(FULL, pending));
+                const bool leave = n_walk <= n_stop;
+                // ---- tentative collisions: sigma_t tap + per-mode decision ----
+                if (n_pend >= kPoolTapBatch || (n_pend > 0 && (n_pend == n_walk || leave))) {
+                    if (pending) {
+                        pending = false;
+                        const float px = fmaf(wt, dx, ox), py = fmaf(wt, dy, oy), pz = fmaf(wt, dz, oz);
+                        float u2 = 0.0f;
+                        if (mode == PM_DRT) u2 = draw(rng, K);
+                        const float st = sigma_tap(P, px, py, pz);
+                        K.add(C_SIGMA, 1);
+                        bool cont = true;
+                        if (mode == PM_DELTA) {
+                            // :354-361 real vs null collision
+                            const float r = st / sb;
+                            if (!(draw(rng, K) >= r)) {
+                                did_scatter = true;
+                                sigma_t = st;
+                                cont = false;
+                            }
+                        } else if (mode == PM_DRT) {
+                            // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
+                            const float wi = T / sb;
+                            drt_D += wi;
+                            if (u2 <= wi / drt_D) {
+                                drt_t = wt;
+                                drt_st = st;
+                                drt_found = true;
+                            }
+                            T *= (sb - st) / sb;
+                            if (!(T > 0.0f)) cont = false;
+                        } else {
+                            // ratio tracking (:461-502); PM_NEE_ADJ scatters -sum(adj)/sigma_n (:483-492)
+                            const float sn = sb - st;
+                            const float tr = sn / sb;
+                            if (BWD && mode == PM_NEE_ADJ && tr > 0.0f) {
+                                scatter_sigma(P, px, py, pz, -asum / sn);
+                                K.add(C_SSCAT, 1);
+                            }
+                            T *= tr;
+                            if (T == 0.0f) cont = false;
+                        }
+                        if (cont) tau = neg_log1m(draw(rng, K));
+                        else walking = false;
+                    }
+                    if (leave || __ballot_sync(FULL, walking) == 0u) break;
+                } else if (leave) {
+                    break;
+                }
+            }
+            // ---- write back finished walks; the slot goes on to its next queue ----
+            if (wslot >= 0 && !walking) {
+                s = (unsigned) wslot;
+                PU(F_RNG_LO, s) = (uint32_t) rng.state;
+                PU(F_RNG_HI, s) = (uint32_t) (rng.state >> 32);
+                PSET(F_WT, s, wt);
+                if (mode == PM_DELTA) {
+                    PSET(F_ST, s, sigma_t);
+                    PU(F_FLAGS, s) = did_scatter ? (wflags | FL_DID_SCATTER) : (wflags & ~FL_DID_SCATTER);
+                    next = Q_VERTEX;
+                } else if (mode == PM_NEE) {
+                    PSET(F_T, s, T);
+                    next = Q_NEE_END;
+                } else if (BWD && mode == PM_NEE_ADJ) {
+                    PU(F_FLAGS, s) = wflags | FL_SPAWN_PHASE;
+                    next = Q_SPAWN;
+                } else if (BWD) {
+                    PSET(F_DRT_D, s, drt_D); PSET(F_DRT_T, s, drt_t); PSET(F_DRT_ST, s, drt_st);
+                    PU(F_FLAGS, s) = drt_found ? (wflags | FL_DRT_FOUND) : (wflags & ~FL_DRT_FOUND);
+                    next = Q_VERTEX;  // the vertex handler serves the DRT vertex as well
+                }
+                wslot = -1;
+            }
+        } else {
+            // ==========================================================================
+            // 4. transition handlers (one batch of up to 32 slots of queue `work`)
+            // ==========================================================================
+            const int got = q_pop(work, 32, exact, s);
+            const bool act = (int) lane < got;
+            if (work == Q_VERTEX) {
+                // ---- end of a delta-tracking segment (:130-245) or of the DRT walk (:550-558) ----
+                if (act) {
+                    unsigned fl = PU(F_FLAGS, s);
+                    const unsigned dw = PU(F_DEPTH, s);
+                    int depth = (int) (dw & 0xFFFFu);
+                    const int pass = (int) (fl & FL_PASS_MASK);
+                    const bool is_drt = BWD && ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT) == (unsigned) PM_DRT;
+                    const bool ds = is_drt ? (fl & FL_DRT_FOUND) != 0u : (fl & FL_DID_SCATTER) != 0u;
+                    // vertex position: on the stored reservoir segment for DRT, else on the current segment
+                    const int fo = is_drt ? F_RSOX : F_OX, fd = is_drt ? F_RSDX : F_DX;
+                    const float sox = PF(fo, s), soy = PF(fo + 1, s), soz = PF(fo + 2, s);
+                    const float sdx = PF(fd, s), sdy = PF(fd + 1, s), sdz = PF(fd + 2, s);
+                    const float swt = PF(is_drt ? F_DRT_T : F_WT, s);
+                    const float vx = fmaf(swt, sdx, sox), vy = fmaf(swt, sdy, soy), vz = fmaf(swt, sdz, soz);
+                    float albedo[3] = {1.0f, 1.0f, 1.0f};
+                    if (ds) {
+                        albedo_tap(P, vx, vy, vz, albedo);
+                        K.add(C_ALBEDO, 1);
+                        PSET(F_VPX, s, vx); PSET(F_VPY, s, vy); PSET(F_VPZ, s, vz);
+                    }
+                    if (is_drt) {
+                        if (ds) {
+                            PSET(F_AL0, s, albedo[0]); PSET(F_AL1, s, albedo[1]); PSET(F_AL2, s, albedo[2]);
+                            PSET(F_LI0, s, 0.0f); PSET(F_LI1, s, 0.0f); PSET(F_LI2, s, 0.0f);
+                            PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
+                            fl = (fl & ~FL_PASS_MASK) | (unsigned) PP_DRTV;
+                            fl = P.use_nee ? (fl & ~FL_SPAWN_PHASE) : (fl | FL_SPAWN_PHASE);
+                            next = Q_SPAWN;
+                        } else {
+                            fl &= ~FL_RESTART;
+                            next = Q_FREE;
+                        }
+                    } else {
+                        const float stmax = PF(F_TMAX, s);
+                        const float beta[3] = {PF(F_B0, s), PF(F_B1, s), PF(F_B2, s)};
+                        if (ds) {
+                            fl |= FL_HAS_SCATTERED;
+                            K.add(C_REAL, 1);
+                        }
+                        if (BWD && pass == PP_ADJ) {
+                            alt.state = (uint64_t) PU(F_ALT_LO, s) | ((uint64_t) PU(F_ALT_HI, s) << 32);
+                            alt.inc = (uint64_t) PU(F_AINC_LO, s) | ((uint64_t) PU(F_AINC_HI, s) << 32);
+                            const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
+                            const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
+                            const float st = PF(F_ST, s);
+                            if (use_rsv) {
+                                // DRTReservoir.update (:745-753), weight = throughput before this vertex
+                                const float u = draw(alt, K);
+                                float wsum[3] = {PF(F_RSW0, s), PF(F_RSW1, s), PF(F_RSW2, s)};
+                                float ratio[3];
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    wsum[c] += beta[c];
+                                    ratio[c] = beta[c] / wsum[c];
+                                }
+                                PSET(F_RSW0, s, wsum[0]); PSET(F_RSW1, s, wsum[1]); PSET(F_RSW2, s, wsum[2]);
+                                if (u <= mean3(ratio)) {
+                                    PSET(F_RSC0, s, beta[0]); PSET(F_RSC1, s, beta[1]); PSET(F_RSC2, s, beta[2]);
+                                    PSET(F_RSOX, s, sox); PSET(F_RSOY, s, soy); PSET(F_RSOZ, s, soz);
+                                    PSET(F_RSDX, s, sdx); PSET(F_RSDY, s, sdy); PSET(F_RSDZ, s, sdz);
+                                    PSET(F_RSTMAX, s, stmax);
+                                    PU(F_DEPTH, s) = (dw & 0xFFFFu) | ((unsigned) depth << 16);
+                                    fl |= FL_RS_VALID;
+                                }
+                            }
+                            // :152-172 free-flight scattering gradient
+                            if ((!P.use_drt || P.use_drt_mis) && ds) {
+                                float m = 1.0f;
+                                if (P.use_drt && P.use_drt_mis) {
+                                    const float s2 = st * st;
+                                    m = s2 / (1.0f + s2);
+                                }
+                                const float inv_pdf = 1.0f / st;
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    const float Li = R[c] / (albedo[c] > 1e-8f ? albedo[c] : 1e-8f);
+                                    const float term = ((m * dL[c]) * Li) * inv_pdf;
+                                    sc_gs = fmaf(term, albedo[c], sc_gs);
+                                    sc_ga[c] = term * st;
+                                }
+                                sc_ff = true;
+                                sc_vx = vx; sc_vy = vy; sc_vz = vz;
+                            }
+                            // :181-189, :584-607 transmittance gradient: 4 uniform taps on the segment
+                            sc_int = ds ? swt : stmax;
+                            const float aw = fmaf(dL[2], R[2], fmaf(dL[1], R[1], dL[0] * R[0]));
+                            sc_g = -(aw * (sc_int * 0.25f));
+                            sc_ox = sox; sc_oy = soy; sc_oz = soz; sc_dx = sdx; sc_dy = sdy; sc_dz = sdz;
+                            sc_taps = true;
+                        }
+                        // :193-200
+                        if (ds) {
+                            PSET(F_B0, s, beta[0] * albedo[0]);
+                            PSET(F_B1, s, beta[1] * albedo[1]);
+                            PSET(F_B2, s, beta[2] * albedo[2]);
+                            depth += 1;
+                        }
+                        const bool active = ds && (depth < P.max_depth);
+                        fl = active ? (fl | FL_ACTIVE) : (fl & ~FL_ACTIVE);
+                        if (!ds) {
+                            fl |= FL_ESCAPED;  // :244-245
+                            next = Q_PATH_END;
+                        } else {
+                            fl = (P.use_nee && active) ? (fl & ~FL_SPAWN_PHASE) : (fl | FL_SPAWN_PHASE);
+                            next = Q_SPAWN;
+                        }
+                        PU(F_DEPTH, s) = (PU(F_DEPTH, s) & 0xFFFF0000u) | (unsigned) depth;
+                    }
+                    PU(F_FLAGS, s) = fl;
+                }
+            } else if (work == Q_NEE_END) {
+                // ---- sample_emitter_for_nee (:380-403) ----
+                if (act) {
+                    unsigned fl = PU(F_FLAGS, s);
+                    const int pass = (int) (fl & FL_PASS_MASK);
+                    const float Tn = PF(F_T, s);
+                    float contrib[3];
+                    contrib[0] = (PF(F_B0, s) * P.half_le[0]) * Tn;
+                    contrib[1] = (PF(F_B1, s) * P.half_le[1]) * Tn;
+                    contrib[2] = (PF(F_B2, s) * P.half_le[2]) * Tn;
+                    next = Q_SPAWN;
+                    if (BWD && pass == PP_DRTV) {
+                        PSET(F_LI0, s, contrib[0]); PSET(F_LI1, s, contrib[1]); PSET(F_LI2, s, contrib[2]);
+                    } else if (BWD && pass == PP_ADJ) {
+                        PSET(F_R0, s, PF(F_R0, s) - contrib[0]);  // path replay (:214)
+                        PSET(F_R1, s, PF(F_R1, s) - contrib[1]);
+                        PSET(F_R2, s, PF(F_R2, s) - contrib[2]);
+                        if (fl & FL_NEE_VALID) {
+                            const float a = (PF(F_DL0, s) * contrib[0] + PF(F_DL1, s) * contrib[1]) + PF(F_DL2, s) * contrib[2];
+                            PSET(F_ASUM, s, a);
+                            PU(F_RNG_LO, s) = PU(F_CLONE_LO, s);  // the replay consumes exactly the same draws again
+                            PU(F_RNG_HI, s) = PU(F_CLONE_HI, s);
+                            fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE_ADJ << FL_MODE_SHIFT);
+                            next = Q_WALK;
+                        }
+                    } else {
+                        PSET(F_R0, s, PF(F_R0, s) + contrib[0]);
+                        PSET(F_R1, s, PF(F_R1, s) + contrib[1]);
+                        PSET(F_R2, s, PF(F_R2, s) + contrib[2]);
+                    }
+                    if (next == Q_SPAWN) fl |= FL_SPAWN_PHASE;
+                    PU(F_FLAGS, s) = fl;
+                }
+            } else if (work == Q_PATH_END) {
+                if (act) {
+                    unsigned fl = PU(F_FLAGS, s);
+                    const int pass = (int) (fl & FL_PASS_MASK);
+                    const unsigned dw = PU(F_DEPTH, s);
+                    const int depth = (int) (dw & 0xFFFFu);
+                    float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
+                    if (pass == PP_PRIMAL || (BWD && pass == PP_REC)) {
+                        // :263-285 envmap
+                        if ((fl & FL_ESCAPED) && !(depth <= 0 && P.hide_emitters)) {
+                            const float wmis = (P.use_nee && (fl & FL_HAS_SCATTERED)) ? 0.5f : 1.0f;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) R[c] = fmaf(PF(F_B0 + c, s) * wmis, P.radiance[c], R[c]);
+                        }
+                    }
+                    next = Q_FREE;
+                    fl &= ~FL_RESTART;
+                    if (pass == PP_PRIMAL) {
+                        const uint32_t idx = PU(F_IDX, s), pix = PU(F_PIX, s);
+                        if (P.sample_L) {
+                            P.sample_L[3 * (size_t) idx + 0] = R[0];
+                            P.sample_L[3 * (size_t) idx + 1] = R[1];
+                            P.sample_L[3 * (size_t) idx + 2] = R[2];
+                        }
+                        if (!BWD) {
+                            atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                            atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                            atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                        } else {
+                            // batched.py:309-318: sample(Backward, state_in = L)
+                            PSET(F_R0, s, R[0]); PSET(F_R1, s, R[1]); PSET(F_R2, s, R[2]);
+                            fl = (fl & ~FL_PASS_MASK) | (unsigned) PP_ADJ | FL_RESTART;
+                        }
+                    } else if (BWD && pass == PP_ADJ) {
+                        if (use_rsv && (fl & FL_RS_VALID)) {
+                            // DRTReservoir.get (:756-760) and adjoint = weight * dL (:255)
+                            const float wcur[3] = {PF(F_RSC0, s), PF(F_RSC1, s), PF(F_RSC2, s)};
+                            const float wsum[3] = {PF(F_RSW0, s), PF(F_RSW1, s), PF(F_RSW2, s)};
+                            const float d = mean3(wcur), ws = mean3(wsum);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float W = (d != 0.0f) ? (ws * wcur[c]) / d : 0.0f;
+                                PSET(F_DL0 + c, s, W * PF(F_DL0 + c, s));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 7; ++k) PU(F_OX + k, s) = PU(F_RSOX + k, s);  // o, d, tmax
+                            PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (dw >> 16);
+                            // everything from here on draws from the alt stream
+                            PU(F_RNG_LO, s) = PU(F_ALT_LO, s); PU(F_RNG_HI, s) = PU(F_ALT_HI, s);
+                            PU(F_INC_LO, s) = PU(F_AINC_LO, s); PU(F_INC_HI, s) = PU(F_AINC_HI, s);
+                            fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DRT << FL_MODE_SHIFT);
+                            next = Q_WALK;
+                        }
+                    } else if (BWD) {  // PP_REC: Li complete -> DRT gradient (:571-581)
+                        const float dst = PF(F_DRT_ST, s), dD = PF(F_DRT_D, s), dt = PF(F_DRT_T, s);
+                        const float m = P.use_drt_mis ? 1.0f / (1.0f + dst * dst) : 1.0f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float Li = PF(F_LI0 + c, s) + R[c];
+                            const float term = ((m * dD) * PF(F_DL0 + c, s)) * Li;
+                            sc_gs = fmaf(term, PF(F_AL0 + c, s), sc_gs);
+                            sc_ga[c] = term * dst;
+                        }
+                        sc_vx = fmaf(dt, PF(F_RSDX, s), PF(F_RSOX, s));
+                        sc_vy = fmaf(dt, PF(F_RSDY, s), PF(F_RSOY, s));
+                        sc_vz = fmaf(dt, PF(F_RSDZ, s), PF(F_RSOZ, s));
+                        sc_ff = true;
+                    }
+                    PU(F_FLAGS, s) = fl;
+                }
+            } else if (work == Q_SPAWN) {
+                // ---- emitter sampling (:406-433) / phase sampling (:221-245, :626-652) ----
+                if (act) {
+                    unsigned fl = PU(F_FLAGS, s);
+                    const bool phase = (fl & FL_SPAWN_PHASE) != 0u;
+                    Rng r;
+                    r.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
+                    r.inc = (uint64_t) PU(F_INC_LO, s) | ((uint64_t) PU(F_INC_HI, s) << 32);
+                    if (phase) draw(r, K);
+                    const float xi1 = draw(r, K), xi2 = draw(r, K);
+                    float wx, wy, wz;
+                    uniform_sphere(xi1, xi2, wx, wy, wz);
+                    Seg sg;
+                    const bool ok = make_segment(P, PF(F_VPX, s), PF(F_VPY, s), PF(F_VPZ, s), wx, wy, wz, sg);
+                    PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
+                    PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
+                    PSET(F_TMAX, s, sg.tmax);
+                    bool active = (fl & FL_ACTIVE) != 0u;
+                    bool rr = false;  // Russian-roulette draw + zero-throughput test of the next loop iteration
+                    if (!phase) {
+                        if (BWD) {
+                            // sampler.clone() position for the adjoint replay (:383)
+                            PU(F_CLONE_LO, s) = (uint32_t) r.state;
+                            PU(F_CLONE_HI, s) = (uint32_t) (r.state >> 32);
+                        }
+                        fl = ok ? (fl | FL_NEE_VALID) : (fl & ~FL_NEE_VALID);
+                        fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE << FL_MODE_SHIFT);
+                        PSET(F_T, s, ok ? 1.0f : 0.0f);
+                        next = ok ? Q_WALK : Q_NEE_END;
+                    } else {
+                        fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DELTA << FL_MODE_SHIFT);
+                        if (BWD && (fl & FL_PASS_MASK) == (unsigned) PP_DRTV) {
+                            const unsigned dw = PU(F_DEPTH, s);
+                            const int depth = (int) (dw & 0xFFFFu) + 1;
+                            PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (unsigned) depth;
+                            active = ok && (depth < P.max_depth);
+                            fl = (fl & ~FL_PASS_MASK) | (unsigned) PP_REC;
+                            PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
+                            PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
+                            fl = (fl & ~FL_ESCAPED) | FL_HAS_SCATTERED;
+                            if (active) draw(r, K);  // :99 of the recursive sample()
+                        } else if (!ok) {
+                            active = false;  // :240-241 accidental escape
+                        }
+                        rr = active;
+                    }
+                    if (rr) {
+                        draw(r, K);  // :120
+                        if (PF(F_B0, s) == 0.0f && PF(F_B1, s) == 0.0f && PF(F_B2, s) == 0.0f) active = false;  // :121
+                    }
+                    if (phase) {
+                        fl = active ? (fl | FL_ACTIVE) : (fl & ~FL_ACTIVE);
+                        next = active ? Q_WALK : Q_PATH_END;
+                    }
+                    PU(F_RNG_LO, s) = (uint32_t) r.state;
+                    PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                    PU(F_FLAGS, s) = fl;
+                }
+            } else {
+                // ---- Q_FREE: next sample from the global queue / adjoint re-start: ray generation +
+                //      reach_medium (batched.py:426-467, volpathsimple.py:292-319) ----
+                unsigned fl = act ? PU(F_FLAGS, s) : 0u;
+                const bool restart = act && (fl & FL_RESTART);
+                bool have = restart;
+                uint32_t idx = 0, pix = 0;
+                if (restart) { idx = PU(F_IDX, s); pix = PU(F_PIX, s); }
+                const unsigned fresh = __ballot_sync(FULL, act && !restart);
+                if (fresh) {
+                    bool none_left = true;
+                    const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
+                    if (exh == 0) {
+                        const int leader = __ffs(fresh) - 1;
+                        unsigned base = 0;
+                        if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (act && !restart) {
+                            const uint64_t item = (uint64_t) base + __popc(fresh & lt_mask);
+                            if (item < total) {
+                                none_left = false;
+                                const uint32_t it = (uint32_t) item;
+                                if (slot_to_pixel(P, it / P.spp, pix)) {
+                                    idx = pix * P.spp + it % P.spp;
+                                    have = true;
+                                    fl = (unsigned) PP_PRIMAL;
+                                    K.add(C_SAMPLES, 1);
+                                } else {
+                                    next = Q_FREE;  // padding slot of a shard: try again
+                                }
+                            }
+                        }
+                        if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
+                    }
+                    // no more samples: the slot retires
+                    const unsigned retire = __ballot_sync(FULL, act && !restart && none_left);
+                    if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
+                }
+                if (have) {
+                    const int pass = (int) (fl & FL_PASS_MASK);
+                    const bool adj = BWD && pass == PP_ADJ;
+                    Rng r;
+                    r.state = r.inc = 0;
+#pragma unroll 1
+                    for (int k = adj ? 1 : 0; k >= 0; --k) {  // sampler.seed(seed, wavefront) [+ the alt sampler, :100-107]
+                        r.seed_sampler(k ? P.alt_seed : P.seed, idx);
+                        if (k) {
+                            PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
+                            PU(F_AINC_LO, s) = (uint32_t) r.inc; PU(F_AINC_HI, s) = (uint32_t) (r.inc >> 32);
+                        }
+                    }
+                    if (adj) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            PSET(F_DL0 + c, s, __ldg(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
+                            PSET(F_RSW0 + c, s, 0.0f);
+                            PSET(F_RSC0 + c, s, 0.0f);
+                        }
+                    } else {
+                        PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
+                    }
+                    const float jx = draw(r, K), jy = draw(r, K);
+                    Seg sg;
+                    const int status = camera_segment(P, pix, jx, jy, sg);
+                    draw(r, K);  // :71
+                    const bool active = status == 1;
+                    const bool escaped = status == 0;
+                    fl = (unsigned) pass | ((unsigned) PM_DELTA << FL_MODE_SHIFT) | (escaped ? FL_ESCAPED : 0u) |
+                         (active ? FL_ACTIVE : 0u);
+                    if (active) {
+                        draw(r, K);  // :99 alt_seed_rnd
+                        if (pass == PP_PRIMAL) K.add(C_HITS, 1);
+                        draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
+                        PU(F_IDX, s) = idx; PU(F_PIX, s) = pix;
+                        PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                        PU(F_INC_LO, s) = (uint32_t) r.inc; PU(F_INC_HI, s) = (uint32_t) (r.inc >> 32);
+                        PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
+                        PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
+                        PSET(F_TMAX, s, sg.tmax);
+                        PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
+                        PU(F_DEPTH, s) = 0u;
+                        next = Q_WALK;
+                    } else {
+                        if (pass == PP_PRIMAL) {
+                            // the ray misses the medium: finish the sample right here
+                            float R[3] = {0.0f, 0.0f, 0.0f};
+                            if (escaped && !P.hide_emitters) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                            }
+                            if (P.sample_L) {
+                                P.sample_L[3 * (size_t) idx + 0] = R[0];
+                                P.sample_L[3 * (size_t) idx + 1] = R[1];
+                                P.sample_L[3 * (size_t) idx + 2] = R[2];
+                            }
+                            if (!BWD) {
+                                atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                                atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                                atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                            } else if (COUNT) {
+                                // the adjoint pass of a missed ray draws jitter + :71 and nothing else
+                                K.add(C_DRAWS, 3);
+                            }
+                        }
+                        fl = 0u;
+                        next = Q_FREE;
+                    }
+                    PU(F_FLAGS, s) = fl;
+                } else if (next == Q_FREE) {
+                    PU(F_FLAGS, s) = 0u;
+                }
+            }
+
+            // ---- gradient scatter of the batch (one code site): 4 transmittance taps, then the
+            //      collision / DRT vertex itself ----
+            if (BWD && __ballot_sync(FULL, sc_taps || sc_ff)) {
+#pragma unroll 1
+                for (int k = 0; k < 5; ++k) {
+                    const bool on = k < 4 ? sc_taps : sc_ff;
+                    if (on) {
+                        float px = sc_vx, py = sc_vy, pz = sc_vz, g = sc_gs;
+                        if (k < 4) {
+                            const float tk = draw(alt, K) * sc_int;
+                            px = fmaf(tk, sc_dx, sc_ox); py = fmaf(tk, sc_dy, sc_oy); pz = fmaf(tk, sc_dz, sc_oz);
+                            g = sc_g;
+                        }
+                        scatter_sigma(P, px, py, pz, g);
+                        K.add(C_SSCAT, 1);
+                        if (k == 4) {
+                            scatter_albedo(P, px, py, pz, sc_ga);
+                            K.add(C_ASCAT, 1);
+                        }
+                    }
+                }
+                if (sc_taps) {
+                    PU(F_ALT_LO, s) = (uint32_t) alt.state;
+                    PU(F_ALT_HI, s) = (uint32_t) (alt.state >> 32);
+                }
+            }
+        }
+
+        // ==============================================================================
+        // 5. route: hand every finished slot to its next queue (the only push site)
+        // ==============================================================================
+        {
+            unsigned todo = __ballot_sync(FULL, next >= 0);
+            __threadfence_block();  // pool fields before the ids become visible
+            while (todo) {
+                const int q = __shfl_sync(FULL, next, __ffs(todo) - 1);
+                const unsigned m = __ballot_sync(FULL, next == q);
+                const int leader = __ffs(m) - 1;
+                unsigned base = 0;
+                if ((int) lane == leader) base = atomicAdd(&ctl->tail[q], (unsigned) __popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                if (next == q) {
+                    unsigned* cell = &ring[q * kPoolRing + ((base + __popc(m & lt_mask)) & (kPoolRing - 1))];
+                    int spins = 0;
+                    // the cell is free unless the consumer of the previous lap has not taken its id yet
+                    while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
+                        if (++spins > kPoolSpinLimit) { trip(0x100u + (unsigned) q); break; }
+                    }
+                }
+                __syncwarp();
+                if ((int) lane == leader) atomicAdd(&ctl->count[q], __popc(m));
+                todo &= ~m;
+            }
+        }
+    }
+#undef PU
+#undef PF
+#undef PSET
+    K.flush(P.counters);
+}
+
+// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 59 words/slot -> 768 slots =
+// 181 KB of the 227 KB shared memory; forward: 27 words/slot.
+constexpr int kPoolSlotsBwd = 768;
+constexpr int kPoolSlotsFwd = 1024;
+
+inline int launch_pool(int num_sms, bool backward, bool counting, const Params& P, cudaStream_t st) {
+    cudaError_t e;
+#define UIVR_POOL_LAUNCH(B, C, N)                                                                       \
+    do {                                                                                                \
+        const size_t smem = pool_smem_bytes<B, N>();                                                    \
+        e = cudaFuncSetAttribute(k_pool<B, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (e != cudaSuccess) return -2;                                                                \
+        k_pool<B, C, N><<<num_sms, kPoolBlock, smem, st>>>(P);                                          \
+    } while (0)
+    if (backward) {
+        if (counting) UIVR_POOL_LAUNCH(true, true, kPoolSlotsBwd); else UIVR_POOL_LAUNCH(true, false, kPoolSlotsBwd);
+    } else {
+        if (counting) UIVR_POOL_LAUNCH(false, true, kPoolSlotsFwd); else UIVR_POOL_LAUNCH(false, false, kPoolSlotsFwd);
+    }
+#undef UIVR_POOL_LAUNCH
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace uivr
