@@ -366,6 +366,7 @@ def run_native(args):
             cnt_b[k] += v
     ctx.set_counting(False)
     torch.cuda.synchronize()
+    ctx.check_watchdog()  # raises if a persistent kernel aborted (results would be invalid)
     my_hw = int(sharding.owned_pixel_mask(HW, shard).sum().item())
     bytes_b = algorithmic_bytes(cnt_b, my_hw * args.steps, True) / args.steps
     bytes_f = algorithmic_bytes(cnt_f, my_hw * args.steps, False) / args.steps
@@ -378,7 +379,7 @@ def run_native(args):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("k_mega_bwd_dram_bytes_per_launch")
+                traffic = json.load(f).get("k_pool_bwd_dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
 
@@ -400,7 +401,7 @@ def run_native(args):
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_mega<BWD> (primal replay + adjoint + DRT megakernel), rank 0",
+                         "kernel": "k_pool<BWD> (slot-pool megakernel: primal replay + adjoint + DRT), rank 0",
                          "kernel_ms": bwd_ms, "algorithmic_bytes_per_launch": bytes_b,
                          "bytes_per_sample": bytes_b / my_samples,
                          "forward_kernel": {"kernel_ms": fwd_ms, "algorithmic_bytes_per_launch": bytes_f,

@@ -9,7 +9,8 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_CSRC, "libuivr.so")
+# UIVR_LIB: alternative build of the same library (tuning sweeps); default = the in-tree build
+LIB_PATH = os.environ.get("UIVR_LIB") or os.path.join(_CSRC, "libuivr.so")
 
 COUNTER_NAMES = ["sigma_taps", "albedo_taps", "majorant_reads", "sigma_scatters",
                  "albedo_scatters", "camera_hits", "real_collisions", "rng_draws", "samples"]

@@ -5,4 +5,4 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
-    -Xcompiler -fPIC -shared ${UIVR_NVCC_EXTRA} -o libuivr.so uivr_api.cu
+    -Xcompiler -fPIC -shared ${UIVR_NVCC_EXTRA} -o ${UIVR_OUT:-libuivr.so} uivr_api.cu

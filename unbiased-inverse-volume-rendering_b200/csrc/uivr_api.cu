@@ -67,6 +67,12 @@ int check_ready(uivr_ctx* ctx) {
     return UIVR_OK;
 }
 
+// the slot-pool kernel packs depth into 16 bits and the supergrid step counters into 9 bits
+bool pool_ok(const uivr_ctx* ctx) {
+    return ctx->variant == 2 && ctx->props.max_depth < 65536 && ctx->mres[0] <= 512 && ctx->mres[1] <= 512 &&
+           ctx->mres[2] <= 512;
+}
+
 int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed, int32_t spp) {
     const uivr_scene_desc& s = ctx->scene;
     const uivr_integrator_props& ip = ctx->props;
@@ -357,7 +363,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
             if ((rc = persistent_grid(ctx, k_forward_v1<false>, kBlock, &grid))) return rc;
             k_forward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
-    } else if (ctx->variant == 2 && ctx->props.max_depth < 65536) {
+    } else if (pool_ok(ctx)) {
         if ((rc = launch_pool(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
         if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
@@ -402,7 +408,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             if ((rc = persistent_grid(ctx, k_backward_v1<false>, kBlock, &grid))) return rc;
             k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
-    } else if (ctx->variant == 2 && ctx->props.max_depth < 65536) {
+    } else if (pool_ok(ctx)) {
         if ((rc = launch_pool(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
         if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");

@@ -25,10 +25,34 @@
 
 namespace uivr {
 
-constexpr int kPoolBlock = 512;
-constexpr int kPoolRing = 1024;      // ring capacity per queue (>= NSLOT, power of two)
-constexpr int kWalkQuantum = 8;      // the walk loop returns once this many lanes have finished
-constexpr int kPoolTapBatch = 8;     // tentative collisions are evaluated when this many lanes wait
+// tuning knobs (overridable at build time for sweeps: scripts/sweep_pool.sh)
+#ifndef UIVR_POOL_BLOCK
+#define UIVR_POOL_BLOCK 512
+#endif
+#ifndef UIVR_POOL_QUANTUM
+#define UIVR_POOL_QUANTUM 16
+#endif
+#ifndef UIVR_POOL_SUBSTEPS
+#define UIVR_POOL_SUBSTEPS 1
+#endif
+#ifndef UIVR_POOL_TAPBATCH
+#define UIVR_POOL_TAPBATCH 8
+#endif
+#ifndef UIVR_POOL_SLOTS_BWD
+#define UIVR_POOL_SLOTS_BWD 768
+#endif
+#ifndef UIVR_POOL_SLOTS_FWD
+#define UIVR_POOL_SLOTS_FWD 1024
+#endif
+constexpr int kPoolBlock = UIVR_POOL_BLOCK;
+constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // the walk loop returns once this many lanes have finished
+constexpr int kPoolTapBatch = UIVR_POOL_TAPBATCH; // tentative collisions are evaluated when this many lanes wait
+constexpr int kPoolSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
+// walker lane states
+enum : int { W_IDLE = 0, W_WALKING = 1, W_PENDING = 2 };
+// remaining-steps counters of the three axes, 10 bits each with a guard bit (bit 9): a counter
+// that steps below zero clears its guard without borrowing from its neighbour
+constexpr unsigned kGuard3 = (512u) | (512u << 10) | (512u << 20);
 constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
 constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
@@ -38,19 +62,30 @@ enum : int { Q_FREE = 0, Q_WALK, Q_VERTEX, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM
 enum : int { PM_DELTA = 0, PM_NEE, PM_NEE_ADJ, PM_DRT };
 enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
 
-// pool fields (one 32-bit word per slot each)
+// pool fields (one 32-bit word per slot each).  Shared memory spent on the pool is L1 taken from
+// the supergrid / sigma_t taps (the carve-out is shared), so fields with disjoint lifetimes alias:
+//   F_TS   sigma_t at the real collision (walk -> vertex) | transmittance T (spawn/walk -> NEE end)
+//          | sum of the NEE adjoint (NEE end -> replay walk)
+//   F_SEQ  PCG32 stream selector v1: inc = (v1 << 1) | 1   (the 64-bit increment is not stored)
+//   pixel = idx / spp is recomputed instead of stored
+//   DRT reservoir sums (live during the adjoint replay) | Li and albedo of the DRT vertex (after it)
+//   sampler clone of the NEE replay (adjoint replay)     | DRT distance-sampling result (after it)
 enum : int {
-    F_IDX = 0, F_PIX, F_RNG_LO, F_RNG_HI, F_INC_LO, F_INC_HI,
+    F_IDX = 0, F_RNG_LO, F_RNG_HI, F_SEQ,
     F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TMAX, F_WT,
-    F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_ST, F_T, F_FLAGS, F_DEPTH, F_VPX, F_VPY, F_VPZ,
+    F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_TS, F_FLAGS, F_DEPTH, F_VPX, F_VPY, F_VPZ,
     F_NUM_FWD,
     // adjoint-only state
-    F_ALT_LO = F_NUM_FWD, F_ALT_HI, F_AINC_LO, F_AINC_HI, F_CLONE_LO, F_CLONE_HI,
-    F_DL0, F_DL1, F_DL2, F_ASUM,
+    F_ALT_LO = F_NUM_FWD, F_ALT_HI, F_ASEQ,
+    F_DL0, F_DL1, F_DL2,
     F_RSW0, F_RSW1, F_RSW2, F_RSC0, F_RSC1, F_RSC2,
     F_RSOX, F_RSOY, F_RSOZ, F_RSDX, F_RSDY, F_RSDZ, F_RSTMAX,
-    F_DRT_D, F_DRT_T, F_DRT_ST, F_LI0, F_LI1, F_LI2, F_AL0, F_AL1, F_AL2,
-    F_NUM_BWD
+    F_CLONE_LO, F_CLONE_HI, F_DRT_ST,
+    F_NUM_BWD,
+    // aliases
+    F_ST = F_TS, F_T = F_TS, F_ASUM = F_TS,
+    F_LI0 = F_RSW0, F_LI1 = F_RSW1, F_LI2 = F_RSW2, F_AL0 = F_RSC0, F_AL1 = F_RSC1, F_AL2 = F_RSC2,
+    F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI
 };
 
 // F_FLAGS bits
@@ -72,18 +107,18 @@ struct PoolCtl {
 
 template <bool BWD, int NSLOT>
 constexpr size_t pool_smem_bytes() {
-    return 128 + (size_t) Q_NUM * kPoolRing * sizeof(unsigned) +
+    return 128 + (size_t) Q_NUM * NSLOT * sizeof(unsigned) +
            (size_t) (BWD ? F_NUM_BWD : F_NUM_FWD) * NSLOT * sizeof(uint32_t);
 }
 
 template <bool BWD, bool COUNT, int NSLOT>
 __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
-    static_assert(NSLOT <= kPoolRing && NSLOT < 0xFFFF, "ring too small");
+    static_assert(NSLOT > (Q_NUM - 1) * 31 && NSLOT % 32 == 0, "pool too small for the full-batch scheduling rule");
     static_assert(sizeof(PoolCtl) <= 128, "PoolCtl must fit its 128-byte header");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PoolCtl* const ctl = reinterpret_cast<PoolCtl*>(smem_raw);
     unsigned* const ring = reinterpret_cast<unsigned*>(smem_raw + 128);  // one mailbox cell per ring position
-    uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * kPoolRing * sizeof(unsigned));
+    uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * NSLOT * sizeof(unsigned));
 
     Counters<COUNT> K;
     const unsigned lane = threadIdx.x & 31u;
@@ -97,7 +132,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
 #define PSET(f, s, v) pool[(f) * NSLOT + (s)] = __float_as_uint(v)
 
     // ---- pool / queue initialisation: every slot starts in Q_FREE ----
-    for (int i = threadIdx.x; i < Q_NUM * kPoolRing; i += kPoolBlock)
+    for (int i = threadIdx.x; i < Q_NUM * NSLOT; i += kPoolBlock)
         ring[i] = (i < NSLOT) ? (unsigned) i : kPoolEmpty;   // ring 0 == Q_FREE
     for (int i = threadIdx.x; i < NSLOT; i += kPoolBlock) PU(F_FLAGS, i) = 0u;
     if (threadIdx.x < Q_NUM) {
@@ -138,7 +173,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
         got = __shfl_sync(FULL, got, 0);
         base = __shfl_sync(FULL, base, 0);
         if ((int) lane < got) {
-            unsigned* cell = &ring[q * kPoolRing + ((base + lane) & (kPoolRing - 1))];
+            unsigned* cell = &ring[q * NSLOT + (base + lane) % (unsigned) NSLOT];
             unsigned v;
             int spins = 0;
             // the position is reserved by a producer; its store may still be in flight
@@ -153,8 +188,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
 
     // ---- walker state (registers; one walk job per lane) ----
     int wslot = -1;            // pool slot this lane walks for, -1 = idle
-    bool walking = false;      // the walk is in progress
-    bool pending = false;      // a tentative collision at `wt` waits for its sigma_t tap
+    int wstate = W_IDLE;       // W_WALKING: stepping cells; W_PENDING: a tentative collision at `wt` waits for its tap
     unsigned wflags = 0;
     int mode = PM_DELTA;
     Rng rng;
@@ -162,7 +196,9 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
     float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f, tmax = 0.0f;
     float wt = 0.0f, tnx = 0.0f, tny = 0.0f, tnz = 0.0f, sb = 0.0f, tau = 0.0f;
     float adx = 0.0f, ady = 0.0f, adz = 0.0f;
-    int cx = 0, cy = 0, cz = 0;
+    int ci = 0;                // linear supergrid cell index
+    int sxl = 0, syl = 0, szl = 0;  // its signed strides along the ray
+    unsigned nrem = 0;         // packed remaining-steps counters (kGuard3)
     float T = 1.0f, asum = 0.0f, sigma_t = 0.0f;
     float drt_D = 0.0f, drt_t = 0.0f, drt_st = 0.0f;
     bool drt_found = false, did_scatter = false;
@@ -189,7 +225,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                         wflags = PU(F_FLAGS, s);
                         mode = (int) ((wflags & FL_MODE_MASK) >> FL_MODE_SHIFT);
                         rng.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
-                        rng.inc = (uint64_t) PU(F_INC_LO, s) | ((uint64_t) PU(F_INC_HI, s) << 32);
+                        rng.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
                         ox = PF(F_OX, s); oy = PF(F_OY, s); oz = PF(F_OZ, s);
                         dx = PF(F_DX, s); dy = PF(F_DY, s); dz = PF(F_DZ, s);
                         tmax = PF(F_TMAX, s);
@@ -203,16 +239,26 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                         const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
                         const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
                         wt = 0.0f;
+                        int cx, cy, cz;
                         walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
                         walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
                         walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
                         adx = fabsf(P.mcs[0] * ix);
                         ady = fabsf(P.mcs[1] * iy);
                         adz = fabsf(P.mcs[2] * iz);
-                        sb = majorant_at<COUNT>(P, cx, cy, cz, K);
+                        // cell coordinates -> linear index + steps left before the walk leaves the grid
+                        const int mx = P.mres[0], mxy = P.mres[0] * P.mres[1];
+                        ci = cz * mxy + cy * mx + cx;
+                        sxl = dx > 0.0f ? 1 : -1;
+                        syl = dy > 0.0f ? mx : -mx;
+                        szl = dz > 0.0f ? mxy : -mxy;
+                        nrem = kGuard3 | (unsigned) (dx > 0.0f ? P.mres[0] - 1 - cx : cx) |
+                               ((unsigned) (dy > 0.0f ? P.mres[1] - 1 - cy : cy) << 10) |
+                               ((unsigned) (dz > 0.0f ? P.mres[2] - 1 - cz : cz) << 20);
+                        K.add(C_MAJ, 1);
+                        sb = __ldg(P.maj + ci);
                         tau = neg_log1m(draw(rng, K));
-                        walking = true;
-                        pending = false;
+                        wstate = W_WALKING;
                     }
                 }
             }
@@ -224,7 +270,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
         //    Before exhaustion no slot retires, so "no full queue and nothing to walk anywhere"
         //    cannot happen: NSLOT > (Q_NUM - 1) * 31 slots cannot all sit in non-full queues.
         // ==============================================================================
-        const unsigned m_walk = __ballot_sync(FULL, walking);
+        const unsigned m_walk = __ballot_sync(FULL, wstate != W_IDLE);
         int work = -1;
         bool exact = true;
         {
@@ -269,46 +315,49 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
             const int n0 = __popc(m_walk);
             const int n_stop = n0 > kWalkQuantum ? n0 - kWalkQuantum : 0;
             for (int guard = 0;; ++guard) {
-                if (guard > kPoolWalkLimit) { trip(0x400u); walking = false; pending = false; break; }
-                // ---- one supergrid cell per iteration (branch-free DDA) ----
-                if (walking && !pending) {
-                    const bool yx = tny < tnx;
-                    float tn = yx ? tny : tnx;
-                    const bool zb = tnz < tn;
-                    tn = zb ? tnz : tn;
-                    const float t_end = tn < tmax ? tn : tmax;
-                    float len = t_end - wt;
-                    len = len < 0.0f ? 0.0f : len;
-                    const float dtau = sb * len;
-                    if (sb > 0.0f && tau < dtau) {
-                        float t = wt + tau / sb;
-                        wt = t > t_end ? t_end : t;
-                        pending = true;
-                    } else {
-                        if (sb > 0.0f) tau -= dtau;
-                        wt = t_end > wt ? t_end : wt;
-                        bool end = !(tn < tmax);
-                        const bool a0 = !zb && !yx, a1 = !zb && yx;
-                        const int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1, sz = dz > 0.0f ? 1 : -1;
-                        cx += a0 ? sx : 0;
-                        cy += a1 ? sy : 0;
-                        cz += zb ? sz : 0;
-                        tnx = a0 ? tnx + adx : tnx;
-                        tny = a1 ? tny + ady : tny;
-                        tnz = zb ? tnz + adz : tnz;
-                        end = end || (unsigned) cx >= (unsigned) P.mres[0] || (unsigned) cy >= (unsigned) P.mres[1] ||
-                              (unsigned) cz >= (unsigned) P.mres[2];
-                        if (end) walking = false;  // segment end: no (further) collision
-                        else sb = majorant_at<COUNT>(P, cx, cy, cz, K);
+                if (guard > kPoolWalkLimit) { trip(0x400u); wstate = W_IDLE; break; }
+                // ---- kPoolSubSteps supergrid cells per iteration (branch-free DDA) ----
+#pragma unroll
+                for (int sub = 0; sub < kPoolSubSteps; ++sub) {
+                    if (wstate == W_WALKING) {
+                        const bool yx = tny < tnx;
+                        float tn = yx ? tny : tnx;
+                        const bool zb = tnz < tn;
+                        tn = zb ? tnz : tn;
+                        const float t_end = tn < tmax ? tn : tmax;
+                        float len = t_end - wt;
+                        len = len < 0.0f ? 0.0f : len;
+                        const float dtau = sb * len;
+                        if (sb > 0.0f && tau < dtau) {
+                            float t = wt + tau / sb;
+                            wt = t > t_end ? t_end : t;
+                            wstate = W_PENDING;
+                        } else {
+                            if (sb > 0.0f) tau -= dtau;
+                            wt = t_end > wt ? t_end : wt;
+                            const bool a0 = !zb && !yx, a1 = !zb && yx;
+                            ci += a0 ? sxl : (a1 ? syl : szl);
+                            nrem -= a0 ? 1u : (a1 ? (1u << 10) : (1u << 20));
+                            tnx = a0 ? tnx + adx : tnx;
+                            tny = a1 ? tny + ady : tny;
+                            tnz = zb ? tnz + adz : tnz;
+                            // segment end (no further collision): t_exit reached, or the walk left the grid
+                            if (!(tn < tmax) || (nrem & kGuard3) != kGuard3) {
+                                wstate = W_IDLE;
+                            } else {
+                                K.add(C_MAJ, 1);
+                                sb = __ldg(P.maj + ci);
+                            }
+                        }
                     }
                 }
-                const int n_walk = __popc(__ballot_sync(FULL, walking));
-                const int n_pend = __popc(__ballot_sync(FULL, pending));
+                const int n_walk = __popc(__ballot_sync(FULL, wstate != W_IDLE));
+                const int n_pend = __popc(__ballot_sync(FULL, wstate == W_PENDING));
                 const bool leave = n_walk <= n_stop;
                 // ---- tentative collisions: sigma_t tap + per-mode decision ----
                 if (n_pend >= kPoolTapBatch || (n_pend > 0 && (n_pend == n_walk || leave))) {
-                    if (pending) {
-                        pending = false;
+                    if (wstate == W_PENDING) {
+                        wstate = W_WALKING;
                         const float px = fmaf(wt, dx, ox), py = fmaf(wt, dy, oy), pz = fmaf(wt, dz, oz);
                         float u2 = 0.0f;
                         if (mode == PM_DRT) u2 = draw(rng, K);
@@ -346,15 +395,15 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                             if (T == 0.0f) cont = false;
                         }
                         if (cont) tau = neg_log1m(draw(rng, K));
-                        else walking = false;
+                        else wstate = W_IDLE;
                     }
-                    if (leave || __ballot_sync(FULL, walking) == 0u) break;
+                    if (leave || __ballot_sync(FULL, wstate != W_IDLE) == 0u) break;
                 } else if (leave) {
                     break;
                 }
             }
             // ---- write back finished walks; the slot goes on to its next queue ----
-            if (wslot >= 0 && !walking) {
+            if (wslot >= 0 && wstate == W_IDLE) {
                 s = (unsigned) wslot;
                 PU(F_RNG_LO, s) = (uint32_t) rng.state;
                 PU(F_RNG_HI, s) = (uint32_t) (rng.state >> 32);
@@ -424,7 +473,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                         }
                         if (BWD && pass == PP_ADJ) {
                             alt.state = (uint64_t) PU(F_ALT_LO, s) | ((uint64_t) PU(F_ALT_HI, s) << 32);
-                            alt.inc = (uint64_t) PU(F_AINC_LO, s) | ((uint64_t) PU(F_AINC_HI, s) << 32);
+                            alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
                             const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
                             const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
                             const float st = PF(F_ST, s);
@@ -544,7 +593,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                     next = Q_FREE;
                     fl &= ~FL_RESTART;
                     if (pass == PP_PRIMAL) {
-                        const uint32_t idx = PU(F_IDX, s), pix = PU(F_PIX, s);
+                        const uint32_t idx = PU(F_IDX, s), pix = idx / P.spp;
                         if (P.sample_L) {
                             P.sample_L[3 * (size_t) idx + 0] = R[0];
                             P.sample_L[3 * (size_t) idx + 1] = R[1];
@@ -575,7 +624,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                             PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (dw >> 16);
                             // everything from here on draws from the alt stream
                             PU(F_RNG_LO, s) = PU(F_ALT_LO, s); PU(F_RNG_HI, s) = PU(F_ALT_HI, s);
-                            PU(F_INC_LO, s) = PU(F_AINC_LO, s); PU(F_INC_HI, s) = PU(F_AINC_HI, s);
+                            PU(F_SEQ, s) = PU(F_ASEQ, s);
                             fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DRT << FL_MODE_SHIFT);
                             next = Q_WALK;
                         }
@@ -603,7 +652,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                     const bool phase = (fl & FL_SPAWN_PHASE) != 0u;
                     Rng r;
                     r.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
-                    r.inc = (uint64_t) PU(F_INC_LO, s) | ((uint64_t) PU(F_INC_HI, s) << 32);
+                    r.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
                     if (phase) draw(r, K);
                     const float xi1 = draw(r, K), xi2 = draw(r, K);
                     float wx, wy, wz;
@@ -616,7 +665,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                     bool active = (fl & FL_ACTIVE) != 0u;
                     bool rr = false;  // Russian-roulette draw + zero-throughput test of the next loop iteration
                     if (!phase) {
-                        if (BWD) {
+                        if (BWD && (fl & FL_PASS_MASK) == (unsigned) PP_ADJ) {
                             // sampler.clone() position for the adjoint replay (:383)
                             PU(F_CLONE_LO, s) = (uint32_t) r.state;
                             PU(F_CLONE_HI, s) = (uint32_t) (r.state >> 32);
@@ -661,7 +710,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                 const bool restart = act && (fl & FL_RESTART);
                 bool have = restart;
                 uint32_t idx = 0, pix = 0;
-                if (restart) { idx = PU(F_IDX, s); pix = PU(F_PIX, s); }
+                if (restart) { idx = PU(F_IDX, s); pix = idx / P.spp; }
                 const unsigned fresh = __ballot_sync(FULL, act && !restart);
                 if (fresh) {
                     bool none_left = true;
@@ -702,7 +751,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                         r.seed_sampler(k ? P.alt_seed : P.seed, idx);
                         if (k) {
                             PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
-                            PU(F_AINC_LO, s) = (uint32_t) r.inc; PU(F_AINC_HI, s) = (uint32_t) (r.inc >> 32);
+                            PU(F_ASEQ, s) = (uint32_t) (r.inc >> 1);
                         }
                     }
                     if (adj) {
@@ -727,9 +776,9 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                         draw(r, K);  // :99 alt_seed_rnd
                         if (pass == PP_PRIMAL) K.add(C_HITS, 1);
                         draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
-                        PU(F_IDX, s) = idx; PU(F_PIX, s) = pix;
+                        PU(F_IDX, s) = idx;
                         PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
-                        PU(F_INC_LO, s) = (uint32_t) r.inc; PU(F_INC_HI, s) = (uint32_t) (r.inc >> 32);
+                        PU(F_SEQ, s) = (uint32_t) (r.inc >> 1);
                         PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
                         PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
                         PSET(F_TMAX, s, sg.tmax);
@@ -809,7 +858,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                 if ((int) lane == leader) base = atomicAdd(&ctl->tail[q], (unsigned) __popc(m));
                 base = __shfl_sync(FULL, base, leader);
                 if (next == q) {
-                    unsigned* cell = &ring[q * kPoolRing + ((base + __popc(m & lt_mask)) & (kPoolRing - 1))];
+                    unsigned* cell = &ring[q * NSLOT + (base + __popc(m & lt_mask)) % (unsigned) NSLOT];
                     int spins = 0;
                     // the cell is free unless the consumer of the previous lap has not taken its id yet
                     while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
@@ -828,10 +877,11 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
     K.flush(P.counters);
 }
 
-// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 59 words/slot -> 768 slots =
-// 181 KB of the 227 KB shared memory; forward: 27 words/slot.
-constexpr int kPoolSlotsBwd = 768;
-constexpr int kPoolSlotsFwd = 1024;
+// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 46 words/slot -> 768 slots = 138 KB
+// (+ 18 KB of queue rings) of the 227 KB shared memory, which leaves ~90 KB of L1 for the supergrid
+// and the taps; forward: 24 words/slot.  Measured optimum on config 3 (scripts/sweep_pool.sh).
+constexpr int kPoolSlotsBwd = UIVR_POOL_SLOTS_BWD;
+constexpr int kPoolSlotsFwd = UIVR_POOL_SLOTS_FWD;
 
 inline int launch_pool(int num_sms, bool backward, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
