@@ -27,7 +27,10 @@ namespace uivr {
 
 // tuning knobs (overridable at build time for sweeps: scripts/sweep_pool.sh)
 #ifndef UIVR_POOL_BLOCK
-#define UIVR_POOL_BLOCK 512
+#define UIVR_POOL_BLOCK 768
+#endif
+#ifndef UIVR_POOL_HANDLER_WARPS
+#define UIVR_POOL_HANDLER_WARPS 8
 #endif
 #ifndef UIVR_POOL_QUANTUM
 #define UIVR_POOL_QUANTUM 16
@@ -45,6 +48,7 @@ namespace uivr {
 #define UIVR_POOL_SLOTS_FWD 1024
 #endif
 constexpr int kPoolBlock = UIVR_POOL_BLOCK;
+constexpr int kPoolHandlerWarps = UIVR_POOL_HANDLER_WARPS;  // warps serving the transition queues; the rest walk
 constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // the walk loop returns once this many lanes have finished
 constexpr int kPoolTapBatch = UIVR_POOL_TAPBATCH; // tentative collisions are evaluated when this many lanes wait
 constexpr int kPoolSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
@@ -203,110 +207,109 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
     float drt_D = 0.0f, drt_t = 0.0f, drt_st = 0.0f;
     bool drt_found = false, did_scatter = false;
 
-    long long t_progress = clock64();
-    for (;;) {
-        if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
-        // per-queue fill levels, one queue per lane
-        const int cnt = (lane < Q_NUM) ? *((volatile int*) &ctl->count[lane]) : 0;
+    // route: hand every finished slot to its next queue (lane-wise: slot `s` -> queue `next`, -1: none)
+    auto route = [&](unsigned s, int next) {
+        unsigned todo = __ballot_sync(FULL, next >= 0);
+        __threadfence_block();  // pool fields before the ids become visible
+        while (todo) {
+            const int q = __shfl_sync(FULL, next, __ffs(todo) - 1);
+            const unsigned m = __ballot_sync(FULL, next == q);
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int) lane == leader) base = atomicAdd(&ctl->tail[q], (unsigned) __popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (next == q) {
+                unsigned* cell = &ring[q * NSLOT + (base + __popc(m & lt_mask)) % (unsigned) NSLOT];
+                int spins = 0;
+                // the cell is free unless the consumer of the previous lap has not taken its id yet
+                while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
+                    if (++spins > kPoolSpinLimit) { trip(0x100u + (unsigned) q); break; }
+                }
+            }
+            __syncwarp();
+            if ((int) lane == leader) atomicAdd(&ctl->count[q], __popc(m));
+            todo &= ~m;
+        }
+    };
 
-        // ==============================================================================
-        // 1. refill idle walker lanes from Q_WALK
-        // ==============================================================================
-        {
-            const unsigned idle = __ballot_sync(FULL, wslot < 0);
-            if (idle && __shfl_sync(FULL, cnt, Q_WALK) > 0) {
-                unsigned got_slot = 0;
-                const int got = q_pop(Q_WALK, __popc(idle), false, got_slot);
-                if (got) {
-                    const int rank = __popc(idle & lt_mask);
-                    const unsigned s = __shfl_sync(FULL, got_slot, rank & 31);
-                    if (wslot < 0 && rank < got) {
-                        wslot = (int) s;
-                        wflags = PU(F_FLAGS, s);
-                        mode = (int) ((wflags & FL_MODE_MASK) >> FL_MODE_SHIFT);
-                        rng.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
-                        rng.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
-                        ox = PF(F_OX, s); oy = PF(F_OY, s); oz = PF(F_OZ, s);
-                        dx = PF(F_DX, s); dy = PF(F_DY, s); dz = PF(F_DZ, s);
-                        tmax = PF(F_TMAX, s);
-                        T = 1.0f;
-                        drt_D = 0.0f;
-                        drt_found = false;
-                        did_scatter = false;
-                        if (BWD) asum = PF(F_ASUM, s);
-                        // walk_init (Medium::sample_interaction set-up, App. B.5)
-                        const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
-                        const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
-                        const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
-                        wt = 0.0f;
-                        int cx, cy, cz;
-                        walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
-                        walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
-                        walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
-                        adx = fabsf(P.mcs[0] * ix);
-                        ady = fabsf(P.mcs[1] * iy);
-                        adz = fabsf(P.mcs[2] * iz);
-                        // cell coordinates -> linear index + steps left before the walk leaves the grid
-                        const int mx = P.mres[0], mxy = P.mres[0] * P.mres[1];
-                        ci = cz * mxy + cy * mx + cx;
-                        sxl = dx > 0.0f ? 1 : -1;
-                        syl = dy > 0.0f ? mx : -mx;
-                        szl = dz > 0.0f ? mxy : -mxy;
-                        nrem = kGuard3 | (unsigned) (dx > 0.0f ? P.mres[0] - 1 - cx : cx) |
-                               ((unsigned) (dy > 0.0f ? P.mres[1] - 1 - cy : cy) << 10) |
-                               ((unsigned) (dz > 0.0f ? P.mres[2] - 1 - cz : cz) << 20);
-                        K.add(C_MAJ, 1);
-                        sb = __ldg(P.maj + ci);
-                        tau = neg_log1m(draw(rng, K));
-                        wstate = W_WALKING;
+    // Warp roles.  The first kPoolHandlerWarps warps serve the transition queues, all others are
+    // walkers.  The two loops share no registers, so the walker loop (the hot code: a few KB of
+    // SASS that stays in the instruction caches) is not charged for the handlers' working set.
+    const bool is_handler = (threadIdx.x >> 5) < kPoolHandlerWarps;
+    long long t_progress = clock64();
+
+    if (!is_handler) {
+        // ==================================================================================
+        // WALKER WARPS
+        // ==================================================================================
+        for (;;) {
+            if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
+            const int cnt = (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0;
+            // ==============================================================================
+            // 1. refill idle walker lanes from Q_WALK
+            // ==============================================================================
+            {
+                const unsigned idle = __ballot_sync(FULL, wslot < 0);
+                if (idle && __shfl_sync(FULL, cnt, 0) > 0) {
+                    unsigned got_slot = 0;
+                    const int got = q_pop(Q_WALK, __popc(idle), false, got_slot);
+                    if (got) {
+                        const int rank = __popc(idle & lt_mask);
+                        const unsigned s = __shfl_sync(FULL, got_slot, rank & 31);
+                        if (wslot < 0 && rank < got) {
+                            wslot = (int) s;
+                            wflags = PU(F_FLAGS, s);
+                            mode = (int) ((wflags & FL_MODE_MASK) >> FL_MODE_SHIFT);
+                            rng.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
+                            rng.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
+                            ox = PF(F_OX, s); oy = PF(F_OY, s); oz = PF(F_OZ, s);
+                            dx = PF(F_DX, s); dy = PF(F_DY, s); dz = PF(F_DZ, s);
+                            tmax = PF(F_TMAX, s);
+                            T = 1.0f;
+                            drt_D = 0.0f;
+                            drt_found = false;
+                            did_scatter = false;
+                            if (BWD) asum = PF(F_ASUM, s);
+                            // walk_init (Medium::sample_interaction set-up, App. B.5)
+                            const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
+                            const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
+                            const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
+                            wt = 0.0f;
+                            int cx, cy, cz;
+                            walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
+                            walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
+                            walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
+                            adx = fabsf(P.mcs[0] * ix);
+                            ady = fabsf(P.mcs[1] * iy);
+                            adz = fabsf(P.mcs[2] * iz);
+                            // cell coordinates -> linear index + steps left before the walk leaves the grid
+                            const int mx = P.mres[0], mxy = P.mres[0] * P.mres[1];
+                            ci = cz * mxy + cy * mx + cx;
+                            sxl = dx > 0.0f ? 1 : -1;
+                            syl = dy > 0.0f ? mx : -mx;
+                            szl = dz > 0.0f ? mxy : -mxy;
+                            nrem = kGuard3 | (unsigned) (dx > 0.0f ? P.mres[0] - 1 - cx : cx) |
+                                   ((unsigned) (dy > 0.0f ? P.mres[1] - 1 - cy : cy) << 10) |
+                                   ((unsigned) (dz > 0.0f ? P.mres[2] - 1 - cz : cz) << 20);
+                            K.add(C_MAJ, 1);
+                            sb = __ldg(P.maj + ci);
+                            tau = neg_log1m(draw(rng, K));
+                            wstate = W_WALKING;
+                        }
                     }
                 }
             }
-        }
 
-        // ==============================================================================
-        // 2. schedule ONE work item: a FULL batch of a transition queue if there is one, else a walk
-        //    quantum, else (only once the global sample queue is exhausted) a partial batch.
-        //    Before exhaustion no slot retires, so "no full queue and nothing to walk anywhere"
-        //    cannot happen: NSLOT > (Q_NUM - 1) * 31 slots cannot all sit in non-full queues.
-        // ==============================================================================
-        const unsigned m_walk = __ballot_sync(FULL, wstate != W_IDLE);
-        int work = -1;
-        bool exact = true;
-        {
-            const unsigned fullq = __ballot_sync(FULL, cnt >= 32) & ~(1u << Q_WALK);
-            if (fullq) {
-                work = __ffs(fullq) - 1;
-            } else if (m_walk) {
-                work = Q_WALK;
-            } else {
-                const unsigned some = __ballot_sync(FULL, cnt > 0) & ~(1u << Q_WALK);
-                if (some && __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0)) {
-                    work = __ffs(some) - 1;
-                    exact = false;
-                }
+            const unsigned m_walk = __ballot_sync(FULL, wstate != W_IDLE);
+            if (!m_walk) {
+                if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
+                if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
+                __nanosleep(64);
+                continue;
             }
-        }
-        if (work < 0) {
-            if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
-            if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
-            __nanosleep(100);
-            continue;
-        }
-        t_progress = clock64();
-
-        // per-lane result of the work item: slot `s` goes to queue `next` (-1: nothing to route)
-        unsigned s = 0;
-        int next = -1;
-        // gradient scatter request of the handlers (executed at one site below)
-        bool sc_taps = false, sc_ff = false;
-        float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
-        float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
-        float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
-        Rng alt;
-        alt.state = alt.inc = 0;
-
-        if (work == Q_WALK) {
+            t_progress = clock64();
+            unsigned s = 0;
+            int next = -1;
             // ==========================================================================
             // 3. walk quantum: free-flight walk over the majorant supergrid (Medium::
             //    sample_interaction and its ratio-tracking / DRT siblings) until kWalkQuantum
@@ -425,7 +428,52 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                 }
                 wslot = -1;
             }
-        } else {
+            route(s, next);
+        }
+    } else {
+        // ==================================================================================
+        // HANDLER WARPS: a FULL batch of a transition queue if there is one; partial batches only
+        // once the global sample queue is exhausted.  Before exhaustion no slot retires, so
+        // "no full queue and nothing to walk anywhere" cannot happen: NSLOT > (Q_NUM - 1) * 31
+        // slots cannot all sit in non-full queues.
+        // ==================================================================================
+        for (;;) {
+            if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
+            // per-queue fill levels, one queue per lane
+            const int cnt = (lane < Q_NUM && lane != Q_WALK) ? *((volatile int*) &ctl->count[lane]) : 0;
+            int work = -1;
+            bool exact = true;
+            {
+                // fullest queue first
+                int best = (cnt << 3) | (int) lane;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+                best = __shfl_sync(FULL, best, 0);
+                if ((best >> 3) >= 32) {
+                    work = best & 7;
+                } else if ((best >> 3) > 0 && __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0)) {
+                    work = best & 7;
+                    exact = false;
+                }
+            }
+            if (work < 0) {
+                if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
+                if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
+                __nanosleep(64);
+                continue;
+            }
+            t_progress = clock64();
+
+            // per-lane result of the work item: slot `s` goes to queue `next` (-1: nothing to route)
+            unsigned s = 0;
+            int next = -1;
+            // gradient scatter request of the handlers (executed at one site below)
+            bool sc_taps = false, sc_ff = false;
+            float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
+            float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
+            float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
+            Rng alt;
+            alt.state = alt.inc = 0;
             // ==========================================================================
             // 4. transition handlers (one batch of up to 32 slots of queue `work`)
             // ==========================================================================
@@ -842,33 +890,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                     PU(F_ALT_HI, s) = (uint32_t) (alt.state >> 32);
                 }
             }
-        }
-
-        // ==============================================================================
-        // 5. route: hand every finished slot to its next queue (the only push site)
-        // ==============================================================================
-        {
-            unsigned todo = __ballot_sync(FULL, next >= 0);
-            __threadfence_block();  // pool fields before the ids become visible
-            while (todo) {
-                const int q = __shfl_sync(FULL, next, __ffs(todo) - 1);
-                const unsigned m = __ballot_sync(FULL, next == q);
-                const int leader = __ffs(m) - 1;
-                unsigned base = 0;
-                if ((int) lane == leader) base = atomicAdd(&ctl->tail[q], (unsigned) __popc(m));
-                base = __shfl_sync(FULL, base, leader);
-                if (next == q) {
-                    unsigned* cell = &ring[q * NSLOT + (base + __popc(m & lt_mask)) % (unsigned) NSLOT];
-                    int spins = 0;
-                    // the cell is free unless the consumer of the previous lap has not taken its id yet
-                    while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
-                        if (++spins > kPoolSpinLimit) { trip(0x100u + (unsigned) q); break; }
-                    }
-                }
-                __syncwarp();
-                if ((int) lane == leader) atomicAdd(&ctl->count[q], __popc(m));
-                todo &= ~m;
-            }
+            route(s, next);
         }
     }
 #undef PU
