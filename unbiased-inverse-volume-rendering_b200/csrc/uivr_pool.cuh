@@ -7,7 +7,7 @@
 // pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA, field-major),
 // and every state of the per-sample state machine has a CTA-wide queue of slot ids:
 //
-//      Q_FREE -> [fetch] -> Q_WALK -> [walk] -> Q_VERTEX -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK ...
+//      Q_FREE -> [fetch] -> Q_WALK -> [walk] -> Q_VERTEX(_ADJ) -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK ...
 //                                            -> Q_NEE_END / Q_PATH_END -> ... -> Q_FREE
 //
 // Any warp can serve any queue: it pops up to 32 slot ids (normally a FULL batch), loads only
@@ -26,11 +26,17 @@
 namespace uivr {
 
 // tuning knobs (overridable at build time for sweeps: scripts/sweep_pool.sh)
-#ifndef UIVR_POOL_BLOCK
-#define UIVR_POOL_BLOCK 768
+#ifndef UIVR_POOL_BLOCK_BWD
+#define UIVR_POOL_BLOCK_BWD 896
 #endif
-#ifndef UIVR_POOL_HANDLER_WARPS
-#define UIVR_POOL_HANDLER_WARPS 8
+#ifndef UIVR_POOL_HANDLERS_BWD
+#define UIVR_POOL_HANDLERS_BWD 12
+#endif
+#ifndef UIVR_POOL_BLOCK_FWD
+#define UIVR_POOL_BLOCK_FWD 1024
+#endif
+#ifndef UIVR_POOL_HANDLERS_FWD
+#define UIVR_POOL_HANDLERS_FWD 8
 #endif
 #ifndef UIVR_POOL_QUANTUM
 #define UIVR_POOL_QUANTUM 16
@@ -42,13 +48,11 @@ namespace uivr {
 #define UIVR_POOL_TAPBATCH 8
 #endif
 #ifndef UIVR_POOL_SLOTS_BWD
-#define UIVR_POOL_SLOTS_BWD 768
+#define UIVR_POOL_SLOTS_BWD 896
 #endif
 #ifndef UIVR_POOL_SLOTS_FWD
-#define UIVR_POOL_SLOTS_FWD 1024
+#define UIVR_POOL_SLOTS_FWD 1280
 #endif
-constexpr int kPoolBlock = UIVR_POOL_BLOCK;
-constexpr int kPoolHandlerWarps = UIVR_POOL_HANDLER_WARPS;  // warps serving the transition queues; the rest walk
 constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // the walk loop returns once this many lanes have finished
 constexpr int kPoolTapBatch = UIVR_POOL_TAPBATCH; // tentative collisions are evaluated when this many lanes wait
 constexpr int kPoolSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
@@ -62,7 +66,7 @@ constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
 constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
 
-enum : int { Q_FREE = 0, Q_WALK, Q_VERTEX, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
+enum : int { Q_FREE = 0, Q_WALK, Q_VERTEX, Q_VERTEX_ADJ, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
 enum : int { PM_DELTA = 0, PM_NEE, PM_NEE_ADJ, PM_DRT };
 enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
 
@@ -115,8 +119,12 @@ constexpr size_t pool_smem_bytes() {
            (size_t) (BWD ? F_NUM_BWD : F_NUM_FWD) * NSLOT * sizeof(uint32_t);
 }
 
-template <bool BWD, bool COUNT, int NSLOT>
-__global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
+// BLOCK threads per CTA (one CTA per SM), of which the first HANDLERS warps serve the transition
+// queues and the rest walk
+template <bool BWD, bool COUNT, int NSLOT, int BLOCK, int HANDLERS>
+__global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
+    constexpr int kPoolBlock = BLOCK;
+    constexpr int kPoolHandlerWarps = HANDLERS;
     static_assert(NSLOT > (Q_NUM - 1) * 31 && NSLOT % 32 == 0, "pool too small for the full-batch scheduling rule");
     static_assert(sizeof(PoolCtl) <= 128, "PoolCtl must fit its 128-byte header");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -362,40 +370,42 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                     if (wstate == W_PENDING) {
                         wstate = W_WALKING;
                         const float px = fmaf(wt, dx, ox), py = fmaf(wt, dy, oy), pz = fmaf(wt, dz, oz);
-                        float u2 = 0.0f;
-                        if (mode == PM_DRT) u2 = draw(rng, K);
+                        // one extra draw for delta tracking (accept test, :359) and for DRT (reservoir, drawn
+                        // before the lookup); the lookup itself draws nothing, so the order is immaterial
+                        float u = 0.0f;
+                        if (mode == PM_DELTA || mode == PM_DRT) u = draw(rng, K);
                         const float st = sigma_tap(P, px, py, pz);
                         K.add(C_SIGMA, 1);
+                        // sigma_t / sigma_bar (delta tracking) or sigma_n / sigma_bar (ratio tracking, DRT): one
+                        // division site for all modes
+                        const float sn = sb - st;
+                        const float q = (mode == PM_DELTA ? st : sn) / sb;
                         bool cont = true;
                         if (mode == PM_DELTA) {
                             // :354-361 real vs null collision
-                            const float r = st / sb;
-                            if (!(draw(rng, K) >= r)) {
+                            if (!(u >= q)) {
                                 did_scatter = true;
                                 sigma_t = st;
                                 cont = false;
                             }
-                        } else if (mode == PM_DRT) {
-                            // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
-                            const float wi = T / sb;
-                            drt_D += wi;
-                            if (u2 <= wi / drt_D) {
-                                drt_t = wt;
-                                drt_st = st;
-                                drt_found = true;
-                            }
-                            T *= (sb - st) / sb;
-                            if (!(T > 0.0f)) cont = false;
                         } else {
-                            // ratio tracking (:461-502); PM_NEE_ADJ scatters -sum(adj)/sigma_n (:483-492)
-                            const float sn = sb - st;
-                            const float tr = sn / sb;
-                            if (BWD && mode == PM_NEE_ADJ && tr > 0.0f) {
+                            if (BWD && mode == PM_DRT) {
+                                // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
+                                const float wi = T / sb;
+                                drt_D += wi;
+                                if (u <= wi / drt_D) {
+                                    drt_t = wt;
+                                    drt_st = st;
+                                    drt_found = true;
+                                }
+                            } else if (BWD && mode == PM_NEE_ADJ && q > 0.0f) {
+                                // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)
                                 scatter_sigma(P, px, py, pz, -asum / sn);
                                 K.add(C_SSCAT, 1);
                             }
-                            T *= tr;
-                            if (T == 0.0f) cont = false;
+                            // ratio tracking (:461-502) / running transmittance of the DRT walk
+                            T *= q;
+                            if (mode == PM_DRT ? !(T > 0.0f) : T == 0.0f) cont = false;
                         }
                         if (cont) tau = neg_log1m(draw(rng, K));
                         else wstate = W_IDLE;
@@ -414,7 +424,9 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
                 if (mode == PM_DELTA) {
                     PSET(F_ST, s, sigma_t);
                     PU(F_FLAGS, s) = did_scatter ? (wflags | FL_DID_SCATTER) : (wflags & ~FL_DID_SCATTER);
-                    next = Q_VERTEX;
+                    // vertices of the adjoint replay scatter gradients: they get their own queue so that
+                    // the scatter loop of a batch runs with all lanes
+                    next = (BWD && (wflags & FL_PASS_MASK) == (unsigned) PP_ADJ) ? Q_VERTEX_ADJ : Q_VERTEX;
                 } else if (mode == PM_NEE) {
                     PSET(F_T, s, T);
                     next = Q_NEE_END;
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(kPoolBlock, 1) k_pool(const Params P) {
             // ==========================================================================
             const int got = q_pop(work, 32, exact, s);
             const bool act = (int) lane < got;
-            if (work == Q_VERTEX) {
+            if (work == Q_VERTEX || work == Q_VERTEX_ADJ) {
                 // ---- end of a delta-tracking segment (:130-245) or of the DRT walk (:550-558) ----
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
@@ -907,17 +919,19 @@ constexpr int kPoolSlotsFwd = UIVR_POOL_SLOTS_FWD;
 
 inline int launch_pool(int num_sms, bool backward, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
-#define UIVR_POOL_LAUNCH(B, C, N)                                                                       \
+#define UIVR_POOL_LAUNCH(B, C, N, T, H)                                                                 \
     do {                                                                                                \
         const size_t smem = pool_smem_bytes<B, N>();                                                    \
-        e = cudaFuncSetAttribute(k_pool<B, C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        e = cudaFuncSetAttribute(k_pool<B, C, N, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
-        k_pool<B, C, N><<<num_sms, kPoolBlock, smem, st>>>(P);                                          \
+        k_pool<B, C, N, T, H><<<num_sms, T, smem, st>>>(P);                                             \
     } while (0)
     if (backward) {
-        if (counting) UIVR_POOL_LAUNCH(true, true, kPoolSlotsBwd); else UIVR_POOL_LAUNCH(true, false, kPoolSlotsBwd);
+        if (counting) UIVR_POOL_LAUNCH(true, true, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD);
+        else UIVR_POOL_LAUNCH(true, false, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD);
     } else {
-        if (counting) UIVR_POOL_LAUNCH(false, true, kPoolSlotsFwd); else UIVR_POOL_LAUNCH(false, false, kPoolSlotsFwd);
+        if (counting) UIVR_POOL_LAUNCH(false, true, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD);
+        else UIVR_POOL_LAUNCH(false, false, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD);
     }
 #undef UIVR_POOL_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
