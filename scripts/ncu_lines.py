@@ -57,7 +57,8 @@ def main():
     rows = allrows[starts[skip]:starts[skip + 1]]
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
-    ci = {k: hdr.index(k) for k in ("Address", "Source", "# Samples", "Instructions Executed",
+    samples_col = os.environ.get("NCU_LINES_STALL", "# Samples")  # e.g. stall_no_inst
+    ci = {k: hdr.index(k) for k in ("Address", "Source", samples_col, "Instructions Executed",
                                     "Thread Instructions Executed", "Predicated-On Thread Instructions Executed")}
     agg = defaultdict(lambda: [0, 0, 0, 0])
     base = None
@@ -71,7 +72,7 @@ def main():
         off = addr - base
         key = lm.get(off, ((None, -1), ""))[0]
         v = [int(r[ci["Instructions Executed"]] or 0), int(r[ci["Thread Instructions Executed"]] or 0),
-             int(r[ci["Predicated-On Thread Instructions Executed"]] or 0), int(r[ci["# Samples"]] or 0)]
+             int(r[ci["Predicated-On Thread Instructions Executed"]] or 0), int(r[ci[samples_col]] or 0)]
         for i in range(4):
             agg[key][i] += v[i]
             tot[i] += v[i]

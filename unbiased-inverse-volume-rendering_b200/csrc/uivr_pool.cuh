@@ -62,6 +62,7 @@ enum : int { W_IDLE = 0, W_WALKING = 1, W_PENDING = 2 };
 // that steps below zero clears its guard without borrowing from its neighbour
 constexpr unsigned kGuard3 = (512u) | (512u << 10) | (512u << 20);
 constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
+constexpr unsigned kPoolHandlerSleepMax = 512;   // ns; idle handler warps back off up to this
 constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
 constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
@@ -449,6 +450,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         // "no full queue and nothing to walk anywhere" cannot happen: NSLOT > (Q_NUM - 1) * 31
         // slots cannot all sit in non-full queues.
         // ==================================================================================
+        int last_work = Q_FREE;
+        unsigned idle_ns = 32;
         for (;;) {
             if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
             // per-queue fill levels, one queue per lane
@@ -456,12 +459,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             int work = -1;
             bool exact = true;
             {
-                // fullest queue first
+                // Stay on the queue served last while it still holds a full batch (its handler code is
+                // hot in the instruction caches), else take the fullest queue.
+                const int c_last = __shfl_sync(FULL, cnt, last_work & 31);
                 int best = (cnt << 3) | (int) lane;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
                 best = __shfl_sync(FULL, best, 0);
-                if ((best >> 3) >= 32) {
+                if (c_last >= 32) {
+                    work = last_work;
+                } else if ((best >> 3) >= 32) {
                     work = best & 7;
                 } else if ((best >> 3) > 0 && __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0)) {
                     work = best & 7;
@@ -471,10 +478,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             if (work < 0) {
                 if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
                 if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
-                __nanosleep(64);
+                __nanosleep(idle_ns);
+                idle_ns = idle_ns < kPoolHandlerSleepMax ? idle_ns * 2 : idle_ns;  // back off: polling costs issue slots
                 continue;
             }
             t_progress = clock64();
+            idle_ns = 32;
+            last_work = work;
 
             // per-lane result of the work item: slot `s` goes to queue `next` (-1: nothing to route)
             unsigned s = 0;
