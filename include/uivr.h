@@ -146,7 +146,9 @@ int uivr_check_watchdog(uivr_ctx* ctx, uint32_t out[64], void* stream);
 /* number of kernel launches issued by this context so far */
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
 /* kernel variant: 0 = persistent lane-refill megakernel, 1 = one-sample-per-lane,
- * 2 = persistent slot-pool megakernel (CTA-wide compaction through shared-memory queues) */
+ * 2 = persistent slot-pool megakernel (CTA-wide compaction through shared-memory queues),
+ * 3 = slot-pool kernels with the backward split into primal replay -> adjoint replay -> DRT
+ *     launches that hand per-sample state through context-owned HBM scratch (default) */
 int uivr_set_variant(uivr_ctx* ctx, int variant);
 
 /* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */

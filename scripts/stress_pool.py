@@ -35,7 +35,7 @@ def run(variant, n, w, h, spp, factor, combo="volpathsimple-drt", max_depth=64):
 
 def main(n=64, w=256, h=256, spp=16, factor=8):
     ref = run(0, n, w, h, spp, factor)
-    new = run(2, n, w, h, spp, factor)
+    new = run(int(os.environ.get("UIVR_STRESS_VARIANT", "3")), n, w, h, spp, factor)
     ok = True
     for name, a, b in zip(("image", "samples_fwd", "samples_bwd"), ref[:3], new[:3]):
         same = torch.equal(a.view(torch.int32), b.view(torch.int32)) if name != "image" else float((a - b).abs().max()) < 1e-5

@@ -58,7 +58,7 @@ def _run_backward(uivr, vol, props, sig, alb, gimg, seed, spp, dev, variant, sha
     return ds.cpu().numpy(), da.cpu().numpy(), samples.cpu().numpy(), cnt
 
 
-VARIANTS = [0, 1, 2]
+VARIANTS = [0, 1, 2, 3]
 
 
 # ---------------------------------------------------------------------------------------

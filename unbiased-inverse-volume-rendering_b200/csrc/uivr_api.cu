@@ -28,7 +28,13 @@ struct uivr_ctx {
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
     unsigned int* debug = nullptr;  // [64] watchdog record of the slot-pool kernel
-    int variant = 2;
+    // scratch of the split backward pipeline (variant 3): per-sample radiance of the primal replay
+    // and the reservoir records handed from the adjoint launch to the DRT launch
+    float* scratch_L = nullptr;
+    size_t scratch_L_samples = 0;
+    uint32_t* records = nullptr;
+    size_t records_cap = 0;
+    int variant = 3;
     int counting = 0;
     uint64_t launches = 0;
     // staging for the *_host entry points
@@ -69,7 +75,7 @@ int check_ready(uivr_ctx* ctx) {
 
 // the slot-pool kernel packs depth into 16 bits and the supergrid step counters into 9 bits
 bool pool_ok(const uivr_ctx* ctx) {
-    return ctx->variant == 2 && ctx->props.max_depth < 65536 && ctx->mres[0] <= 512 && ctx->mres[1] <= 512 &&
+    return ctx->variant >= 2 && ctx->props.max_depth < 65536 && ctx->mres[0] <= 512 && ctx->mres[1] <= 512 &&
            ctx->mres[2] <= 512;
 }
 
@@ -205,7 +211,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
     for (int i = 0; i < 2; ++i)
@@ -248,7 +254,7 @@ int uivr_set_counting(uivr_ctx* ctx, int enable) {
 }
 
 int uivr_set_variant(uivr_ctx* ctx, int variant) {
-    if (!ctx || variant < 0 || variant > 2) return UIVR_ERR_INVALID;
+    if (!ctx || variant < 0 || variant > 3) return UIVR_ERR_INVALID;
     ctx->variant = variant;
     return UIVR_OK;
 }
@@ -364,7 +370,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
             k_forward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
     } else if (pool_ok(ctx)) {
-        if ((rc = launch_pool(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+        if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
         if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }
@@ -409,7 +415,41 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
     } else if (pool_ok(ctx)) {
-        if ((rc = launch_pool(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+        const bool split = ctx->variant == 3 && ctx->props.use_drt && ctx->props.use_drt_subsampling;
+        if (!split) {
+            if ((rc = launch_pool(ctx->num_sms, KIND_BWD, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+        } else {
+            // split pipeline: primal replay (forward kernel, radiance per sample to HBM) -> adjoint replay
+            // (reservoir records to HBM) -> DRT pass.  Work counters: [0] primal, [1] adjoint, [2] DRT, [3] records.
+            const size_t n_global = (size_t) P.npix * P.spp, n_local = (size_t) P.n_slots * P.spp;
+            if (!P.sample_L) {
+                if (ctx->scratch_L_samples < n_global) {
+                    cudaFree(ctx->scratch_L);
+                    ctx->scratch_L = nullptr;
+                    ctx->scratch_L_samples = 0;
+                    UIVR_CUDA(ctx, cudaMalloc(&ctx->scratch_L, n_global * 3 * sizeof(float)));
+                    ctx->scratch_L_samples = n_global;
+                }
+                P.sample_L = ctx->scratch_L;
+            }
+            if (ctx->records_cap < n_local) {
+                cudaFree(ctx->records);
+                ctx->records = nullptr;
+                ctx->records_cap = 0;
+                UIVR_CUDA(ctx, cudaMalloc(&ctx->records, n_local * kRecWords * sizeof(uint32_t)));
+                ctx->records_cap = n_local;
+            }
+            P.records = ctx->records;
+            P.rec_count = ctx->work_counter + 3;
+            Params PA = P;
+            PA.image = nullptr;
+            if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, PA, st))) return fail(ctx, rc, "pool kernel launch failed");
+            P.work_counter = ctx->work_counter + 1;
+            if ((rc = launch_pool(ctx->num_sms, KIND_ADJ, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+            P.work_counter = ctx->work_counter + 2;
+            if ((rc = launch_pool(ctx->num_sms, KIND_DRT, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+            ctx->launches += 2;
+        }
     } else {
         if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }

@@ -53,6 +53,8 @@ struct Params {
     float* dalbedo;           // [Z,Y,X,3]
     unsigned long long* counters;
     unsigned int* work_counter;
+    uint32_t* records;        // split backward: reservoir records (kRecWords words each), adjoint -> DRT launch
+    unsigned int* rec_count;  // number of records appended
     unsigned int* debug;      // [64] watchdog record of the slot-pool kernel (word 0 != 0: tripped)
 };
 

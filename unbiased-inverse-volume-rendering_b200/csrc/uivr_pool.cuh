@@ -32,6 +32,24 @@ namespace uivr {
 #ifndef UIVR_POOL_HANDLERS_BWD
 #define UIVR_POOL_HANDLERS_BWD 12
 #endif
+#ifndef UIVR_POOL_BLOCK_ADJ
+#define UIVR_POOL_BLOCK_ADJ 896
+#endif
+#ifndef UIVR_POOL_HANDLERS_ADJ
+#define UIVR_POOL_HANDLERS_ADJ 12
+#endif
+#ifndef UIVR_POOL_SLOTS_ADJ
+#define UIVR_POOL_SLOTS_ADJ 896
+#endif
+#ifndef UIVR_POOL_BLOCK_DRT
+#define UIVR_POOL_BLOCK_DRT 896
+#endif
+#ifndef UIVR_POOL_HANDLERS_DRT
+#define UIVR_POOL_HANDLERS_DRT 12
+#endif
+#ifndef UIVR_POOL_SLOTS_DRT
+#define UIVR_POOL_SLOTS_DRT 896
+#endif
 #ifndef UIVR_POOL_BLOCK_FWD
 #define UIVR_POOL_BLOCK_FWD 1024
 #endif
@@ -114,6 +132,14 @@ struct PoolCtl {
     int abort;       // watchdog tripped: every warp leaves
 };
 
+// kernel kinds: the forward / primal kernel, the combined backward kernel (primal replay + adjoint
+// + DRT in one launch), and the two halves of the SPLIT backward pipeline, which runs the primal
+// replay with the forward kernel (per-sample radiance to HBM), then the adjoint replay (reservoir
+// records to HBM), then the DRT pass.  Splitting trades ~1.3 GB of coalesced HBM traffic (the
+// path is at < 10 % of the HBM roofline) for three lean kernels with fewer live modes each.
+enum : int { KIND_FWD = 0, KIND_BWD = 1, KIND_ADJ = 2, KIND_DRT = 3 };
+constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) alt seq(1) depth(1) pad(2)
+
 template <bool BWD, int NSLOT>
 constexpr size_t pool_smem_bytes() {
     return 128 + (size_t) Q_NUM * NSLOT * sizeof(unsigned) +
@@ -122,8 +148,12 @@ constexpr size_t pool_smem_bytes() {
 
 // BLOCK threads per CTA (one CTA per SM), of which the first HANDLERS warps serve the transition
 // queues and the rest walk
-template <bool BWD, bool COUNT, int NSLOT, int BLOCK, int HANDLERS>
+template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS>
 __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
+    constexpr bool BWD = KIND != KIND_FWD;                            // any gradient work
+    constexpr bool HAS_PRIMAL = KIND == KIND_FWD || KIND == KIND_BWD; // sample(Primal) from the camera
+    constexpr bool HAS_ADJ = KIND == KIND_BWD || KIND == KIND_ADJ;    // adjoint replay (reservoir, NEE adjoint)
+    constexpr bool HAS_DRT = KIND == KIND_BWD || KIND == KIND_DRT;    // DRT walk, DRT vertex, recursive path
     constexpr int kPoolBlock = BLOCK;
     constexpr int kPoolHandlerWarps = HANDLERS;
     static_assert(NSLOT > (Q_NUM - 1) * 31 && NSLOT % 32 == 0, "pool too small for the full-batch scheduling rule");
@@ -137,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint64_t total = (uint64_t) P.n_slots * P.spp;
+    const uint64_t total = KIND == KIND_DRT ? (uint64_t) *P.rec_count : (uint64_t) P.n_slots * P.spp;
     const bool use_rsv = BWD && P.use_drt && P.use_drt_subsampling;
 
 #define PU(f, s) pool[(f) * NSLOT + (s)]
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             drt_D = 0.0f;
                             drt_found = false;
                             did_scatter = false;
-                            if (BWD) asum = PF(F_ASUM, s);
+                            if (HAS_ADJ) asum = PF(F_ASUM, s);
                             // walk_init (Medium::sample_interaction set-up, App. B.5)
                             const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
                             const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
@@ -390,7 +420,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 cont = false;
                             }
                         } else {
-                            if (BWD && mode == PM_DRT) {
+                            if (HAS_DRT && mode == PM_DRT) {
                                 // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
                                 const float wi = T / sb;
                                 drt_D += wi;
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                     drt_st = st;
                                     drt_found = true;
                                 }
-                            } else if (BWD && mode == PM_NEE_ADJ && q > 0.0f) {
+                            } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
                                 // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)
                                 scatter_sigma(P, px, py, pz, -asum / sn);
                                 K.add(C_SSCAT, 1);
@@ -427,14 +457,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_FLAGS, s) = did_scatter ? (wflags | FL_DID_SCATTER) : (wflags & ~FL_DID_SCATTER);
                     // vertices of the adjoint replay scatter gradients: they get their own queue so that
                     // the scatter loop of a batch runs with all lanes
-                    next = (BWD && (wflags & FL_PASS_MASK) == (unsigned) PP_ADJ) ? Q_VERTEX_ADJ : Q_VERTEX;
+                    next = (HAS_ADJ && (wflags & FL_PASS_MASK) == (unsigned) PP_ADJ) ? Q_VERTEX_ADJ : Q_VERTEX;
                 } else if (mode == PM_NEE) {
                     PSET(F_T, s, T);
                     next = Q_NEE_END;
-                } else if (BWD && mode == PM_NEE_ADJ) {
+                } else if (HAS_ADJ && mode == PM_NEE_ADJ) {
                     PU(F_FLAGS, s) = wflags | FL_SPAWN_PHASE;
                     next = Q_SPAWN;
-                } else if (BWD) {
+                } else if (HAS_DRT && mode == PM_DRT) {
                     PSET(F_DRT_D, s, drt_D); PSET(F_DRT_T, s, drt_t); PSET(F_DRT_ST, s, drt_st);
                     PU(F_FLAGS, s) = drt_found ? (wflags | FL_DRT_FOUND) : (wflags & ~FL_DRT_FOUND);
                     next = Q_VERTEX;  // the vertex handler serves the DRT vertex as well
@@ -508,7 +538,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const unsigned dw = PU(F_DEPTH, s);
                     int depth = (int) (dw & 0xFFFFu);
                     const int pass = (int) (fl & FL_PASS_MASK);
-                    const bool is_drt = BWD && ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT) == (unsigned) PM_DRT;
+                    const bool is_drt = HAS_DRT && ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT) == (unsigned) PM_DRT;
                     const bool ds = is_drt ? (fl & FL_DRT_FOUND) != 0u : (fl & FL_DID_SCATTER) != 0u;
                     // vertex position: on the stored reservoir segment for DRT, else on the current segment
                     const int fo = is_drt ? F_RSOX : F_OX, fd = is_drt ? F_RSDX : F_DX;
@@ -541,7 +571,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             fl |= FL_HAS_SCATTERED;
                             K.add(C_REAL, 1);
                         }
-                        if (BWD && pass == PP_ADJ) {
+                        if (HAS_ADJ && pass == PP_ADJ) {
                             alt.state = (uint64_t) PU(F_ALT_LO, s) | ((uint64_t) PU(F_ALT_HI, s) << 32);
                             alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
                             const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
@@ -623,9 +653,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     contrib[1] = (PF(F_B1, s) * P.half_le[1]) * Tn;
                     contrib[2] = (PF(F_B2, s) * P.half_le[2]) * Tn;
                     next = Q_SPAWN;
-                    if (BWD && pass == PP_DRTV) {
+                    if (HAS_DRT && pass == PP_DRTV) {
                         PSET(F_LI0, s, contrib[0]); PSET(F_LI1, s, contrib[1]); PSET(F_LI2, s, contrib[2]);
-                    } else if (BWD && pass == PP_ADJ) {
+                    } else if (HAS_ADJ && pass == PP_ADJ) {
                         PSET(F_R0, s, PF(F_R0, s) - contrib[0]);  // path replay (:214)
                         PSET(F_R1, s, PF(F_R1, s) - contrib[1]);
                         PSET(F_R2, s, PF(F_R2, s) - contrib[2]);
@@ -646,13 +676,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_FLAGS, s) = fl;
                 }
             } else if (work == Q_PATH_END) {
+                bool want_rec = false;
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
                     const int pass = (int) (fl & FL_PASS_MASK);
                     const unsigned dw = PU(F_DEPTH, s);
                     const int depth = (int) (dw & 0xFFFFu);
                     float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
-                    if (pass == PP_PRIMAL || (BWD && pass == PP_REC)) {
+                    if (pass == PP_PRIMAL || (HAS_DRT && pass == PP_REC)) {
                         // :263-285 envmap
                         if ((fl & FL_ESCAPED) && !(depth <= 0 && P.hide_emitters)) {
                             const float wmis = (P.use_nee && (fl & FL_HAS_SCATTERED)) ? 0.5f : 1.0f;
@@ -669,16 +700,18 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             P.sample_L[3 * (size_t) idx + 1] = R[1];
                             P.sample_L[3 * (size_t) idx + 2] = R[2];
                         }
-                        if (!BWD) {
-                            atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
-                            atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
-                            atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                        if (KIND == KIND_FWD) {
+                            if (P.image) {  // (null when this launch is the primal replay of the split backward)
+                                atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                                atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                                atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                            }
                         } else {
                             // batched.py:309-318: sample(Backward, state_in = L)
                             PSET(F_R0, s, R[0]); PSET(F_R1, s, R[1]); PSET(F_R2, s, R[2]);
                             fl = (fl & ~FL_PASS_MASK) | (unsigned) PP_ADJ | FL_RESTART;
                         }
-                    } else if (BWD && pass == PP_ADJ) {
+                    } else if (HAS_ADJ && pass == PP_ADJ) {
                         if (use_rsv && (fl & FL_RS_VALID)) {
                             // DRTReservoir.get (:756-760) and adjoint = weight * dL (:255)
                             const float wcur[3] = {PF(F_RSC0, s), PF(F_RSC1, s), PF(F_RSC2, s)};
@@ -689,16 +722,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 const float W = (d != 0.0f) ? (ws * wcur[c]) / d : 0.0f;
                                 PSET(F_DL0 + c, s, W * PF(F_DL0 + c, s));
                             }
+                            if (KIND == KIND_ADJ) {
+                                want_rec = true;  // the DRT pass is a separate launch: hand the sample over through HBM
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < 7; ++k) PU(F_OX + k, s) = PU(F_RSOX + k, s);  // o, d, tmax
-                            PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (dw >> 16);
-                            // everything from here on draws from the alt stream
-                            PU(F_RNG_LO, s) = PU(F_ALT_LO, s); PU(F_RNG_HI, s) = PU(F_ALT_HI, s);
-                            PU(F_SEQ, s) = PU(F_ASEQ, s);
-                            fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DRT << FL_MODE_SHIFT);
-                            next = Q_WALK;
+                                for (int k = 0; k < 7; ++k) PU(F_OX + k, s) = PU(F_RSOX + k, s);  // o, d, tmax
+                                PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (dw >> 16);
+                                // everything from here on draws from the alt stream
+                                PU(F_RNG_LO, s) = PU(F_ALT_LO, s); PU(F_RNG_HI, s) = PU(F_ALT_HI, s);
+                                PU(F_SEQ, s) = PU(F_ASEQ, s);
+                                fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DRT << FL_MODE_SHIFT);
+                                next = Q_WALK;
+                            }
                         }
-                    } else if (BWD) {  // PP_REC: Li complete -> DRT gradient (:571-581)
+                    } else if (HAS_DRT) {  // PP_REC: Li complete -> DRT gradient (:571-581)
                         const float dst = PF(F_DRT_ST, s), dD = PF(F_DRT_D, s), dt = PF(F_DRT_T, s);
                         const float m = P.use_drt_mis ? 1.0f / (1.0f + dst * dst) : 1.0f;
 #pragma unroll
@@ -714,6 +751,24 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         sc_ff = true;
                     }
                     PU(F_FLAGS, s) = fl;
+                }
+                if (KIND == KIND_ADJ) {
+                    // reservoir record for the DRT launch (warp-aggregated append)
+                    const unsigned m = __ballot_sync(FULL, want_rec);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        unsigned base = 0;
+                        if ((int) lane == leader) base = atomicAdd(P.rec_count, (unsigned) __popc(m));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (want_rec) {
+                            uint32_t* rec = P.records + (size_t) (base + __popc(m & lt_mask)) * kRecWords;
+                            uint4* r4 = reinterpret_cast<uint4*>(rec);
+                            r4[0] = make_uint4(PU(F_RSOX, s), PU(F_RSOY, s), PU(F_RSOZ, s), PU(F_RSDX, s));
+                            r4[1] = make_uint4(PU(F_RSDY, s), PU(F_RSDZ, s), PU(F_RSTMAX, s), PU(F_DL0, s));
+                            r4[2] = make_uint4(PU(F_DL1, s), PU(F_DL2, s), PU(F_ALT_LO, s), PU(F_ALT_HI, s));
+                            r4[3] = make_uint4(PU(F_ASEQ, s), PU(F_DEPTH, s) >> 16, 0u, 0u);
+                        }
+                    }
                 }
             } else if (work == Q_SPAWN) {
                 // ---- emitter sampling (:406-433) / phase sampling (:221-245, :626-652) ----
@@ -735,7 +790,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     bool active = (fl & FL_ACTIVE) != 0u;
                     bool rr = false;  // Russian-roulette draw + zero-throughput test of the next loop iteration
                     if (!phase) {
-                        if (BWD && (fl & FL_PASS_MASK) == (unsigned) PP_ADJ) {
+                        if (HAS_ADJ && (fl & FL_PASS_MASK) == (unsigned) PP_ADJ) {
                             // sampler.clone() position for the adjoint replay (:383)
                             PU(F_CLONE_LO, s) = (uint32_t) r.state;
                             PU(F_CLONE_HI, s) = (uint32_t) (r.state >> 32);
@@ -746,7 +801,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         next = ok ? Q_WALK : Q_NEE_END;
                     } else {
                         fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DELTA << FL_MODE_SHIFT);
-                        if (BWD && (fl & FL_PASS_MASK) == (unsigned) PP_DRTV) {
+                        if (HAS_DRT && (fl & FL_PASS_MASK) == (unsigned) PP_DRTV) {
                             const unsigned dw = PU(F_DEPTH, s);
                             const int depth = (int) (dw & 0xFFFFu) + 1;
                             PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (unsigned) depth;
@@ -776,6 +831,37 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             } else {
                 // ---- Q_FREE: next sample from the global queue / adjoint re-start: ray generation +
                 //      reach_medium (batched.py:426-467, volpathsimple.py:292-319) ----
+                if (KIND == KIND_DRT) {
+                    // split pipeline, DRT launch: the work items are the reservoir records of the adjoint launch
+                    bool none_left = true;
+                    const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
+                    const unsigned fresh = __ballot_sync(FULL, act);
+                    if (exh == 0 && fresh) {
+                        const int leader = __ffs(fresh) - 1;
+                        unsigned base = 0;
+                        if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
+                        base = __shfl_sync(FULL, base, leader);
+                        const uint64_t item = (uint64_t) base + __popc(fresh & lt_mask);
+                        if (act && item < total) {
+                            none_left = false;
+                            const uint4* r4 = reinterpret_cast<const uint4*>(P.records + (size_t) item * kRecWords);
+                            const uint4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+                            // DRT on the stored segment (:543-581): the walk draws from the alt stream
+                            PU(F_OX, s) = a.x; PU(F_OY, s) = a.y; PU(F_OZ, s) = a.z; PU(F_DX, s) = a.w;
+                            PU(F_DY, s) = b.x; PU(F_DZ, s) = b.y; PU(F_TMAX, s) = b.z;
+                            PU(F_RSOX, s) = a.x; PU(F_RSOY, s) = a.y; PU(F_RSOZ, s) = a.z; PU(F_RSDX, s) = a.w;
+                            PU(F_RSDY, s) = b.x; PU(F_RSDZ, s) = b.y;
+                            PU(F_DL0, s) = b.w; PU(F_DL1, s) = c.x; PU(F_DL2, s) = c.y;
+                            PU(F_RNG_LO, s) = c.z; PU(F_RNG_HI, s) = c.w; PU(F_SEQ, s) = d.x;
+                            PU(F_DEPTH, s) = d.y;
+                            PU(F_FLAGS, s) = (unsigned) PP_ADJ | ((unsigned) PM_DRT << FL_MODE_SHIFT);
+                            next = Q_WALK;
+                        }
+                        if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
+                    }
+                    const unsigned retire = __ballot_sync(FULL, act && none_left);
+                    if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
+                } else {
                 unsigned fl = act ? PU(F_FLAGS, s) : 0u;
                 const bool restart = act && (fl & FL_RESTART);
                 bool have = restart;
@@ -798,8 +884,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 if (slot_to_pixel(P, it / P.spp, pix)) {
                                     idx = pix * P.spp + it % P.spp;
                                     have = true;
-                                    fl = (unsigned) PP_PRIMAL;
-                                    K.add(C_SAMPLES, 1);
+                                    fl = (unsigned) (KIND == KIND_ADJ ? PP_ADJ : PP_PRIMAL);
+                                    if (HAS_PRIMAL) K.add(C_SAMPLES, 1);
                                 } else {
                                     next = Q_FREE;  // padding slot of a shard: try again
                                 }
@@ -813,7 +899,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 }
                 if (have) {
                     const int pass = (int) (fl & FL_PASS_MASK);
-                    const bool adj = BWD && pass == PP_ADJ;
+                    const bool adj = HAS_ADJ && pass == PP_ADJ;
                     Rng r;
                     r.state = r.inc = 0;
 #pragma unroll 1
@@ -830,6 +916,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             PSET(F_DL0 + c, s, __ldg(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
                             PSET(F_RSW0 + c, s, 0.0f);
                             PSET(F_RSC0 + c, s, 0.0f);
+                            // split pipeline: state_in = radiance of the primal replay launch (batched.py:255-264)
+                            if (KIND == KIND_ADJ) PSET(F_R0 + c, s, P.sample_L[3 * (size_t) idx + c]);
                         }
                     } else {
                         PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
@@ -868,10 +956,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 P.sample_L[3 * (size_t) idx + 1] = R[1];
                                 P.sample_L[3 * (size_t) idx + 2] = R[2];
                             }
-                            if (!BWD) {
-                                atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
-                                atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
-                                atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                            if (KIND == KIND_FWD) {
+                                if (P.image) {
+                                    atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                                    atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                                    atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                                }
                             } else if (COUNT) {
                                 // the adjoint pass of a missed ray draws jitter + :71 and nothing else
                                 K.add(C_DRAWS, 3);
@@ -883,6 +973,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_FLAGS, s) = fl;
                 } else if (next == Q_FREE) {
                     PU(F_FLAGS, s) = 0u;
+                }
                 }
             }
 
@@ -927,22 +1018,28 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 constexpr int kPoolSlotsBwd = UIVR_POOL_SLOTS_BWD;
 constexpr int kPoolSlotsFwd = UIVR_POOL_SLOTS_FWD;
 
-inline int launch_pool(int num_sms, bool backward, bool counting, const Params& P, cudaStream_t st) {
+// kind: KIND_FWD / KIND_BWD / KIND_ADJ / KIND_DRT
+inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
-#define UIVR_POOL_LAUNCH(B, C, N, T, H)                                                                 \
+#define UIVR_POOL_LAUNCH(KD, C, N, T, H)                                                                \
     do {                                                                                                \
-        const size_t smem = pool_smem_bytes<B, N>();                                                    \
-        e = cudaFuncSetAttribute(k_pool<B, C, N, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N>();                                     \
+        e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
-        k_pool<B, C, N, T, H><<<num_sms, T, smem, st>>>(P);                                             \
+        k_pool<KD, C, N, T, H><<<num_sms, T, smem, st>>>(P);                                            \
     } while (0)
-    if (backward) {
-        if (counting) UIVR_POOL_LAUNCH(true, true, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD);
-        else UIVR_POOL_LAUNCH(true, false, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD);
-    } else {
-        if (counting) UIVR_POOL_LAUNCH(false, true, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD);
-        else UIVR_POOL_LAUNCH(false, false, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD);
+#define UIVR_POOL_LAUNCH2(KD, N, T, H)                                                                  \
+    do {                                                                                                \
+        if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H); else UIVR_POOL_LAUNCH(KD, false, N, T, H);   \
+    } while (0)
+    switch (kind) {
+        case KIND_FWD: UIVR_POOL_LAUNCH2(KIND_FWD, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD); break;
+        case KIND_BWD: UIVR_POOL_LAUNCH2(KIND_BWD, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD); break;
+        case KIND_ADJ: UIVR_POOL_LAUNCH2(KIND_ADJ, UIVR_POOL_SLOTS_ADJ, UIVR_POOL_BLOCK_ADJ, UIVR_POOL_HANDLERS_ADJ); break;
+        case KIND_DRT: UIVR_POOL_LAUNCH2(KIND_DRT, UIVR_POOL_SLOTS_DRT, UIVR_POOL_BLOCK_DRT, UIVR_POOL_HANDLERS_DRT); break;
+        default: return -1;
     }
+#undef UIVR_POOL_LAUNCH2
 #undef UIVR_POOL_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
