@@ -17,6 +17,6 @@ else
   shift
   for so in sweep/*.so; do
     echo "== $so"
-    UIVR_LIB=$PWD/$so timeout 200 python scripts/quick_bench.py variant=2 reps=3 "$@" 2>&1 | grep "Msamples" | tail -1
+    UIVR_LIB=$PWD/$so timeout 200 python scripts/quick_bench.py variant=${SWEEP_VARIANT:-3} reps=3 "$@" 2>&1 | grep "Msamples" | tail -1
   done
 fi

@@ -33,22 +33,22 @@ namespace uivr {
 #define UIVR_POOL_HANDLERS_BWD 12
 #endif
 #ifndef UIVR_POOL_BLOCK_ADJ
-#define UIVR_POOL_BLOCK_ADJ 896
+#define UIVR_POOL_BLOCK_ADJ 768
 #endif
 #ifndef UIVR_POOL_HANDLERS_ADJ
-#define UIVR_POOL_HANDLERS_ADJ 12
+#define UIVR_POOL_HANDLERS_ADJ 8
 #endif
 #ifndef UIVR_POOL_SLOTS_ADJ
-#define UIVR_POOL_SLOTS_ADJ 896
+#define UIVR_POOL_SLOTS_ADJ 768
 #endif
 #ifndef UIVR_POOL_BLOCK_DRT
-#define UIVR_POOL_BLOCK_DRT 896
+#define UIVR_POOL_BLOCK_DRT 768
 #endif
 #ifndef UIVR_POOL_HANDLERS_DRT
-#define UIVR_POOL_HANDLERS_DRT 12
+#define UIVR_POOL_HANDLERS_DRT 8
 #endif
 #ifndef UIVR_POOL_SLOTS_DRT
-#define UIVR_POOL_SLOTS_DRT 896
+#define UIVR_POOL_SLOTS_DRT 768
 #endif
 #ifndef UIVR_POOL_BLOCK_FWD
 #define UIVR_POOL_BLOCK_FWD 1024
