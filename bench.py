@@ -379,7 +379,7 @@ def run_native(args):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("k_pool_bwd_dram_bytes_per_launch")
+                traffic = json.load(f).get("bwd_pipeline_dram_bytes_per_step")
         except (OSError, ValueError):
             traffic = None
 
@@ -401,7 +401,7 @@ def run_native(args):
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_pool<BWD> (slot-pool megakernel: primal replay + adjoint + DRT), rank 0",
+                         "kernel": "backward pipeline, rank 0: k_pool<FWD> primal replay -> k_pool<ADJ> adjoint replay -> k_pool<DRT> (three slot-pool launches timed as one bracket)",
                          "kernel_ms": bwd_ms, "algorithmic_bytes_per_launch": bytes_b,
                          "bytes_per_sample": bytes_b / my_samples,
                          "forward_kernel": {"kernel_ms": fwd_ms, "algorithmic_bytes_per_launch": bytes_f,

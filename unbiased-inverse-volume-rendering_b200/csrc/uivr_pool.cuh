@@ -80,6 +80,14 @@ enum : int { W_IDLE = 0, W_WALKING = 1, W_PENDING = 2 };
 // that steps below zero clears its guard without borrowing from its neighbour
 constexpr unsigned kGuard3 = (512u) | (512u << 10) | (512u << 20);
 constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
+#ifndef UIVR_POOL_MINBATCH
+#define UIVR_POOL_MINBATCH 12
+#endif
+#ifndef UIVR_POOL_STARVE
+#define UIVR_POOL_STARVE 16
+#endif
+constexpr int kPoolMinBatch = UIVR_POOL_MINBATCH;    // smallest handler batch while the walk queue runs dry
+constexpr int kPoolStarveBelow = UIVR_POOL_STARVE;   // "runs dry": fewer walk jobs than this are queued
 constexpr unsigned kPoolHandlerSleepMax = 512;   // ns; idle handler warps back off up to this
 constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
@@ -485,7 +493,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         for (;;) {
             if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
             // per-queue fill levels, one queue per lane
-            const int cnt = (lane < Q_NUM && lane != Q_WALK) ? *((volatile int*) &ctl->count[lane]) : 0;
+            const int cnt_all = (lane < Q_NUM) ? *((volatile int*) &ctl->count[lane]) : 0;
+            const int cnt = (lane != Q_WALK) ? cnt_all : 0;
+            // the walkers are running dry: accept smaller batches rather than let them idle
+            const int min_batch = __shfl_sync(FULL, cnt_all, Q_WALK) < kPoolStarveBelow ? kPoolMinBatch : 32;
             int work = -1;
             bool exact = true;
             {
@@ -498,8 +509,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 best = __shfl_sync(FULL, best, 0);
                 if (c_last >= 32) {
                     work = last_work;
-                } else if ((best >> 3) >= 32) {
+                } else if ((best >> 3) >= min_batch) {
                     work = best & 7;
+                    exact = (best >> 3) >= 32;
                 } else if ((best >> 3) > 0 && __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0)) {
                     work = best & 7;
                     exact = false;
