@@ -97,7 +97,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "25", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 

@@ -129,6 +129,18 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
                               const uivr_shard* shard, float* h_dsigma_t, float* h_dalbedo,
                               void* stream);
 
+/* ---- optimisation step ("next" row after the path itself) ----
+ * opt.step() of mi.ad.Adam (python/opt_config.py:46-48, python/optimize.py:352) fused with
+ * enforce_valid_params (python/optimize.py:169-179, :353): for every element
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p = clip(p - lr_t m / (sqrt(v) + eps), lo, hi),
+ *   lr_t = lr sqrt(1 - b2^t) / (1 - b1^t),  t = 1, 2, ...
+ * All arrays are DEVICE pointers of n floats (16-byte aligned); param / m / v are updated in
+ * place.  Call uivr_update_medium afterwards when the tensor is sigma_t (params.update(),
+ * python/optimize.py:354). */
+int uivr_adam_step(uivr_ctx* ctx, float* d_param, const float* d_grad, float* d_m, float* d_v,
+                   uint64_t n, float lr, float beta1, float beta2, float eps, int32_t t,
+                   float lo, float hi, void* stream);
+
 /* ---- instrumentation ---- */
 /* Event counters (SURVEY §8d algorithmic bytes).  Counting kernels are separate template
  * instances; enable only for accounting passes, not for timing. */

@@ -223,3 +223,13 @@ def build_majorant(sigma_t, scale: float, factor: int) -> np.ndarray:
     lib().uivr_oracle_build_majorant(_ptr(sigma_t, C.c_float), res, C.c_float(scale), factor, mres, _ptr(out, C.c_float))
     assert list(mres) == m
     return out
+
+
+def adam_step(param, grad, m, v, lr, beta1, beta2, eps, t, lo, hi):
+    """In place on float32 arrays: mi.ad.Adam step + clip (optimize.py:169-179, :352-353)."""
+    n = param.size
+    for a in (param, grad, m, v):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.size == n
+    lib().uivr_oracle_adam_step(_ptr(param, C.c_float), _ptr(grad, C.c_float), _ptr(m, C.c_float), _ptr(v, C.c_float),
+                                C.c_uint64(n), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                C.c_int32(t), C.c_float(lo), C.c_float(hi))

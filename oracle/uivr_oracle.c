@@ -954,3 +954,30 @@ int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sig
     free(C.majorant);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* optimiser step: mi.ad.Adam + enforce_valid_params (optimize.py:169-179, :352-353)    */
+/* ------------------------------------------------------------------------------------ */
+
+float uivr_oracle_adam_step_size(float lr, float beta1, float beta2, int32_t t) {
+    const double b1t = pow((double) beta1, (double) t), b2t = pow((double) beta2, (double) t);
+    return (float) ((double) lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+}
+
+void uivr_oracle_adam_step(float* param, const float* grad, float* m, float* v, uint64_t n,
+                           float lr, float beta1, float beta2, float eps, int32_t t,
+                           float lo, float hi) {
+    const float step = uivr_oracle_adam_step_size(lr, beta1, beta2, t);
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float g = grad[i];
+        const float mi = FMA(beta1, m[i], omb1 * g);
+        const float vi = FMA(beta2, v[i], (omb2 * g) * g);
+        float p = param[i] - (step * mi) / (sqrtf(vi) + eps);
+        p = p < lo ? lo : p;
+        p = p > hi ? hi : p;
+        m[i] = mi;
+        v[i] = vi;
+        param[i] = p;
+    }
+}

@@ -100,6 +100,17 @@ int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sig
                                 double* dsigma_out, double* dalbedo_out,
                                 float* sample_L_out, uint64_t* counters);
 
+/* ---- optimiser step ("next" row) ----
+ * mi.ad.Adam.step() (python/opt_config.py:46-48, python/optimize.py:352; update rule SURVEY App.
+ * B.10) followed by enforce_valid_params (python/optimize.py:169-179): clip to [lo, hi].
+ *   step = lr * sqrt(1 - beta2^t) / (1 - beta1^t)           (double on the host, then float)
+ *   m = fma(beta1, m, (1 - beta1) * g);  v = fma(beta2, v, ((1 - beta2) * g) * g)
+ *   p = clip(p - (step * m) / (sqrt(v) + eps), lo, hi) */
+float uivr_oracle_adam_step_size(float lr, float beta1, float beta2, int32_t t);
+void  uivr_oracle_adam_step(float* param, const float* grad, float* m, float* v, uint64_t n,
+                            float lr, float beta1, float beta2, float eps, int32_t t,
+                            float lo, float hi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,11 +6,11 @@ nproc >> gpurun_out/gpu.txt
 ( time python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-for v in 2 0 1; do python scripts/quick_bench.py variant=$v reps=3 > gpurun_out/quick_v$v.log 2>&1; tail -4 gpurun_out/quick_v$v.log | head -2; done
+for v in 3 2 0 1; do python scripts/quick_bench.py variant=$v reps=3 > gpurun_out/quick_v$v.log 2>&1; tail -4 gpurun_out/quick_v$v.log | head -2; done
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pool -s 2 -c 2 -f -o gpurun_out/prof_pool \
-    python scripts/profile_step.py variant=2 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pool -s 4 -c 4 -f -o gpurun_out/prof_split \
+    python scripts/profile_step.py variant=3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out

@@ -445,3 +445,53 @@ def test_full_size_properties_config3(uivr, dev):
     ds0, da0 = integ.render_backward(scene, params, torch.zeros_like(g), seed=uivr.tea32(1234, 1), spp=spp)
     assert float(ds0.abs().max()) == 0.0 and float(da0.abs().max()) == 0.0
     scene.ctx.check_watchdog()
+
+
+# ---------------------------------------------------------------------------------------
+# optimisation step
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1003, 1 << 16])
+def test_adam_step_bit_exact(uivr, oracle, dev, n):
+    """uivr_adam_step (fused mi.ad.Adam + enforce_valid_params) vs the oracle, bit for bit, over
+    three steps, ragged sizes, clipping active."""
+    rng = np.random.default_rng(n)
+    p = rng.uniform(-0.2, 1.2, n).astype(np.float32)
+    m = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    ctx = uivr._native.Context(0)
+    tp, tm, tv = _gpu(p, dev), _gpu(m, dev), _gpu(v, dev)
+    for t in (1, 2, 3):
+        g = rng.normal(0, 1e-3, n).astype(np.float32)
+        oracle.adam_step(p, g, m, v, 5e-3, 0.9, 0.999, 1e-8, t, 0.0, 1.0)
+        tg = _gpu(g, dev)
+        ctx.adam_step(tp.data_ptr(), tg.data_ptr(), tm.data_ptr(), tv.data_ptr(), n, 5e-3, 0.9, 0.999, 1e-8, t, 0.0, 1.0)
+        torch.cuda.synchronize()
+        for a, b in ((tp, p), (tm, m), (tv, v)):
+            assert np.array_equal(a.cpu().numpy().view(np.uint32), b.view(np.uint32))
+    with pytest.raises(uivr.NativeError):
+        ctx.adam_step(tp.data_ptr(), tp.data_ptr(), tm.data_ptr(), tv.data_ptr(), n, 5e-3, 0.9, 0.999, 1e-8, 0, 0.0, 1.0)
+
+
+def test_optimization_step_multiview(uivr, dev):
+    """Config-4 shaped step on a small problem: several views, L1 loss, Adam + projection + medium
+    rebuild.  The loss against renders of a target medium must go down and the parameters must
+    stay in their legal range (optimize.py:169-179)."""
+    n, w, h, spp = 16, 32, 32, 32
+    sig_t, alb_t = hetero_grids(n, seed=3)
+    vol = uivr.benchmark_scene(n, w, h, scale=6.0, majorant_resolution_factor=4)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.get_int_config("volpathsimple-drt").create(max_depth=16)
+    sensors = uivr.circle_sensors(4, w, h)
+    target = {"m.sigma_t.data": _gpu(sig_t, dev), "m.albedo.data": _gpu(alb_t, dev)}
+    refs = [integ.render(scene, target, sensor=s, seed=900 + i, spp=256).clone() for i, s in enumerate(sensors)]
+    params = {"m.sigma_t.data": torch.full((n, n, n, 1), 0.3, device=dev),
+              "m.albedo.data": torch.full((n, n, n, 3), 0.6, device=dev)}
+    opt = uivr.Adam(lr=2e-2, params=params)
+    opt.set_learning_rate(uivr.learning_rates(2e-2, list(params), 0, 20, "last25", {"m.albedo.data": 2.0}))
+    losses = [uivr.optimization_step(scene, integ, opt, sensors, refs, it, spp) for it in range(12)]
+    scene.ctx.check_watchdog()
+    assert np.mean(losses[-3:]) < 0.8 * np.mean(losses[:3]), losses
+    s, a = params["m.sigma_t.data"], params["m.albedo.data"]
+    assert float(s.min()) >= 0.0 and float(s.max()) <= 250.0 and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    assert opt.t == 12

@@ -370,3 +370,46 @@ def test_forward_ignores_ad_flags_and_seeds_matter(uivr, oracle):
     # hide_emitters removes directly visible radiance only (volpathsimple.py:268-269)
     h, _, _ = oracle.render_forward(vol.as_dict(), dict(base, use_drt=False, hide_emitters=True), sig, alb, 1, 4)
     assert np.all(h <= a + 1e-7) and h[0, 0].sum() == 0.0 and a[0, 0].sum() > 0.0
+
+
+# ---------------------------------------------------------------------------------------
+# optimiser step: mi.ad.Adam + enforce_valid_params
+# ---------------------------------------------------------------------------------------
+
+def test_adam_step_against_float64_restatement(oracle):
+    """SURVEY App. B.10 in float64 numpy vs the oracle's float32 restatement, three steps, with
+    the projection of optimize.py:169-179 active on part of the data."""
+    rng = np.random.default_rng(5)
+    n = 1003
+    p = rng.uniform(-0.2, 1.2, n).astype(np.float32)
+    m = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    p64, m64, v64 = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    lr, b1, b2, eps = 5e-3, 0.9, 0.999, 1e-8
+    for t in (1, 2, 3):
+        g = rng.normal(0, 1e-3, n).astype(np.float32)
+        oracle.adam_step(p, g, m, v, lr, b1, b2, eps, t, 0.0, 1.0)
+        m64 = b1 * m64 + (1 - b1) * g
+        v64 = b2 * v64 + (1 - b2) * g.astype(np.float64) ** 2
+        p64 = np.clip(p64 - lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t) * m64 / (np.sqrt(v64) + eps), 0.0, 1.0)
+        assert np.max(np.abs(p - p64)) < 2e-6
+        assert p.min() >= 0.0 and p.max() <= 1.0
+    assert np.allclose(m, m64, rtol=1e-5, atol=1e-9) and np.allclose(v, v64, rtol=1e-5, atol=1e-12)
+
+
+def test_learning_rate_schedule_and_bounds(uivr):
+    """opt_config.py:50-69 (Last25 halves the rate at 75 %, 85 %, 95 % of the run; per-key factors)
+    and optimize.py:169-179."""
+    keys = ["m.sigma_t.data", "m.albedo.data"]
+    f = {"m.albedo.data": 2.0}
+    assert uivr.learning_rates(5e-3, keys, 0, 101, "last25", f) == {keys[0]: 5e-3, keys[1]: 1e-2}
+    assert uivr.learning_rates(5e-3, keys, 75, 101, "last25", f)[keys[0]] == 2.5e-3
+    assert uivr.learning_rates(5e-3, keys, 85, 101, "last25", f)[keys[0]] == 1.25e-3
+    assert uivr.learning_rates(5e-3, keys, 100, 101, "last25", f)[keys[1]] == 1.25e-3
+    assert uivr.learning_rates(5e-3, keys, 100, 101, None)[keys[0]] == 5e-3
+    with pytest.raises(ValueError):
+        uivr.learning_rates(5e-3, keys, 1, 10, "cosine")
+    assert uivr.param_bounds("x.sigma_t.data", 250) == (0.0, 250.0)
+    assert uivr.param_bounds("x.albedo.data") == (0.0, 1.0)
+    with pytest.raises(ValueError):
+        uivr.param_bounds("x.bogus")

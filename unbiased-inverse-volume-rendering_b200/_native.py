@@ -24,7 +24,7 @@ EXPORTS = [
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
-    "uivr_set_variant", "uivr_check_watchdog",
+    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
 ]
@@ -94,6 +94,8 @@ def lib():
         "uivr_get_launch_count": ([vp, C.POINTER(C.c_uint64)], C.c_int),
         "uivr_set_variant": ([vp, C.c_int], C.c_int),
         "uivr_check_watchdog": ([vp, C.POINTER(C.c_uint32), vp], C.c_int),
+        "uivr_adam_step": ([vp, fp, fp, fp, fp, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, i32,
+                            C.c_float, C.c_float, vp], C.c_int),
         "uivr_test_neg_log1m": ([vp, fp, C.c_int, fp, vp], C.c_int),
         "uivr_test_sincos2pi": ([vp, fp, C.c_int, fp, fp, vp], C.c_int),
         "uivr_test_sampler": ([vp, u32, u32, C.c_int, C.c_int, fp, vp], C.c_int),
@@ -207,6 +209,11 @@ class Context:
                                                       seed_grad & 0xFFFFFFFF, int(spp_grad),
                                                       self._shard(shard), dsigma_ptr, dalbedo_ptr, stream),
                     "uivr_render_backward_host")
+
+    def adam_step(self, param_ptr, grad_ptr, m_ptr, v_ptr, n, lr, beta1, beta2, eps, t, lo, hi, stream=0):
+        self._check(self._L.uivr_adam_step(self._h, param_ptr, grad_ptr, m_ptr, v_ptr, int(n), float(lr), float(beta1),
+                                           float(beta2), float(eps), int(t), float(lo), float(hi), stream),
+                    "uivr_adam_step")
 
     # -- instrumentation --
     def reset_counters(self, stream: int = 0):

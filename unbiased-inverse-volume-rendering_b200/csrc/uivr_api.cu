@@ -2,6 +2,7 @@
 // configuration, derived-layout management.  No torch types, no exceptions across the ABI.
 #include "../../include/uivr.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -505,6 +506,23 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
     UIVR_CUDA(ctx, cudaMemcpyAsync(h_dsigma_t, ctx->st_dsigma, ctx->st_vox * sizeof(float), cudaMemcpyDeviceToHost, st));
     UIVR_CUDA(ctx, cudaMemcpyAsync(h_dalbedo, ctx->st_dalbedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     UIVR_CUDA(ctx, cudaStreamSynchronize(st));
+    return UIVR_OK;
+}
+
+int uivr_adam_step(uivr_ctx* ctx, float* d_param, const float* d_grad, float* d_m, float* d_v, uint64_t n, float lr,
+                   float beta1, float beta2, float eps, int32_t t, float lo, float hi, void* stream) {
+    if (!ctx || !d_param || !d_grad || !d_m || !d_v) return UIVR_ERR_INVALID;
+    if (t < 1) return fail(ctx, UIVR_ERR_INVALID, "Adam step counter t starts at 1");
+    if (!(lo <= hi)) return fail(ctx, UIVR_ERR_INVALID, "clip range must satisfy lo <= hi");
+    if ((((uintptr_t) d_param | (uintptr_t) d_grad | (uintptr_t) d_m | (uintptr_t) d_v) & 15u) != 0)
+        return fail(ctx, UIVR_ERR_INVALID, "Adam tensors must be 16-byte aligned");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double b1t = pow((double) beta1, (double) t), b2t = pow((double) beta2, (double) t);
+    const float step = (float) ((double) lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    if (n) k_adam_step<<<ctx->num_sms * 8, kBlock, 0, (cudaStream_t) stream>>>(d_param, d_grad, d_m, d_v, (size_t) n, step, beta1,
+                                                                             beta2, eps, lo, hi);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
     return UIVR_OK;
 }
 

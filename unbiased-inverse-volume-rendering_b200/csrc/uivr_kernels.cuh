@@ -80,6 +80,42 @@ __global__ void __launch_bounds__(kBlock) k_scale(float* __restrict__ x, size_t 
 }
 
 // ---------------------------------------------------------------------------------------
+// K6: optimiser step.  mi.ad.Adam.step() (optimize.py:352) fused with
+// enforce_valid_params (optimize.py:169-179): one streaming pass, 16 B read + 12 B written per
+// element (param, grad, m, v -> param, m, v); HBM-bound.
+// ---------------------------------------------------------------------------------------
+UIVR_DEV void adam_element(float& p, float g, float& m, float& v, float step, float beta1, float omb1, float beta2,
+                           float omb2, float eps, float lo, float hi) {
+    m = fmaf(beta1, m, omb1 * g);
+    v = fmaf(beta2, v, (omb2 * g) * g);
+    float q = p - (step * m) / (sqrtf(v) + eps);
+    q = q < lo ? lo : q;
+    p = q > hi ? hi : q;
+}
+
+__global__ void __launch_bounds__(kBlock) k_adam_step(float* __restrict__ param, const float* __restrict__ grad,
+                                                      float* __restrict__ m, float* __restrict__ v, size_t n, float step,
+                                                      float beta1, float beta2, float eps, float lo, float hi) {
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    const size_t n4 = n / 4, tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t) gridDim.x * blockDim.x;
+    float4* p4 = reinterpret_cast<float4*>(param);
+    const float4* g4 = reinterpret_cast<const float4*>(grad);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (size_t i = tid; i < n4; i += nth) {
+        float4 p = p4[i], mm = m4[i], vv = v4[i];
+        const float4 g = __ldg(g4 + i);
+        adam_element(p.x, g.x, mm.x, vv.x, step, beta1, omb1, beta2, omb2, eps, lo, hi);
+        adam_element(p.y, g.y, mm.y, vv.y, step, beta1, omb1, beta2, omb2, eps, lo, hi);
+        adam_element(p.z, g.z, mm.z, vv.z, step, beta1, omb1, beta2, omb2, eps, lo, hi);
+        adam_element(p.w, g.w, mm.w, vv.w, step, beta1, omb1, beta2, omb2, eps, lo, hi);
+        p4[i] = p; m4[i] = mm; v4[i] = vv;
+    }
+    for (size_t i = 4 * n4 + tid; i < n; i += nth)
+        adam_element(param[i], grad[i], m[i], v[i], step, beta1, omb1, beta2, omb2, eps, lo, hi);
+}
+
+// ---------------------------------------------------------------------------------------
 // variant 1: one sample per lane, warps pull 32-sample chunks from a global counter
 // ---------------------------------------------------------------------------------------
 UIVR_DEV bool next_chunk(const Params& P, uint64_t total, uint32_t& item) {
