@@ -51,7 +51,7 @@ def workload_config(n_gpus: int, spp: int, extra=None):
         "integrator": "volpathsimple-drt (nee, drt, subsampling, mis), max_depth 64, majorant factor 8",
         "samples_per_step": FILM_W * FILM_H * spp,
         "parallelism": "single GPU" if n_gpus == 1 else
-                       f"pixel-sharded x{n_gpus} (interleaved 64-px blocks), spp={SPP}*{n_gpus}, NCCL grad all-reduce in step",
+                       f"pixel-sharded x{n_gpus} (pixels interleaved across ranks), spp={SPP}*{n_gpus}, NCCL grad all-reduce in step",
         "l2_policy": "inputs larger than L2 (sigma_t octets 537 MB + albedo 192 MB + gradients 256 MB vs 126 MB L2); "
                      "gradient buffers re-zeroed every step; seeds change every step",
     }

@@ -22,11 +22,13 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-# Interleaving granularity (pixels).  Path cost varies strongly across the image (rays that
-# miss the medium are ~free), so contiguous row blocks would be badly balanced; small
-# interleaved blocks keep every rank's share statistically identical while neighbouring pixels
-# (which touch the same voxels) stay on one GPU.
-DEFAULT_BLOCK = 64
+# Interleaving granularity (pixels).  Path cost varies strongly across the image (rays that miss
+# the medium are ~free), so contiguous row blocks are badly balanced, and a block size that divides
+# the row length hands whole COLUMN strips to one rank (64-pixel blocks of a 512-wide film on 8
+# ranks: rank 0 renders only the empty left border).  Pure pixel interleaving (block 1) gives every
+# rank the same statistical mix and -- measured on config 3, scripts/shard_bench.py -- the same
+# kernel times as the unsharded render (block 64: +50 % forward, +13 % backward at 4 ranks).
+DEFAULT_BLOCK = 1
 
 
 def pixel_shard(rank: int, world_size: int, block: int = DEFAULT_BLOCK) -> Optional[Tuple[int, int, int]]:
