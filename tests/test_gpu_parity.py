@@ -495,3 +495,40 @@ def test_optimization_step_multiview(uivr, dev):
     s, a = params["m.sigma_t.data"], params["m.albedo.data"]
     assert float(s.min()) >= 0.0 and float(s.max()) <= 250.0 and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
     assert opt.t == 12
+
+
+# ---------------------------------------------------------------------------------------
+# ragged shapes: anisotropic grid resolution, non-square film, supergrid factor that does
+# not divide the resolution, anisotropic medium box, odd spp
+# ---------------------------------------------------------------------------------------
+
+def _ragged_case(uivr):
+    rng = np.random.default_rng(11)
+    x, y, z = 20, 28, 37
+    az, ay, ax = [(np.arange(m) + 0.5) / m - 0.5 for m in (z, y, x)]
+    r2 = az[:, None, None] ** 2 + ay[None, :, None] ** 2 + ax[None, None, :] ** 2
+    sig = (np.clip(1.0 - r2 / 0.2, 0.0, 1.0) * (0.3 + 0.7 * rng.random((z, y, x)))).astype(np.float32)
+    sig[sig < 0.08] = 0.0
+    alb = (0.2 + 0.75 * rng.random((z, y, x, 3))).astype(np.float32)
+    vol = uivr.VolumeScene(res=(x, y, z), sensor=uivr.Sensor(target=(0.4, 0.5, 0.6), width=44, height=26),
+                           bbox_min=(-0.5, -0.4, -0.3), bbox_extent=(2.0, 1.6, 1.8), scale=7.0,
+                           majorant_resolution_factor=8)
+    return vol, sig[..., None].copy(), alb
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ragged_shapes(uivr, oracle, dev, variant):
+    vol, sig, alb = _ragged_case(uivr)
+    props = dict(max_depth=24)
+    spp = 7
+    img_o, smp_fo, cnt_fo = oracle.render_forward(vol.as_dict(), props, sig, alb, 321, spp, want_samples=True)
+    img_g, smp_fg, cnt_fg = _run_forward(uivr, vol, props, sig, alb, 321, spp, dev, variant)
+    assert np.array_equal(smp_fg.view(np.uint32), smp_fo.view(np.uint32))
+    assert cnt_fg == cnt_fo
+    gimg = loss_grad(img_o)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 654, spp, want_samples=True)
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, 654, spp, dev, variant)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL

@@ -1,24 +1,28 @@
-// uivr_pool.cuh -- variant 2: persistent SLOT-POOL megakernel (sm_100a).
+// uivr_pool.cuh -- persistent SLOT-POOL megakernels (sm_100a): variants 2 and 3 (default).
 //
 // Why: in the lane-refill megakernel (uivr_mega.cuh) every lane keeps its sample in registers,
-// so a warp can only batch the <= 32 samples it owns; ncu shows the transition handlers
+// so a warp can only batch the <= 32 samples it owns; ncu showed the transition handlers
 // (vertex / NEE end / path end / fetch) running with ~4 of 32 lanes active and 37 % of the
-// stall samples waiting for instruction fetch (profiles/r01_*).  Here ONE CTA per SM owns a
-// pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA, field-major),
-// and every state of the per-sample state machine has a CTA-wide queue of slot ids:
+// stall samples waiting for instruction fetch (profiles/r01_history.md).  Here ONE CTA per SM
+// owns a pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA,
+// field-major), and every state of the per-sample state machine has a CTA-wide queue of slot ids:
 //
 //      Q_FREE -> [fetch] -> Q_WALK -> [walk] -> Q_VERTEX(_ADJ) -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK ...
 //                                            -> Q_NEE_END / Q_PATH_END -> ... -> Q_FREE
 //
-// Any warp can serve any queue: it pops up to 32 slot ids (normally a FULL batch), loads only
-// the fields that handler needs from the pool, and pushes the slots on to their next queue --
-// compaction of live rays across all 16 warps of the CTA instead of within one warp.  The
-// free-flight walk (the hot loop: branch-free supergrid DDA + batched sigma_t taps) keeps ITS
-// state in registers: every lane of every warp is a walker that is refilled from Q_WALK as soon
-// as kWalkQuantum lanes of the warp have finished.
+// Warps are specialised.  HANDLER warps serve the transition queues: a handler warp pops a FULL
+// batch of 32 slot ids from the fullest queue, loads only the fields that handler needs from the
+// pool, and routes the slots on to their next queue -- compaction of live rays across the whole
+// CTA instead of within one warp.  WALKER warps only run the free-flight walk (the hot loop: a
+// branch-free supergrid DDA with batched sigma_t taps), whose state lives in registers; a walker
+// warp is refilled from Q_WALK whenever kWalkQuantum of its lanes have finished.  The two roles
+// run separate loops, so the walk loop is not charged for the handlers' registers or code.
 //
-// Per-sample arithmetic, RNG draw order and handler logic are exactly those of uivr_mega.cuh /
-// uivr_path.cuh (= volpathsimple.py), so results stay bit-identical per sample.
+// KIND selects what is compiled in: the forward / primal kernel, the combined backward kernel
+// (variant 2), or the two halves of the split backward pipeline (variant 3, see KIND_* below).
+//
+// Per-sample arithmetic, RNG draw order and handler logic are exactly those of uivr_path.cuh
+// (= volpathsimple.py), so results stay bit-identical per sample (tests/test_gpu_parity.py).
 #pragma once
 
 #include "uivr_kernels.cuh"
