@@ -68,6 +68,21 @@ typedef struct {
     int32_t use_drt_mis;
 } uivr_integrator_props;
 
+/* Ray-batch rendering: render_batch(batch_size, scene, sensors, film_size, ..., seed, seed_grad, spp,
+ * spp_grad) of python/batched.py:88-131 (the reference's production mode, python/optimize.py:334).
+ * The wavefront is a batch of B (sensor, pixel) pairs drawn uniformly -- element b: stream
+ * (tea32(seed, 5), b): sensor = uint(n_sensors u), pixel = uint((W, H) (u, u)) (batched.py:409-421) --
+ * with spp samples each; sub-pixel offsets come from stream (tea32(seed, 22), k) in the primal and
+ * (tea32(seed, 39), k) in the adjoint, k = b spp + j (batched.py:409-413, :437-439); the film is
+ * (B x 1), box filter: image / grad_image are [B, 3].  All sensors share the film size. */
+typedef struct {
+    int32_t n_sensors;
+    const float* sensors;   /* HOST, n_sensors x 16 floats: origin[3] left[3] up[3] dir[3] tan_x tan_y near_clip 0 */
+    int32_t film_w, film_h;
+    int32_t batch_size;     /* B */
+    uint32_t seed;          /* the `seed` of render_batch: selects the pixels; uivr_render_forward must get the same */
+} uivr_batch_desc;
+
 /* Pixel p is rendered by this call iff (p / block) % count == rank.  count<=1: all pixels.
  * RNG streams are keyed by the GLOBAL sample index, so results do not depend on the split. */
 typedef struct {
@@ -96,6 +111,11 @@ int         uivr_version(void);
 /* ---- configuration (host side, cheap) ---- */
 int uivr_set_scene(uivr_ctx* ctx, const uivr_scene_desc* scene);              /* mi.load_dict(scene) */
 int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props);   /* IntegratorConfig.create, opt_config.py:97-108 */
+
+/* Enter (batch != NULL) or leave (NULL) ray-batch mode.  In batch mode uivr_render_forward /
+ * uivr_render_backward render the batch: d_image / d_grad_image are [B, 3]; the sensor and film of
+ * uivr_set_scene are ignored; shards split the batch elements.  Needs kernel variant >= 2. */
+int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch);
 
 /* params.update(): rebuild the device-side lookup structures derived from sigma_t -- the
  * corner-octet tap layout and the majorant supergrid (upstream does the latter on

@@ -233,3 +233,73 @@ def adam_step(param, grad, m, v, lr, beta1, beta2, eps, t, lo, hi):
     lib().uivr_oracle_adam_step(_ptr(param, C.c_float), _ptr(grad, C.c_float), _ptr(m, C.c_float), _ptr(v, C.c_float),
                                 C.c_uint64(n), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                 C.c_int32(t), C.c_float(lo), C.c_float(hi))
+
+
+# ---- ray-batch rendering (python/batched.py) ----
+
+class _Batch(C.Structure):
+    _fields_ = [("n_sensors", C.c_int32), ("sensors", C.POINTER(C.c_float)), ("film_w", C.c_int32),
+                ("film_h", C.c_int32), ("seed_pixels", C.c_uint32), ("seed_offsets", C.c_uint32)]
+
+
+def _make_batch(sensors16, film_size, seed_pixels, seed_offsets):
+    a = np.ascontiguousarray(sensors16, dtype=np.float32).reshape(-1, 16)
+    b = _Batch()
+    b.n_sensors = a.shape[0]
+    b.sensors = a.ctypes.data_as(C.POINTER(C.c_float))
+    b.film_w, b.film_h = int(film_size[0]), int(film_size[1])
+    b.seed_pixels, b.seed_offsets = seed_pixels & 0xFFFFFFFF, seed_offsets & 0xFFFFFFFF
+    return b, a  # keep `a` alive
+
+
+def batch_elements(sensors16, film_size, seed: int, batch_size: int) -> np.ndarray:
+    """[B, 3] (sensor, px, py) per batched.py:397-423 for render_batch(seed=seed)."""
+    b, keep = _make_batch(sensors16, film_size, tea(seed, 5)[0], 0)
+    out = np.zeros((batch_size, 3), dtype=np.uint32)
+    e = (C.c_uint32 * 3)()
+    for i in range(batch_size):
+        lib().uivr_oracle_batch_element(C.byref(b), C.c_uint32(i), e)
+        out[i] = (e[0], e[1], e[2])
+    return out
+
+
+def render_batch_forward(desc, props, sensors16, film_size, batch_size, sigma_t, albedo, seed, spp,
+                         nthreads: Optional[int] = None, want_samples: bool = False):
+    """batched.py render_batch primal: image [B, 3]; desc supplies the medium / emitter only."""
+    d = dict(desc)
+    d["width"], d["height"] = int(batch_size), 1
+    sc = make_scene(d, props)
+    sigma_t, albedo = _check_grids(desc, sigma_t, albedo)
+    b, keep = _make_batch(sensors16, film_size, tea(seed, 5)[0], tea(seed, 22)[0])
+    image = np.zeros((batch_size, 3), dtype=np.float32)
+    samples = np.zeros((batch_size * spp, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib().uivr_oracle_render_batch_forward(C.byref(sc), C.byref(b), _ptr(sigma_t, C.c_float), _ptr(albedo, C.c_float),
+                                                seed & 0xFFFFFFFF, spp, nthreads or os.cpu_count() or 1,
+                                                _ptr(image, C.c_float), _ptr(samples, C.c_float), _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_render_batch_forward failed ({rc})")
+    return image, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def render_batch_backward(desc, props, sensors16, film_size, batch_size, sigma_t, albedo, grad_image, seed, seed_grad,
+                          spp_grad, nthreads: Optional[int] = None, want_samples: bool = False):
+    """batched.py render_batch adjoint: `seed` selects the pixels, `seed_grad` the paths."""
+    d = dict(desc)
+    d["width"], d["height"] = int(batch_size), 1
+    sc = make_scene(d, props)
+    sigma_t, albedo = _check_grids(desc, sigma_t, albedo)
+    x, y, z = desc["res"]
+    b, keep = _make_batch(sensors16, film_size, tea(seed, 5)[0], tea(seed, 39)[0])
+    grad_image = _f32(grad_image).reshape(batch_size, 3)
+    dsig = np.zeros((z, y, x, 1), dtype=np.float64)
+    dalb = np.zeros((z, y, x, 3), dtype=np.float64)
+    samples = np.zeros((batch_size * spp_grad, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib().uivr_oracle_render_batch_backward(C.byref(sc), C.byref(b), _ptr(sigma_t, C.c_float), _ptr(albedo, C.c_float),
+                                                 _ptr(grad_image, C.c_float), seed_grad & 0xFFFFFFFF, spp_grad,
+                                                 nthreads or os.cpu_count() or 1, _ptr(dsig, C.c_double),
+                                                 _ptr(dalb, C.c_double), _ptr(samples, C.c_float), _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_render_batch_backward failed ({rc})")
+    return dsig, dalb, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))

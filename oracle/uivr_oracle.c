@@ -173,6 +173,7 @@ static inline void uniform_sphere(float xi1, float xi2, float w[3]) {
 
 typedef struct {
     const uivr_oracle_scene* sc;
+    const uivr_oracle_batch* batch; /* ray-batch mode (batched.py), else NULL */
     const float* sigma_t;  /* (Z,Y,X)   */
     const float* albedo;   /* (Z,Y,X,3) */
     int32_t mres[3];
@@ -740,21 +741,59 @@ static void drt_backprop(const ctx_t* C, counters_t* K, const seg_t* s, int dept
 /* ------------------------------------------------------------------------------------ */
 
 /* returns: 0 = missed the box (escaped), 1 = entered the medium, 2 = dead (corner case) */
+/* perspective sensor frame: origin[3] left[3] up[3] dir[3] tan_x tan_y near_clip */
+static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v, seg_t* s);
+
 static int camera_segment(const ctx_t* C, uint32_t pix, float jx, float jy, seg_t* s) {
     const uivr_oracle_scene* sc = C->sc;
     uint32_t px = pix % (uint32_t) sc->width, py = pix / (uint32_t) sc->width;
     float u = ((float) px + jx) * (1.0f / (float) sc->width);
     float v = ((float) py + jy) * (1.0f / (float) sc->height);
-    float cx = sc->tan_x * FMA(-2.0f, u, 1.0f);
-    float cy = sc->tan_y * FMA(-2.0f, v, 1.0f);
+    float F[15];
+    for (int a = 0; a < 3; ++a) {
+        F[a] = sc->cam_origin[a]; F[3 + a] = sc->cam_left[a]; F[6 + a] = sc->cam_up[a]; F[9 + a] = sc->cam_dir[a];
+    }
+    F[12] = sc->tan_x; F[13] = sc->tan_y; F[14] = sc->near_clip;
+    return camera_segment_frame(C, F, u, v, s);
+}
+
+/* sample_batch_pixels (batched.py:397-423): sensor + pixel of batch element b */
+void uivr_oracle_batch_element(const uivr_oracle_batch* B, uint32_t b, uint32_t out[3]) {
+    rng_t q;
+    sampler_seed(&q, B->seed_pixels, b);
+    float u0 = rng_f(&q), u1 = rng_f(&q), u2 = rng_f(&q);
+    uint32_t si = (uint32_t) ((float) B->n_sensors * u0);
+    uint32_t px = (uint32_t) ((float) B->film_w * u1), py = (uint32_t) ((float) B->film_h * u2);
+    out[0] = si < (uint32_t) B->n_sensors ? si : (uint32_t) B->n_sensors - 1u;
+    out[1] = px < (uint32_t) B->film_w ? px : (uint32_t) B->film_w - 1u;
+    out[2] = py < (uint32_t) B->film_h ? py : (uint32_t) B->film_h - 1u;
+}
+
+/* sample_batch_rays (batched.py:426-467): ray of wavefront entry idx = b * spp + j */
+static int batch_segment(const ctx_t* C, uint32_t idx, uint32_t spp, seg_t* s) {
+    const uivr_oracle_batch* B = C->batch;
+    uint32_t e[3];
+    uivr_oracle_batch_element(B, idx / spp, e);
+    rng_t o;
+    sampler_seed(&o, B->seed_offsets, idx);
+    float jx = rng_f(&o), jy = rng_f(&o);
+    float u = ((float) e[1] + jx) * (1.0f / (float) B->film_w);
+    float v = ((float) e[2] + jy) * (1.0f / (float) B->film_h);
+    return camera_segment_frame(C, B->sensors + 16 * (size_t) e[0], u, v, s);
+}
+
+static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v, seg_t* s) {
+    const uivr_oracle_scene* sc = C->sc;
+    float cx = F[12] * FMA(-2.0f, u, 1.0f);
+    float cy = F[13] * FMA(-2.0f, v, 1.0f);
     float d[3], o[3];
-    for (int a = 0; a < 3; ++a) d[a] = FMA(cx, sc->cam_left[a], FMA(cy, sc->cam_up[a], sc->cam_dir[a]));
+    for (int a = 0; a < 3; ++a) d[a] = FMA(cx, F[3 + a], FMA(cy, F[6 + a], F[9 + a]));
     float len = sqrtf(FMA(d[0], d[0], FMA(d[1], d[1], d[2] * d[2])));
     float inv_len = 1.0f / len;
-    float near_t = sc->near_clip * len;
+    float near_t = F[14] * len;
     for (int a = 0; a < 3; ++a) {
         d[a] *= inv_len;
-        o[a] = FMA(near_t, d[a], sc->cam_origin[a]);
+        o[a] = FMA(near_t, d[a], F[a]);
     }
     /* to local space */
     const float* M = sc->to_local;
@@ -795,9 +834,14 @@ static void sample_from_camera(const ctx_t* C, counters_t* K, int adjoint, uint3
     rng_t rng, alt;
     sampler_seed(&rng, seed, idx);
     if (adjoint) sampler_seed(&alt, alt_seed, idx);
-    float jx = rng_f(&rng), jy = rng_f(&rng);
     path_state_t ps;
-    int status = camera_segment(C, idx / spp, jx, jy, &ps.seg);
+    int status;
+    if (C->batch) {
+        status = batch_segment(C, idx, spp, &ps.seg);  /* the path sampler draws no jitter (batched.py:390) */
+    } else {
+        float jx = rng_f(&rng), jy = rng_f(&rng);
+        status = camera_segment(C, idx / spp, jx, jy, &ps.seg);
+    }
     rng_f(&rng); /* :71 colour-channel placeholder draw */
     ps.depth = 0;
     ps.active = (status == 1);
@@ -951,6 +995,52 @@ int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sig
     if (sample_L_out)
         memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * scene->height * (size_t) spp_grad);
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, shard, nthreads, grad_image, NULL, sample_L_out, counters);
+    free(C.majorant);
+    return rc;
+}
+
+/* ray-batch entry points: the same drivers with C.batch set (film = B x 1) */
+int uivr_oracle_render_batch_forward(const uivr_oracle_scene* scene, const uivr_oracle_batch* batch,
+                                     const float* sigma_t, const float* albedo, uint32_t seed,
+                                     int32_t spp, int nthreads, float* image_out,
+                                     float* sample_L_out, uint64_t* counters) {
+    if (!scene || !batch || !batch->sensors || batch->n_sensors < 1 || scene->height != 1 || !sigma_t || !albedo ||
+        !image_out || spp < 1)
+        return -1;
+    ctx_t C;
+    if (setup_ctx(&C, scene, sigma_t, albedo)) return -1;
+    C.batch = batch;
+    size_t n = (size_t) scene->width * 3;
+    double* acc = (double*) calloc(n, sizeof(double));
+    if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * n * (size_t) spp);
+    int rc = acc ? run(&C, 0, seed, (uint32_t) spp, NULL, nthreads, NULL, acc, sample_L_out, counters) : -1;
+    if (!rc) {
+        float inv_spp = 1.0f / (float) spp;
+        for (size_t i = 0; i < n; ++i) image_out[i] = (float) acc[i] * inv_spp;
+    }
+    free(acc);
+    free(C.majorant);
+    return rc;
+}
+
+int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr_oracle_batch* batch,
+                                      const float* sigma_t, const float* albedo,
+                                      const float* grad_image, uint32_t seed_grad, int32_t spp_grad,
+                                      int nthreads, double* dsigma_out, double* dalbedo_out,
+                                      float* sample_L_out, uint64_t* counters) {
+    if (!scene || !batch || !batch->sensors || batch->n_sensors < 1 || scene->height != 1 || !sigma_t || !albedo ||
+        !grad_image || !dsigma_out || !dalbedo_out || spp_grad < 1)
+        return -1;
+    ctx_t C;
+    if (setup_ctx(&C, scene, sigma_t, albedo)) return -1;
+    C.batch = batch;
+    size_t nvox = (size_t) scene->res[0] * scene->res[1] * scene->res[2];
+    memset(dsigma_out, 0, sizeof(double) * nvox);
+    memset(dalbedo_out, 0, sizeof(double) * nvox * 3);
+    C.dsigma = dsigma_out;
+    C.dalbedo = dalbedo_out;
+    if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * (size_t) spp_grad);
+    int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, NULL, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
     return rc;
 }

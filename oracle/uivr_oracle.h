@@ -49,6 +49,22 @@ typedef struct {
     int32_t use_drt_mis;
 } uivr_oracle_scene;
 
+/* Ray-batch rendering (python/batched.py:88-131, "next" row SURVEY 8f rank 2): instead of the
+ * pixels of one sensor, the wavefront is a batch of B (sensor, pixel) pairs drawn uniformly, spp
+ * samples each; the film is (B x 1) with a box filter.  Set scene->width = B, scene->height = 1.
+ *   element b:  stream (seed_pixels, b):  sensor = uint(n_sensors * u), pixel = uint((W,H) * (u,u))
+ *                                                                      (batched.py:416-421)
+ *   sample  k = b*spp + j:  sub-pixel offset = two draws of stream (seed_offsets, k)  (:437-439);
+ *   the path sampler (seed, k) draws NO jitter (prepare_batch seeds it for integrator.sample only).
+ * seed_pixels = tea32(seed, 5); seed_offsets = tea32(seed, 22) for the primal, tea32(seed, 39) for
+ * the adjoint (batched.py:409-413: sub_seed_i = tea32(seed, 17 i + 5)). */
+typedef struct {
+    int32_t n_sensors;
+    const float* sensors;    /* n_sensors x 16: origin[3] left[3] up[3] dir[3] tan_x tan_y near_clip pad */
+    int32_t film_w, film_h;  /* film size shared by all sensors (batched.py:428) */
+    uint32_t seed_pixels, seed_offsets;
+} uivr_oracle_batch;
+
 /* Pixel sharding: pixel p belongs to this call iff (p / shard_block) % shard_count == shard_rank. */
 typedef struct {
     int32_t shard_rank, shard_count, shard_block;
@@ -99,6 +115,19 @@ int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sig
                                 const uivr_oracle_shard* shard, int nthreads,
                                 double* dsigma_out, double* dalbedo_out,
                                 float* sample_L_out, uint64_t* counters);
+
+/* same as the two calls above with the wavefront drawn per `batch` (image: B x 1 x 3) */
+int uivr_oracle_render_batch_forward(const uivr_oracle_scene* scene, const uivr_oracle_batch* batch,
+                                     const float* sigma_t, const float* albedo, uint32_t seed,
+                                     int32_t spp, int nthreads, float* image_out,
+                                     float* sample_L_out, uint64_t* counters);
+int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr_oracle_batch* batch,
+                                      const float* sigma_t, const float* albedo,
+                                      const float* grad_image, uint32_t seed_grad, int32_t spp_grad,
+                                      int nthreads, double* dsigma_out, double* dalbedo_out,
+                                      float* sample_L_out, uint64_t* counters);
+/* the (sensor, pixel x, pixel y) triple of batch element b (host-side check of the index sampler) */
+void uivr_oracle_batch_element(const uivr_oracle_batch* batch, uint32_t b, uint32_t out[3]);
 
 /* ---- optimiser step ("next" row) ----
  * mi.ad.Adam.step() (python/opt_config.py:46-48, python/optimize.py:352; update rule SURVEY App.

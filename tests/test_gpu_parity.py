@@ -532,3 +532,87 @@ def test_ragged_shapes(uivr, oracle, dev, variant):
     assert cnt_g == cnt_o
     assert rel_linf(ds_g, ds_o) < GRAD_TOL
     assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------
+# ray-batch rendering (python/batched.py)
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_render_batch_matches_oracle(uivr, oracle, dev, variant):
+    """render_batch: B (sensor, pixel) pairs x spp through the C-ABI in batch mode vs the oracle's
+    restatement of batched.py: per-sample radiance bit-exact (primal at `seed`, primal replay at
+    `seed_grad` on the decorrelated adjoint rays), counters equal, gradients < 1e-3."""
+    n, B, spp, spp_grad = 24, 700, 6, 3
+    sig, alb = hetero_grids(n)
+    vol = uivr.benchmark_scene(n, 32, 32, scale=8.0, majorant_resolution_factor=4)
+    sensors = uivr.circle_sensors(6, 40, 24)
+    table = uivr.sensor_table(sensors)
+    props = dict(max_depth=32)
+    seed = 2024
+    seed_grad = uivr.tea32(seed, 1)
+    img_o, smp_fo, cnt_fo = oracle.render_batch_forward(vol.as_dict(), props, table, (40, 24), B, sig, alb, seed, spp,
+                                                        want_samples=True)
+    gimg = (2.0 * (img_o.astype(np.float64) - 0.5) / img_o.size).astype(np.float32)
+    ds_o, da_o, smp_bo, cnt_bo = oracle.render_batch_backward(vol.as_dict(), props, table, (40, 24), B, sig, alb, gimg,
+                                                              seed, seed_grad, spp_grad, want_samples=True)
+    scene = uivr.Scene(vol, device=0)
+    scene.ctx.set_variant(variant)
+    scene.ctx.set_counting(True)
+    integ = uivr.VolpathSimpleIntegrator(props)
+    params = {"m.sigma_t.data": _gpu(sig, dev), "m.albedo.data": _gpu(alb, dev)}
+    from uivr_b200 import batched
+    batch = (table, (40, 24), B, seed)
+    smp_f = torch.zeros((B * spp, 3), device=dev)
+    scene.ctx.reset_counters()
+    img_g = batched._launch(scene, integ, params, batch, seed, spp, None, smp_f)
+    torch.cuda.synchronize()
+    cnt_fg = scene.ctx.get_counters()
+    assert np.array_equal(smp_f.cpu().numpy().view(np.uint32), smp_fo.view(np.uint32))
+    assert cnt_fg == cnt_fo
+    assert np.max(np.abs(img_g.cpu().numpy() - img_o)) < IMAGE_TOL
+    smp_b = torch.zeros((B * spp_grad, 3), device=dev)
+    scene.ctx.reset_counters()
+    ds_g, da_g = batched._launch(scene, integ, params, batch, seed_grad, spp_grad, _gpu(gimg, dev), smp_b)
+    torch.cuda.synchronize()
+    cnt_bg = scene.ctx.get_counters()
+    assert np.array_equal(smp_b.cpu().numpy().view(np.uint32), smp_bo.view(np.uint32))
+    assert cnt_bg == cnt_bo
+    assert rel_linf(ds_g.cpu().numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(da_g.cpu().numpy(), da_o) < GRAD_TOL
+    # the context is back in sensor-centric mode afterwards
+    img = integ.render(scene, params, seed=5, spp=2)
+    assert tuple(img.shape) == (32, 32, 3)
+
+
+def test_render_batch_autograd_and_rules(uivr, oracle, dev):
+    """render_batch(...) as optimize.py:334-341 uses it: differentiable image [B, 3] + the batch
+    indices for gather_ref_values; seed rules of batched.py:116-124."""
+    n, B, spp = 16, 256, 8
+    sig, alb = hetero_grids(n, seed=9)
+    vol = uivr.benchmark_scene(n, 16, 16, scale=6.0, majorant_resolution_factor=4)
+    sensors = uivr.circle_sensors(3, 24, 24)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.get_int_config("volpathsimple-drt").create(max_depth=16)
+    params = {"m.sigma_t.data": _gpu(sig, dev).requires_grad_(True), "m.albedo.data": _gpu(alb, dev).requires_grad_(True)}
+    image, si, px = uivr.render_batch(B, scene, sensors, params, integ, seed=77, spp=spp, spp_grad=4)
+    assert tuple(image.shape) == (B, 3) and si.shape == (B,) and px.shape == (B, 2)
+    refs = torch.rand((3, 24, 24, 3), device=dev)
+    ref = uivr.gather_ref_values(refs, si, px)
+    assert torch.equal(ref[10], refs[int(si[10]), int(px[10, 1]), int(px[10, 0])])
+    loss = (image - ref).abs().mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    table = uivr.sensor_table(sensors)
+    img_o, _, _ = oracle.render_batch_forward(vol.as_dict(), integ.props(), table, (24, 24), B, sig, alb, 77, spp)
+    assert np.max(np.abs(image.detach().cpu().numpy() - img_o)) < IMAGE_TOL
+    g = (torch.sign(image.detach() - ref) / image.numel()).cpu().numpy()
+    ds_o, da_o, _, _ = oracle.render_batch_backward(vol.as_dict(), integ.props(), table, (24, 24), B, sig, alb, g, 77,
+                                                    uivr.tea32(77, 1), 4)
+    assert rel_linf(params["m.sigma_t.data"].grad.cpu().numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(params["m.albedo.data"].grad.cpu().numpy(), da_o) < GRAD_TOL
+    with pytest.raises(Exception):
+        uivr.render_batch(B, scene, sensors, params, integ, seed=5, seed_grad=5, spp=spp)
+    scene.ctx.set_variant(0)
+    with pytest.raises(uivr.NativeError):
+        uivr.render_batch(B, scene, sensors, params, integ, seed=5, spp=spp)

@@ -159,3 +159,21 @@ def test_bench_reference_arm_contract():
     assert bench.algorithmic_bytes({"sigma_taps": 1, "albedo_taps": 1, "majorant_reads": 1, "sigma_scatters": 1,
                                     "albedo_scatters": 1}, 2, True) == 32 + 96 + 4 + 64 + 192 + 24
     json.dumps(bench.workload_config(2, 128))
+
+
+def test_batch_index_sampler_matches_oracle(uivr, oracle):
+    """Host restatement of sample_batch_pixels (batched.py:397-423) vs the oracle's per-element
+    sampler: same sensors / pixels, bit for bit, and inside the film."""
+    sensors = uivr.circle_sensors(5, 40, 24)
+    table = uivr.sensor_table(sensors)
+    assert table.shape == (5, 16) and table.dtype == np.float32
+    for seed in (0, 1234, 0xDEADBEEF):
+        si, px = uivr.sample_batch_pixels(300, 5, (40, 24), seed)
+        ref = oracle.batch_elements(table, (40, 24), seed, 300)
+        assert np.array_equal(si, ref[:, 0]) and np.array_equal(px, ref[:, 1:])
+        assert si.max() < 5 and px[:, 0].max() < 40 and px[:, 1].max() < 24
+    # every sensor / film region is hit (uniform sampling)
+    si, px = uivr.sample_batch_pixels(4000, 5, (40, 24), 7)
+    assert set(si.tolist()) == set(range(5)) and px[:, 0].min() == 0 and px[:, 0].max() == 39
+    with pytest.raises(ValueError):
+        uivr.sensor_table([uivr.Sensor(width=8, height=8), uivr.Sensor(width=9, height=8)])

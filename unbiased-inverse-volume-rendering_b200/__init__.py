@@ -5,6 +5,7 @@ from ._native import NativeError, tea32
 from .integrator import (INTEGRATORS, Scene, VolpathSimpleIntegrator, load_dict,
                          register_integrator, render)
 from .opt_config import IntegratorConfig, add_int_config, get_int_config
+from .batched import gather_ref_values, render_batch, sample_batch_pixels, sensor_table
 from .optimize import Adam, l1_loss_grad, learning_rates, optimization_step, param_bounds
 from .scene import (Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_test_grids,
                     cube_test_scene, look_at, synthetic_grids)
@@ -14,5 +15,6 @@ __all__ = [
     "register_integrator", "render", "IntegratorConfig", "add_int_config", "get_int_config",
     "Sensor", "VolumeScene", "benchmark_scene", "circle_sensors", "cube_test_grids",
     "cube_test_scene", "look_at", "synthetic_grids",
+    "gather_ref_values", "render_batch", "sample_batch_pixels", "sensor_table",
     "Adam", "l1_loss_grad", "learning_rates", "optimization_step", "param_bounds",
 ]

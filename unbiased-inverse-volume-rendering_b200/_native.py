@@ -24,7 +24,7 @@ EXPORTS = [
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
-    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step",
+    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
 ]
@@ -48,6 +48,11 @@ class SceneDesc(C.Structure):
 class IntegratorProps(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("hide_emitters", C.c_int32), ("use_nee", C.c_int32),
                 ("use_drt", C.c_int32), ("use_drt_subsampling", C.c_int32), ("use_drt_mis", C.c_int32)]
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [("n_sensors", C.c_int32), ("sensors", C.POINTER(C.c_float)), ("film_w", C.c_int32),
+                ("film_h", C.c_int32), ("batch_size", C.c_int32), ("seed", C.c_uint32)]
 
 
 class Shard(C.Structure):
@@ -82,6 +87,7 @@ def lib():
         "uivr_last_error": ([vp], C.c_char_p),
         "uivr_set_scene": ([vp, C.POINTER(SceneDesc)], C.c_int),
         "uivr_set_integrator": ([vp, C.POINTER(IntegratorProps)], C.c_int),
+        "uivr_set_batch": ([vp, C.POINTER(BatchDesc)], C.c_int),
         "uivr_update_medium": ([vp, fp, vp], C.c_int),
         "uivr_render_forward": ([vp, fp, u32, i32, C.POINTER(Shard), fp, fp, vp], C.c_int),
         "uivr_render_backward": ([vp, fp, fp, u32, i32, C.POINTER(Shard), fp, fp, fp, vp], C.c_int),
@@ -167,6 +173,19 @@ class Context:
         p.use_drt_subsampling = int(bool(props.get("use_drt_subsampling", True)))
         p.use_drt_mis = int(bool(props.get("use_drt_mis", True)))
         self._check(self._L.uivr_set_integrator(self._h, C.byref(p)), "uivr_set_integrator")
+
+    def set_batch(self, sensors16=None, film_w: int = 0, film_h: int = 0, batch_size: int = 0, seed: int = 0):
+        """Enter ray-batch mode (sensors16: float32 array [n, 16]) or leave it (sensors16 = None)."""
+        if sensors16 is None:
+            self._check(self._L.uivr_set_batch(self._h, None), "uivr_set_batch")
+            return
+        import numpy as np
+        a = np.ascontiguousarray(sensors16, dtype=np.float32).reshape(-1, 16)
+        d = BatchDesc()
+        d.n_sensors = a.shape[0]
+        d.sensors = a.ctypes.data_as(C.POINTER(C.c_float))
+        d.film_w, d.film_h, d.batch_size, d.seed = int(film_w), int(film_h), int(batch_size), seed & 0xFFFFFFFF
+        self._check(self._L.uivr_set_batch(self._h, C.byref(d)), "uivr_set_batch")
 
     def set_variant(self, variant: int):
         self._check(self._L.uivr_set_variant(self._h, int(variant)), "uivr_set_variant")

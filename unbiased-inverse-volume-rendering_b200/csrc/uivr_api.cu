@@ -36,6 +36,11 @@ struct uivr_ctx {
     uint32_t* records = nullptr;
     size_t records_cap = 0;
     int variant = 3;
+    // ray-batch mode (uivr_set_batch)
+    bool batch_on = false;
+    uivr_batch_desc batch{};
+    float* d_sensors = nullptr;
+    int d_sensors_cap = 0;
     int counting = 0;
     uint64_t launches = 0;
     // staging for the *_host entry points
@@ -84,7 +89,7 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     const uivr_scene_desc& s = ctx->scene;
     const uivr_integrator_props& ip = ctx->props;
     if (spp < 1) return fail(ctx, UIVR_ERR_INVALID, "spp must be >= 1");
-    const uint64_t npix = (uint64_t) s.width * (uint64_t) s.height;
+    const uint64_t npix = ctx->batch_on ? (uint64_t) ctx->batch.batch_size : (uint64_t) s.width * (uint64_t) s.height;
     if (npix * (uint64_t) spp >= (1ull << 32) - (1ull << 24))
         return fail(ctx, UIVR_ERR_INVALID, "wavefront too large: W*H*spp must be < 2^32 (batched.py:378-388)");
     memset(&P, 0, sizeof(P));
@@ -109,10 +114,19 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.tan_x = s.tan_x;
     P.tan_y = s.tan_y;
     P.near_clip = s.near_clip;
-    P.width = s.width;
-    P.height = s.height;
-    P.inv_w = 1.0f / (float) s.width;
-    P.inv_h = 1.0f / (float) s.height;
+    P.width = ctx->batch_on ? ctx->batch.batch_size : s.width;
+    P.height = ctx->batch_on ? 1 : s.height;
+    P.inv_w = 1.0f / (float) P.width;
+    P.inv_h = 1.0f / (float) P.height;
+    if (ctx->batch_on) {
+        if (!pool_ok(ctx)) return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering needs the slot-pool kernels (variant >= 2)");
+        P.sensors = ctx->d_sensors;
+        P.n_sensors = ctx->batch.n_sensors;
+        P.film_w = ctx->batch.film_w;
+        P.film_h = ctx->batch.film_h;
+        P.seed_pixels = uivr_tea32(ctx->batch.seed, 5);    // batched.py:409-413: sub_seed_i = tea32(seed, 17 i + 5)
+        P.seed_offsets = uivr_tea32(ctx->batch.seed, 22);  // primal offsets; the backward entry switches to i = 2
+    }
     P.max_depth = ip.max_depth;
     P.hide_emitters = ip.hide_emitters;
     P.use_nee = ip.use_nee;
@@ -212,7 +226,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
     for (int i = 0; i < 2; ++i)
@@ -237,6 +251,31 @@ int uivr_set_scene(uivr_ctx* ctx, const uivr_scene_desc* scene) {
     ctx->scene = *scene;
     ctx->have_scene = true;
     if (res_changed) ctx->have_medium = false;  // derived layouts are stale
+    return UIVR_OK;
+}
+
+int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    if (!batch) {
+        ctx->batch_on = false;
+        return UIVR_OK;
+    }
+    if (batch->n_sensors < 1 || !batch->sensors || batch->film_w < 1 || batch->film_h < 1 || batch->batch_size < 1)
+        return fail(ctx, UIVR_ERR_INVALID, "invalid batch descriptor");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (batch->n_sensors > ctx->d_sensors_cap) {
+        cudaFree(ctx->d_sensors);
+        ctx->d_sensors = nullptr;
+        ctx->d_sensors_cap = 0;
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->d_sensors, (size_t) batch->n_sensors * 16 * sizeof(float)));
+        ctx->d_sensors_cap = batch->n_sensors;
+    }
+    // (synchronous copy: a handful of KB, and the host array need not outlive the call)
+    UIVR_CUDA(ctx, cudaMemcpy(ctx->d_sensors, batch->sensors, (size_t) batch->n_sensors * 16 * sizeof(float),
+                              cudaMemcpyHostToDevice));
+    ctx->batch = *batch;
+    ctx->batch.sensors = nullptr;
+    ctx->batch_on = true;
     return UIVR_OK;
 }
 
@@ -354,6 +393,8 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     cudaStream_t st = (cudaStream_t) stream;
     Params P;
     if ((rc = fill_params(ctx, P, shard, seed, spp))) return rc;
+    if (ctx->batch_on && seed != ctx->batch.seed)
+        return fail(ctx, UIVR_ERR_INVALID, "ray-batch mode: the forward seed must be the seed of uivr_set_batch");
     P.albedo = d_albedo;
     P.image = d_image;
     P.sample_L = d_sample_L;
@@ -394,6 +435,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     Params P;
     if ((rc = fill_params(ctx, P, shard, seed_grad, spp_grad))) return rc;
     P.alt_seed = uivr_alt_seed(seed_grad);
+    if (ctx->batch_on) P.seed_offsets = uivr_tea32(ctx->batch.seed, 39);  // decorrelated offsets, same pixels (batched.py:69-75)
     P.albedo = d_albedo;
     P.grad_image = d_grad_image;
     P.dsigma = d_dsigma_t;
@@ -465,6 +507,7 @@ int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float*
                              const uivr_shard* shard, float* h_image, void* stream) {
     if (!ctx || !h_sigma_t || !h_albedo || !h_image) return UIVR_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    if (ctx->batch_on) return fail(ctx, UIVR_ERR_STATE, "the *_host entry points render a sensor, not a ray batch");
     UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t) stream;
     int rc = ensure_staging(ctx);
@@ -485,6 +528,7 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
                               float* h_dalbedo, void* stream) {
     if (!ctx || !h_grad_image || !h_dsigma_t || !h_dalbedo || (!h_sigma_t != !h_albedo)) return UIVR_ERR_INVALID;
     if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    if (ctx->batch_on) return fail(ctx, UIVR_ERR_STATE, "the *_host entry points render a sensor, not a ray batch");
     UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t) stream;
     const size_t old_vox = ctx->st_vox;

@@ -37,6 +37,10 @@ struct Params {
     int   width, height;
     float inv_w, inv_h;
     float radiance[3], half_le[3];
+    // ray-batch mode (python/batched.py): the wavefront is a batch of (sensor, pixel) pairs, film = (B x 1)
+    const float* __restrict__ sensors;  // n_sensors x 16: origin[3] left[3] up[3] dir[3] tan_x tan_y near pad; NULL = off
+    int   n_sensors, film_w, film_h;
+    uint32_t seed_pixels, seed_offsets;
     // integrator
     int max_depth, hide_emitters, use_nee, use_drt, use_drt_subsampling, use_drt_mis;
     // launch
@@ -331,23 +335,33 @@ UIVR_DEV bool make_segment(const Params& P, float px, float py, float pz, float 
     return s.tmax > 0.0f && s.tmax < UIVR_INF;
 }
 
-// perspective sensor + reach_medium.  0 = missed (escaped), 1 = entered, 2 = dead
+// perspective sensor + reach_medium.  0 = missed (escaped), 1 = entered, 2 = dead.
+// F = sensor frame: origin[3] left[3] up[3] dir[3] tan_x tan_y near_clip; (u, v) = film position in [0,1]^2
+UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, float v, Seg& s);
+
 UIVR_DEV int camera_segment(const Params& P, uint32_t pix, float jx, float jy, Seg& s) {
     uint32_t px = pix % (uint32_t) P.width, py = pix / (uint32_t) P.width;
     float u = ((float) px + jx) * P.inv_w;
     float v = ((float) py + jy) * P.inv_h;
-    float cx = P.tan_x * fmaf(-2.0f, u, 1.0f);
-    float cy = P.tan_y * fmaf(-2.0f, v, 1.0f);
-    float d0 = fmaf(cx, P.cam_left[0], fmaf(cy, P.cam_up[0], P.cam_dir[0]));
-    float d1 = fmaf(cx, P.cam_left[1], fmaf(cy, P.cam_up[1], P.cam_dir[1]));
-    float d2 = fmaf(cx, P.cam_left[2], fmaf(cy, P.cam_up[2], P.cam_dir[2]));
+    const float F[15] = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2], P.cam_left[0], P.cam_left[1], P.cam_left[2],
+                         P.cam_up[0], P.cam_up[1], P.cam_up[2], P.cam_dir[0], P.cam_dir[1], P.cam_dir[2],
+                         P.tan_x, P.tan_y, P.near_clip};
+    return camera_segment_frame(P, F, u, v, s);
+}
+
+UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, float v, Seg& s) {
+    float cx = F[12] * fmaf(-2.0f, u, 1.0f);
+    float cy = F[13] * fmaf(-2.0f, v, 1.0f);
+    float d0 = fmaf(cx, F[3], fmaf(cy, F[6], F[9]));
+    float d1 = fmaf(cx, F[4], fmaf(cy, F[7], F[10]));
+    float d2 = fmaf(cx, F[5], fmaf(cy, F[8], F[11]));
     float len = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
     float inv_len = 1.0f / len;
-    float near_t = P.near_clip * len;
+    float near_t = F[14] * len;
     d0 *= inv_len; d1 *= inv_len; d2 *= inv_len;
-    float o0 = fmaf(near_t, d0, P.cam_origin[0]);
-    float o1 = fmaf(near_t, d1, P.cam_origin[1]);
-    float o2 = fmaf(near_t, d2, P.cam_origin[2]);
+    float o0 = fmaf(near_t, d0, F[0]);
+    float o1 = fmaf(near_t, d1, F[1]);
+    float o2 = fmaf(near_t, d2, F[2]);
     const float* M = P.to_local;
     float ol[3], dl[3];
     ol[0] = fmaf(M[0], o0, fmaf(M[1], o1, fmaf(M[2], o2, M[3])));
@@ -377,6 +391,29 @@ UIVR_DEV int camera_segment(const Params& P, uint32_t pix, float jx, float jy, S
     s.dx = dl[0]; s.dy = dl[1]; s.dz = dl[2];
     s.tmax = exit_distance(s);
     return (s.tmax > 0.0f && s.tmax < UIVR_INF) ? 1 : 2;
+}
+
+// sample_batch_pixels + sample_batch_rays (batched.py:397-467): ray of wavefront entry idx = b * spp + j
+UIVR_DEV int batch_segment(const Params& P, uint32_t b, uint32_t idx, Seg& s) {
+    Rng q;
+    q.seed_sampler(P.seed_pixels, b);
+    const float u0 = q.f(), u1 = q.f(), u2 = q.f();
+    uint32_t si = (uint32_t) ((float) P.n_sensors * u0);
+    uint32_t px = (uint32_t) ((float) P.film_w * u1), py = (uint32_t) ((float) P.film_h * u2);
+    si = min(si, (uint32_t) P.n_sensors - 1u);
+    px = min(px, (uint32_t) P.film_w - 1u);
+    py = min(py, (uint32_t) P.film_h - 1u);
+    Rng o;
+    o.seed_sampler(P.seed_offsets, idx);
+    const float jx = o.f(), jy = o.f();
+    const float u = ((float) px + jx) * (1.0f / (float) P.film_w);
+    const float v = ((float) py + jy) * (1.0f / (float) P.film_h);
+    float F[15];
+    const float4* f4 = reinterpret_cast<const float4*>(P.sensors + 16 * (size_t) si);
+    const float4 a = __ldg(f4), bb = __ldg(f4 + 1), c = __ldg(f4 + 2), d = __ldg(f4 + 3);
+    F[0] = a.x; F[1] = a.y; F[2] = a.z; F[3] = a.w; F[4] = bb.x; F[5] = bb.y; F[6] = bb.z; F[7] = bb.w;
+    F[8] = c.x; F[9] = c.y; F[10] = c.z; F[11] = c.w; F[12] = d.x; F[13] = d.y; F[14] = d.z;
+    return camera_segment_frame(P, F, u, v, s);
 }
 
 // --------------------------------------------------------------------------------------

@@ -938,9 +938,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     } else {
                         PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
                     }
-                    const float jx = draw(r, K), jy = draw(r, K);
                     Seg sg;
-                    const int status = camera_segment(P, pix, jx, jy, sg);
+                    int status;
+                    if (P.sensors) {
+                        // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
+                        status = batch_segment(P, pix, idx, sg);
+                    } else {
+                        const float jx = draw(r, K), jy = draw(r, K);
+                        status = camera_segment(P, pix, jx, jy, sg);
+                    }
                     draw(r, K);  // :71
                     const bool active = status == 1;
                     const bool escaped = status == 0;
@@ -980,7 +986,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 }
                             } else if (COUNT) {
                                 // the adjoint pass of a missed ray draws jitter + :71 and nothing else
-                                K.add(C_DRAWS, 3);
+                                K.add(C_DRAWS, P.sensors ? 1 : 3);
                             }
                         }
                         fl = 0u;
