@@ -161,6 +161,11 @@ int uivr_adam_step(uivr_ctx* ctx, float* d_param, const float* d_grad, float* d_
                    uint64_t n, float lr, float beta1, float beta2, float eps, int32_t t,
                    float lo, float hi, void* stream);
 
+/* Multires step: upsample_grid(values, old_res, 2 * old_res) of python/optimize.py:203-252 (first-order
+ * scipy zoom with grid_mode=True, mode='nearest').  d_in (Z,Y,X,C) -> d_out (2Z,2Y,2X,C), both DEVICE. */
+int uivr_upsample2x(uivr_ctx* ctx, const float* d_in, const int32_t res[3], int32_t channels, float* d_out,
+                    void* stream);
+
 /* ---- instrumentation ---- */
 /* Event counters (SURVEY §8d algorithmic bytes).  Counting kernels are separate template
  * instances; enable only for accounting passes, not for timing. */

@@ -494,7 +494,7 @@ def test_optimization_step_multiview(uivr, dev):
     assert np.mean(losses[-3:]) < 0.8 * np.mean(losses[:3]), losses
     s, a = params["m.sigma_t.data"], params["m.albedo.data"]
     assert float(s.min()) >= 0.0 and float(s.max()) <= 250.0 and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
-    assert opt.t == 12
+    assert set(opt.t.values()) == {12}
 
 
 # ---------------------------------------------------------------------------------------
@@ -616,3 +616,52 @@ def test_render_batch_autograd_and_rules(uivr, oracle, dev):
     scene.ctx.set_variant(0)
     with pytest.raises(uivr.NativeError):
         uivr.render_batch(B, scene, sensors, params, integ, seed=5, spp=spp)
+
+
+# ---------------------------------------------------------------------------------------
+# multires upsampling
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(3, 3, 3, 1), (8, 5, 6, 3), (1, 4, 2, 1)])
+def test_upsample_grid_matches_scipy_zoom(uivr, dev, shape):
+    """upsample_grid (optimize.py:203-225) vs the scipy call the reference makes: zoom(order=1,
+    mode='nearest', prefilter=False, grid_mode=True).  Tolerance: float32 rounding of a double result."""
+    from scipy.ndimage import zoom
+    rng = np.random.default_rng(1)
+    a = rng.random(shape).astype(np.float32)
+    new_res = (2 * shape[0], 2 * shape[1], 2 * shape[2], shape[3])
+    ref = zoom(a, [2, 2, 2, 1], order=1, mode="nearest", prefilter=False, grid_mode=True)
+    ctx = uivr._native.Context(0)
+    out = uivr.upsample_grid(ctx, _gpu(a, dev), new_res)
+    assert tuple(out.shape) == new_res
+    assert np.max(np.abs(out.cpu().numpy() - ref)) < 1e-6
+    same = uivr.upsample_grid(ctx, _gpu(a, dev), shape)
+    assert np.array_equal(same.cpu().numpy(), a)
+    with pytest.raises(NotImplementedError):
+        uivr.upsample_grid(ctx, _gpu(a, dev), (3 * shape[0], 3 * shape[1], 3 * shape[2], shape[3]))
+
+
+def test_upsample_params_in_the_loop(uivr, dev):
+    """optimize.py:228-252 inside a short optimisation: grids double, Adam state of the re-sized
+    tensors starts over, the supergrid factor is re-derived, rendering continues at the new resolution."""
+    n, w, h, spp = 8, 24, 24, 16
+    sig_t, alb_t = hetero_grids(16, seed=4)
+    vol = uivr.benchmark_scene(n, w, h, scale=6.0, majorant_resolution_factor=uivr.adjust_majorant_res_factor(8, (n, n, n, 1)))
+    assert vol.majorant_resolution_factor == 2
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.get_int_config("volpathsimple-drt").create(max_depth=16)
+    sensors = uivr.circle_sensors(2, w, h)
+    tscene = uivr.Scene(uivr.benchmark_scene(16, w, h, scale=6.0, majorant_resolution_factor=4), device=0)
+    target = {"m.sigma_t.data": _gpu(sig_t, dev), "m.albedo.data": _gpu(alb_t, dev)}
+    refs = [integ.render(tscene, target, sensor=s, seed=50 + i, spp=128).clone() for i, s in enumerate(sensors)]
+    params = {"m.sigma_t.data": torch.full((n, n, n, 1), 0.3, device=dev), "m.albedo.data": torch.full((n, n, n, 3), 0.6, device=dev)}
+    opt = uivr.Adam(lr=2e-2, params=params)
+    for it in range(3):
+        uivr.optimization_step(scene, integ, opt, sensors, refs, it, spp)
+    shapes = uivr.upsample_params(scene, opt, 8)
+    assert shapes["m.sigma_t.data"] == (16, 16, 16, 1) and shapes["m.albedo.data"] == (16, 16, 16, 3)
+    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 4
+    assert set(opt.t.values()) == {0} and float(opt.m["m.sigma_t.data"].abs().max()) == 0.0
+    losses = [uivr.optimization_step(scene, integ, opt, sensors, refs, 3 + it, spp) for it in range(3)]
+    scene.ctx.check_watchdog()
+    assert all(np.isfinite(losses)) and tuple(opt.params["m.sigma_t.data"].shape) == (16, 16, 16, 1)

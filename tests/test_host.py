@@ -177,3 +177,42 @@ def test_batch_index_sampler_matches_oracle(uivr, oracle):
     assert set(si.tolist()) == set(range(5)) and px[:, 0].min() == 0 and px[:, 0].max() == 39
     with pytest.raises(ValueError):
         uivr.sensor_table([uivr.Sensor(width=8, height=8), uivr.Sensor(width=9, height=8)])
+
+
+def test_multires_host_rules(uivr):
+    """adjust_majorant_res_factor (optimize.py:182-199) and the upsampling schedule (opt_config.py:40-44)."""
+    f = uivr.adjust_majorant_res_factor
+    assert f(8, (256, 256, 256, 1)) == 8
+    assert f(8, (32, 32, 32, 1)) == 8        # 32 // 8 = 4: still a meaningful supergrid
+    assert f(8, (16, 16, 16, 1)) == 4        # largest factor with >= 4 cells
+    assert f(8, (6, 6, 6, 1)) == 0           # -> 1 -> supergrid disabled
+    assert f(8, (64, 16, 32, 1)) == 4        # shortest axis decides
+    assert f(0, (256, 256, 256, 1)) == 0 and f(1, (256,) * 3) == 0
+    assert uivr.upsample_iterations([0.04, 0.16, 0.36, 0.64], 6000) == {240, 960, 2160, 3840}  # reproduce.py:58
+    assert uivr.upsample_iterations(None, 10) == set()
+
+
+def test_vol_roundtrip_and_header(uivr, tmp_path):
+    """Mitsuba VOL v3 layout (util.save_params -> mi.VolumeGrid.write, util.py:55-71): 48-byte header,
+    float32 data with x fastest, then channels."""
+    rng = np.random.default_rng(0)
+    g = rng.random((5, 4, 3, 3)).astype(np.float32)  # (Z, Y, X, C)
+    p = tmp_path / "a.vol"
+    uivr.write_vol(str(p), g, (-0.5, -0.5, -0.5), (1.5, 1.5, 1.5))
+    raw = p.read_bytes()
+    assert raw[:4] == b"VOL\x03" and len(raw) == 48 + g.size * 4
+    assert np.frombuffer(raw[4:24], dtype="<i4").tolist() == [1, 3, 4, 5, 3]
+    assert np.allclose(np.frombuffer(raw[24:48], dtype="<f4"), [-0.5, -0.5, -0.5, 1.5, 1.5, 1.5])
+    # value (z=2, y=1, x=0, c=1) sits at ((z*Y + y)*X + x)*C + c
+    off = 48 + 4 * (((2 * 4 + 1) * 3 + 0) * 3 + 1)
+    assert np.frombuffer(raw[off:off + 4], dtype="<f4")[0] == g[2, 1, 0, 1]
+    back, lo, hi = uivr.read_vol(str(p))
+    assert np.array_equal(back, g) and lo == (-0.5, -0.5, -0.5) and hi == (1.5, 1.5, 1.5)
+    import torch
+    out = uivr.save_params(str(tmp_path / "params"), {"medium1.sigma_t.data": torch.from_numpy(g[..., :1].copy())}, "final")
+    assert os.path.basename(out["medium1.sigma_t.data"]) == "final-medium1_sigma_t.vol"
+    with pytest.raises(NotImplementedError):
+        uivr.save_params(str(tmp_path), {"medium1.scale": torch.zeros(1)}, "x")
+    (tmp_path / "bad.vol").write_bytes(b"nope")
+    with pytest.raises(ValueError):
+        uivr.read_vol(str(tmp_path / "bad.vol"))

@@ -24,7 +24,7 @@ EXPORTS = [
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
-    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch",
+    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
 ]
@@ -88,6 +88,7 @@ def lib():
         "uivr_set_scene": ([vp, C.POINTER(SceneDesc)], C.c_int),
         "uivr_set_integrator": ([vp, C.POINTER(IntegratorProps)], C.c_int),
         "uivr_set_batch": ([vp, C.POINTER(BatchDesc)], C.c_int),
+        "uivr_upsample2x": ([vp, fp, C.POINTER(C.c_int32), i32, fp, vp], C.c_int),
         "uivr_update_medium": ([vp, fp, vp], C.c_int),
         "uivr_render_forward": ([vp, fp, u32, i32, C.POINTER(Shard), fp, fp, vp], C.c_int),
         "uivr_render_backward": ([vp, fp, fp, u32, i32, C.POINTER(Shard), fp, fp, fp, vp], C.c_int),
@@ -233,6 +234,10 @@ class Context:
         self._check(self._L.uivr_adam_step(self._h, param_ptr, grad_ptr, m_ptr, v_ptr, int(n), float(lr), float(beta1),
                                            float(beta2), float(eps), int(t), float(lo), float(hi), stream),
                     "uivr_adam_step")
+
+    def upsample2x(self, in_ptr, res_xyz, channels, out_ptr, stream=0):
+        r = (C.c_int32 * 3)(*[int(v) for v in res_xyz])
+        self._check(self._L.uivr_upsample2x(self._h, in_ptr, r, int(channels), out_ptr, stream), "uivr_upsample2x")
 
     # -- instrumentation --
     def reset_counters(self, stream: int = 0):

@@ -570,6 +570,16 @@ int uivr_adam_step(uivr_ctx* ctx, float* d_param, const float* d_grad, float* d_
     return UIVR_OK;
 }
 
+int uivr_upsample2x(uivr_ctx* ctx, const float* d_in, const int32_t res[3], int32_t channels, float* d_out, void* stream) {
+    if (!ctx || !d_in || !d_out || !res) return UIVR_ERR_INVALID;
+    if (res[0] < 1 || res[1] < 1 || res[2] < 1 || channels < 1) return fail(ctx, UIVR_ERR_INVALID, "invalid grid shape");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_upsample2x<<<ctx->num_sms * 8, kBlock, 0, (cudaStream_t) stream>>>(d_in, d_out, res[0], res[1], res[2], channels);
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
 // ---- primitives ----
 
 uint32_t uivr_tea32(uint32_t v0, uint32_t v1) {

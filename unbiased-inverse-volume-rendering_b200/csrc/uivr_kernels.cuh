@@ -116,6 +116,34 @@ __global__ void __launch_bounds__(kBlock) k_adam_step(float* __restrict__ param,
 }
 
 // ---------------------------------------------------------------------------------------
+// K7: multires upsampling x2 (upsample_grid, optimize.py:203-225: scipy zoom(order=1, mode='nearest',
+// grid_mode=True)).  Output voxel o samples the input at o/2 - 1/4 per axis, i.e. weights
+// (1/4, 3/4) on the two nearest input voxels, indices clamped at the border.  (Z,Y,X,C) layout.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_upsample2x(const float* __restrict__ in, float* __restrict__ out, int rx, int ry,
+                                                       int rz, int ch) {
+    const size_t ox = 2 * (size_t) rx, oy = 2 * (size_t) ry, oz = 2 * (size_t) rz;
+    const size_t n = ox * oy * oz * ch;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int c = (int) (i % ch);
+        size_t r = i / ch;
+        const int x = (int) (r % ox); r /= ox;
+        const int y = (int) (r % oy);
+        const int z = (int) (r / oy);
+        // even output index 2k: inputs (k-1, k) with weights (1/4, 3/4); odd 2k+1: (k, k+1) with (3/4, 1/4)
+        const int x0 = max((x - 1) >> 1, 0), x1 = min((x + 1) >> 1, rx - 1);
+        const int y0 = max((y - 1) >> 1, 0), y1 = min((y + 1) >> 1, ry - 1);
+        const int z0 = max((z - 1) >> 1, 0), z1 = min((z + 1) >> 1, rz - 1);
+        const float wx = (x & 1) ? 0.25f : 0.75f, wy = (y & 1) ? 0.25f : 0.75f, wz = (z & 1) ? 0.25f : 0.75f;
+#define UIVR_V(zz, yy, xx) __ldg(in + (((size_t) (zz) * ry + (yy)) * rx + (xx)) * ch + c)
+        const float c00 = lerpf(UIVR_V(z0, y0, x0), UIVR_V(z0, y0, x1), wx), c10 = lerpf(UIVR_V(z0, y1, x0), UIVR_V(z0, y1, x1), wx);
+        const float c01 = lerpf(UIVR_V(z1, y0, x0), UIVR_V(z1, y0, x1), wx), c11 = lerpf(UIVR_V(z1, y1, x0), UIVR_V(z1, y1, x1), wx);
+#undef UIVR_V
+        out[i] = lerpf(lerpf(c00, c10, wy), lerpf(c01, c11, wy), wz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // variant 1: one sample per lane, warps pull 32-sample chunks from a global counter
 // ---------------------------------------------------------------------------------------
 UIVR_DEV bool next_chunk(const Params& P, uint64_t total, uint32_t& item) {

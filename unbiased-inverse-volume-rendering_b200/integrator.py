@@ -88,6 +88,13 @@ class Scene:
             self._medium_key = key
 
 
+    def update_medium_after_reshape(self, sigma_t: torch.Tensor):
+        """The medium changed resolution (self.volume was replaced): re-describe the scene to the
+        native context and rebuild its lookup structures on the next render."""
+        self._scene_key = None
+        self._medium_key = None
+
+
 class VolpathSimpleIntegrator:
     """Same property names / defaults as python/integrators/volpathsimple.py:19-34."""
 

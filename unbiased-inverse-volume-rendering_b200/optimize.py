@@ -64,7 +64,7 @@ class Adam:
         self.params = params
         self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
         self.lr = {k: float(lr) for k in params}
-        self.t = 0
+        self.t = {k: 0 for k in params}   # step counter per parameter (mi.ad.Adam keeps its state per key)
         self.m = {k: torch.zeros_like(p) for k, p in params.items()}
         self.v = {k: torch.zeros_like(p) for k, p in params.items()}
         for k, p in params.items():
@@ -83,16 +83,27 @@ class Adam:
     def items(self):
         return self.params.items()
 
+    def replace(self, key: str, value: torch.Tensor):
+        """opt[key] = value with a new shape (multires upsampling, optimize.py:239-242): the moments and
+        the step counter of that parameter start over, as mi.ad.Optimizer resets a re-sized parameter."""
+        if key not in self.params:
+            raise KeyError(key)
+        value = value.detach().to(torch.float32).contiguous()
+        self.params[key] = value
+        self.m[key] = torch.zeros_like(value)
+        self.v[key] = torch.zeros_like(value)
+        self.t[key] = 0
+
     def step(self, ctx: _native.Context, grads: Dict[str, torch.Tensor], max_density: float = 250.0):
         """opt.step() + enforce_valid_params in one pass per tensor."""
-        self.t += 1
         for k, p in self.params.items():
+            self.t[k] += 1
             g = grads[k]
             if g.shape != p.shape or g.dtype != torch.float32 or not g.is_contiguous():
                 raise ValueError(f"gradient of {k} must match its parameter")
             lo, hi = param_bounds(k, max_density)
             ctx.adam_step(p.data_ptr(), g.data_ptr(), self.m[k].data_ptr(), self.v[k].data_ptr(), p.numel(),
-                          self.lr[k], self.beta_1, self.beta_2, self.epsilon, self.t, lo,
+                          self.lr[k], self.beta_1, self.beta_2, self.epsilon, self.t[k], lo,
                           hi if hi != float("inf") else 3.4028234663852886e38, _stream())
 
 

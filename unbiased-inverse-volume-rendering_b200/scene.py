@@ -103,6 +103,14 @@ class VolumeScene:
         s.sensor = sensor
         return s
 
+    def with_resolution(self, res, majorant_resolution_factor: int) -> "VolumeScene":
+        """The same scene with a re-sampled medium (multires upsampling, optimize.py:228-252)."""
+        import copy
+        s = copy.copy(self)
+        s.res = tuple(int(r) for r in res)
+        s.majorant_resolution_factor = int(majorant_resolution_factor)
+        return s
+
     def as_dict(self) -> Dict[str, object]:
         d = {
             "res": tuple(int(r) for r in self.res),
