@@ -199,7 +199,8 @@ int uivr_test_sigma_lookup(uivr_ctx* ctx, const float* d_p, int n, float* d_out,
 /* copy the current majorant supergrid to d_out (mres[0]*mres[1]*mres[2] floats) */
 int uivr_get_majorant(uivr_ctx* ctx, int32_t mres[3], float* d_out, void* stream);
 uint32_t uivr_tea32(uint32_t v0, uint32_t v1);          /* mi.sample_tea_32(v0, v1)[0] */
-uint32_t uivr_alt_seed(uint32_t seed_grad);             /* volpathsimple.py:99-107 */
+uint32_t uivr_alt_seed(uint32_t seed_grad);             /* volpathsimple.py:99-107 under mi.render */
+uint32_t uivr_alt_seed_batch(uint32_t seed_grad);       /* same under render_batch (no jitter draws, batched.py:390) */
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,8 @@ def lib():
     L.uivr_oracle_render_backward.restype = C.c_int
     L.uivr_oracle_alt_seed.argtypes = [C.c_uint32]
     L.uivr_oracle_alt_seed.restype = C.c_uint32
+    L.uivr_oracle_alt_seed_batch.argtypes = [C.c_uint32]
+    L.uivr_oracle_alt_seed_batch.restype = C.c_uint32
     _lib = L
     return L
 
@@ -201,6 +203,10 @@ def sincos2pi(x):
 
 def alt_seed(seed_grad: int) -> int:
     return int(lib().uivr_oracle_alt_seed(seed_grad & 0xFFFFFFFF))
+
+
+def alt_seed_batch(seed_grad: int) -> int:
+    return int(lib().uivr_oracle_alt_seed_batch(seed_grad & 0xFFFFFFFF))
 
 
 def trilinear(grid, p) -> np.ndarray:

@@ -80,19 +80,24 @@ void uivr_oracle_sampler_floats(uint32_t seed, uint32_t idx, int n, float* out) 
 }
 
 /* volpathsimple.py:99-107: the alt sampler's seed is derived from the bit pattern of lane
- * 0's `alt_seed_rnd`, i.e. the 4th float of stream (seed_grad, idx 0): 2 jitter draws
- * (sample_rays), 1 burned draw (:71), then alt_seed_rnd (:99).  A masked-out lane still
- * yields the value it would have drawn, so this is a pure function of seed_grad. */
-uint32_t uivr_oracle_alt_seed(uint32_t seed_grad) {
+ * 0's `alt_seed_rnd`: the float of stream (seed_grad, idx 0) that follows the draws made
+ * before :99 -- for mi.render 2 jitter draws (sample_rays) + 1 burned draw (:71), so the 4th
+ * float; for render_batch the path sampler draws no jitter (batched.py:390, :437), so the 2nd.
+ * A masked-out lane still yields the value it would have drawn, so this is a pure function of
+ * seed_grad. */
+static uint32_t alt_seed_after(uint32_t seed_grad, int skipped) {
     rng_t r;
     sampler_seed(&r, seed_grad, 0);
-    rng_f(&r); rng_f(&r); rng_f(&r);
+    for (int i = 0; i < skipped; ++i) rng_f(&r);
     union { float f; uint32_t u; } c;
     c.f = rng_f(&r);
     uint32_t v[2];
     uivr_oracle_tea(c.u, 1, v);
     return v[0];
 }
+
+uint32_t uivr_oracle_alt_seed(uint32_t seed_grad) { return alt_seed_after(seed_grad, 3); }
+uint32_t uivr_oracle_alt_seed_batch(uint32_t seed_grad) { return alt_seed_after(seed_grad, 1); }
 
 /* ------------------------------------------------------------------------------------ */
 /* Exact-op transcendental replacements (DESIGN.md "Arithmetic contract")                */
@@ -782,7 +787,8 @@ static int batch_segment(const ctx_t* C, uint32_t idx, uint32_t spp, seg_t* s) {
     return camera_segment_frame(C, B->sensors + 16 * (size_t) e[0], u, v, s);
 }
 
-static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v, seg_t* s) {
+/* perspective sensor: primary ray through film position (u, v), in the medium's local space */
+static void camera_ray_local(const ctx_t* C, const float* F, float u, float v, float ol[3], float dl[3]) {
     const uivr_oracle_scene* sc = C->sc;
     float cx = F[12] * FMA(-2.0f, u, 1.0f);
     float cy = F[13] * FMA(-2.0f, v, 1.0f);
@@ -795,13 +801,16 @@ static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v
         d[a] *= inv_len;
         o[a] = FMA(near_t, d[a], F[a]);
     }
-    /* to local space */
     const float* M = sc->to_local;
-    float ol[3], dl[3];
     for (int a = 0; a < 3; ++a)
         ol[a] = FMA(M[4 * a + 0], o[0], FMA(M[4 * a + 1], o[1], FMA(M[4 * a + 2], o[2], M[4 * a + 3])));
     dir_to_local(M, d, dl);
-    /* reach_medium (volpathsimple.py:292-319): slab test against local [0,1]^3 */
+}
+
+/* scene.ray_intersect against the medium box from a ray origin not known to be inside
+ * (volpathsimple.py:298): slab test against local [0,1]^3.
+ * 0 = miss, 1 = enters at *t, 2 = origin inside, first hit is the far wall at *t */
+static int box_entry(const float ol[3], const float dl[3], float* t) {
     float tn = -UIVR_INF, tf = UIVR_INF;
     for (int a = 0; a < 3; ++a) {
         if (dl[a] != 0.0f) {
@@ -815,14 +824,28 @@ static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v
         }
     }
     if (!(tn <= tf) || !(tf > 0.0f)) return 0;
-    if (!(tn > 0.0f)) return 2; /* origin inside: first hit is the far wall, re-spawn misses */
-    /* spawn just inside (si.spawn_ray, :306): entry point clamped into [eps, 1-eps] */
+    if (!(tn > 0.0f)) { *t = tf; return 2; }
+    *t = tn;
+    return 1;
+}
+
+/* si.spawn_ray across the null boundary INTO the medium (:306): entry point clamped into
+ * [eps, 1-eps] */
+static inline void entry_spawn(const float ol[3], const float dl[3], float tn, float o[3]) {
     for (int a = 0; a < 3; ++a) {
         float e = FMA(tn, dl[a], ol[a]);
-        e = e < ENTRY_EPS ? ENTRY_EPS : (e > 1.0f - ENTRY_EPS ? 1.0f - ENTRY_EPS : e);
-        s->o[a] = e;
-        s->d[a] = dl[a];
+        o[a] = e < ENTRY_EPS ? ENTRY_EPS : (e > 1.0f - ENTRY_EPS ? 1.0f - ENTRY_EPS : e);
     }
+}
+
+static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v, seg_t* s) {
+    float ol[3], dl[3], tn = 0.0f;
+    camera_ray_local(C, F, u, v, ol, dl);
+    /* reach_medium (volpathsimple.py:292-319) */
+    int hit = box_entry(ol, dl, &tn);
+    if (hit != 1) return hit; /* 2: origin inside, the re-spawned ray misses */
+    entry_spawn(ol, dl, tn, s->o);
+    for (int a = 0; a < 3; ++a) s->d[a] = dl[a];
     s->tmax = exit_distance(s);
     return (s->tmax > 0.0f && s->tmax < UIVR_INF) ? 1 : 2;
 }
@@ -933,7 +956,7 @@ static int run(ctx_t* C, int backward, uint32_t seed, uint32_t spp, const uivr_o
     job_t* jobs = (job_t*) calloc((size_t) nthreads, sizeof(job_t));
     pthread_t* th = (pthread_t*) calloc((size_t) nthreads, sizeof(pthread_t));
     if (!jobs || !th) return -1;
-    uint32_t alt_seed = backward ? uivr_oracle_alt_seed(seed) : 0;
+    uint32_t alt_seed = backward ? alt_seed_after(seed, C->batch ? 1 : 3) : 0;
     for (int i = 0; i < nthreads; ++i) {
         jobs[i].C = C;
         jobs[i].backward = backward;
@@ -1043,6 +1066,175 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, NULL, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
     return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* upstream primitives for oracle/refshim.py (see uivr_oracle.h)                          */
+/* ------------------------------------------------------------------------------------ */
+
+struct uivr_oracle_shim {
+    ctx_t C;
+    uivr_oracle_scene sc;
+};
+
+uivr_oracle_shim* uivr_oracle_shim_create(const uivr_oracle_scene* scene, const float* sigma_t, const float* albedo) {
+    uivr_oracle_shim* h = (uivr_oracle_shim*) calloc(1, sizeof(*h));
+    if (!h) return NULL;
+    h->sc = *scene;
+    if (setup_ctx(&h->C, &h->sc, sigma_t, albedo)) { free(h); return NULL; }
+    return h;
+}
+
+void uivr_oracle_shim_destroy(uivr_oracle_shim* h) {
+    if (!h) return;
+    free(h->C.majorant);
+    free(h);
+}
+
+void uivr_oracle_shim_camera_ray(const uivr_oracle_shim* h, int n, const float* frames, const int32_t* frame_idx,
+                                 const float* u, const float* v, float* o, float* d) {
+    const uivr_oracle_scene* sc = &h->sc;
+    float F0[16] = {0};
+    for (int a = 0; a < 3; ++a) {
+        F0[a] = sc->cam_origin[a]; F0[3 + a] = sc->cam_left[a]; F0[6 + a] = sc->cam_up[a]; F0[9 + a] = sc->cam_dir[a];
+    }
+    F0[12] = sc->tan_x; F0[13] = sc->tan_y; F0[14] = sc->near_clip;
+    for (int i = 0; i < n; ++i) {
+        const float* F = frames ? frames + 16 * (size_t) frame_idx[i] : F0;
+        camera_ray_local(&h->C, F, u[i], v[i], o + 3 * i, d + 3 * i);
+    }
+}
+
+void uivr_oracle_shim_film_uv(const uivr_oracle_shim* h, int n, const uint32_t* pix, const float* jx,
+                              const float* jy, float* u, float* v) {
+    const uivr_oracle_scene* sc = &h->sc;
+    for (int i = 0; i < n; ++i) {
+        uint32_t px = pix[i] % (uint32_t) sc->width, py = pix[i] / (uint32_t) sc->width;
+        u[i] = ((float) px + jx[i]) * (1.0f / (float) sc->width);
+        v[i] = ((float) py + jy[i]) * (1.0f / (float) sc->height);
+    }
+}
+
+void uivr_oracle_shim_box_entry(int n, const float* o, const float* d, float* t, int32_t* kind) {
+    for (int i = 0; i < n; ++i) {
+        t[i] = UIVR_INF;
+        kind[i] = box_entry(o + 3 * i, d + 3 * i, &t[i]);
+    }
+}
+
+void uivr_oracle_shim_entry_spawn(int n, const float* o, const float* d, const float* t, float* o_new) {
+    for (int i = 0; i < n; ++i) entry_spawn(o + 3 * i, d + 3 * i, t[i], o_new + 3 * i);
+}
+
+void uivr_oracle_shim_exit(int n, const float* o, const float* d, float* t, uint8_t* ok) {
+    for (int i = 0; i < n; ++i) {
+        seg_t s;
+        for (int a = 0; a < 3; ++a) { s.o[a] = o[3 * i + a]; s.d[a] = d[3 * i + a]; }
+        t[i] = exit_distance(&s);
+        ok[i] = (uint8_t) (t[i] > 0.0f && t[i] < UIVR_INF);
+    }
+}
+
+void uivr_oracle_shim_dir_to_local(const uivr_oracle_shim* h, int n, const float* w, float* d) {
+    for (int i = 0; i < n; ++i) dir_to_local(h->sc.to_local, w + 3 * i, d + 3 * i);
+}
+
+static void shim_seg(const float* o, const float* d, float maxt, seg_t* s) {
+    for (int a = 0; a < 3; ++a) {
+        s->o[a] = o[a];
+        s->d[a] = d[a];
+        s->inv_d[a] = d[a] != 0.0f ? 1.0f / d[a] : UIVR_INF;
+    }
+    s->tmax = maxt;
+}
+
+void uivr_oracle_shim_sample_interaction(const uivr_oracle_shim* h, int n, const float* o, const float* d,
+                                         const float* maxt, const float* u, const uint8_t* active,
+                                         float* t, float* sigma_t, float* sigma_bar, uint8_t* valid) {
+    counters_t K;
+    memset(&K, 0, sizeof(K));
+    for (int i = 0; i < n; ++i) {
+        valid[i] = 0;
+        t[i] = UIVR_INF;
+        sigma_t[i] = 0.0f;
+        sigma_bar[i] = 0.0f;
+        if (!active[i]) continue;
+        seg_t s;
+        shim_seg(o + 3 * i, d + 3 * i, maxt[i], &s);
+        walk_t w;
+        walk_init(&h->C, &K, &s, &w);
+        float tt, sb, p[3];
+        if (!walk_next(&h->C, &K, &w, u[i], &tt, &sb)) continue;
+        seg_point(&s, tt, p);
+        t[i] = tt;
+        sigma_t[i] = eval_sigma_t(&h->C, &K, p);
+        sigma_bar[i] = sb;
+        valid[i] = 1;
+    }
+}
+
+void uivr_oracle_shim_sample_interaction_drt(const uivr_oracle_shim* h, int n, const float* o, const float* d,
+                                             const float* maxt, uint64_t* rng_state, const uint64_t* rng_inc,
+                                             const uint8_t* active, float* t, float* sigma_t, float* weight,
+                                             uint8_t* valid) {
+    counters_t K;
+    memset(&K, 0, sizeof(K));
+    for (int i = 0; i < n; ++i) {
+        valid[i] = 0;
+        t[i] = UIVR_INF;
+        sigma_t[i] = 0.0f;
+        weight[i] = 0.0f;
+        if (!active[i]) continue;
+        seg_t s;
+        shim_seg(o + 3 * i, d + 3 * i, maxt[i], &s);
+        rng_t r;
+        r.state = rng_state[i];
+        r.inc = rng_inc[i];
+        r.draws = 0;
+        float ts = 0.0f, st = 0.0f, D = 0.0f;
+        valid[i] = (uint8_t) drt_sample(&h->C, &K, &s, &r, &ts, &st, &D);
+        rng_state[i] = r.state;
+        weight[i] = D;
+        if (valid[i]) { t[i] = ts; sigma_t[i] = st; }
+    }
+}
+
+void uivr_oracle_shim_lookup(const uivr_oracle_shim* h, int which, int n, const float* p, float* out) {
+    counters_t K;
+    memset(&K, 0, sizeof(K));
+    for (int i = 0; i < n; ++i) {
+        if (which == 0) {
+            out[i] = eval_sigma_t(&h->C, &K, p + 3 * i);
+        } else if (which == 1) {
+            eval_albedo(&h->C, &K, p + 3 * i, out + 3 * i);
+        } else {
+            int cell[3];
+            for (int a = 0; a < 3; ++a)
+                cell[a] = clampi((int) floorf(p[3 * i + a] * (float) h->C.mres[a]), 0, h->C.mres[a] - 1);
+            out[i] = majorant_at(&h->C, &K, cell);
+        }
+    }
+}
+
+void uivr_oracle_shim_scatter(const uivr_oracle_shim* h, int which, int n, const float* p, const float* g,
+                              const uint8_t* mask, double* dgrid) {
+    for (int i = 0; i < n; ++i) {
+        if (!mask[i]) continue;
+        if (which == 0) {
+            float gs = h->sc.scale * g[i];
+            scatter(dgrid, h->sc.res, 1, p + 3 * i, &gs);
+        } else {
+            scatter(dgrid, h->sc.res, 3, p + 3 * i, g + 3 * i);
+        }
+    }
+}
+
+void uivr_oracle_shim_uniform_sphere(int n, const float* xi1, const float* xi2, float* w) {
+    for (int i = 0; i < n; ++i) uniform_sphere(xi1[i], xi2[i], w + 3 * i);
+}
+
+void uivr_oracle_shim_fma(int n, const float* a, const float* b, const float* c, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = FMA(a[i], b[i], c[i]);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -89,7 +89,8 @@ void  uivr_oracle_pcg32_stream(uint64_t initstate, uint64_t initseq, int n, uint
 void  uivr_oracle_sampler_floats(uint32_t seed, uint32_t idx, int n, float* out);
 void  uivr_oracle_neg_log1m(const float* u, int n, float* out);
 void  uivr_oracle_sincos2pi(const float* x, int n, float* s, float* c);
-uint32_t uivr_oracle_alt_seed(uint32_t seed_grad);
+uint32_t uivr_oracle_alt_seed(uint32_t seed_grad);        /* mi.render: 4th float of lane 0 */
+uint32_t uivr_oracle_alt_seed_batch(uint32_t seed_grad);  /* render_batch: 2nd float (no jitter draws) */
 /* trilinear lookup at local points p (n x 3); grid (Z,Y,X,C) */
 void  uivr_oracle_trilinear(const float* grid, const int32_t res[3], int channels,
                             const float* p, int n, float* out);
@@ -128,6 +129,50 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
                                       float* sample_L_out, uint64_t* counters);
 /* the (sensor, pixel x, pixel y) triple of batch element b (host-side check of the index sampler) */
 void uivr_oracle_batch_element(const uivr_oracle_batch* batch, uint32_t b, uint32_t out[3]);
+
+/* ---- upstream primitives for oracle/refshim.py ----
+ * refshim runs the reference's UNMODIFIED python/integrators/volpathsimple.py (and the drivers of
+ * python/batched.py) on a small numpy stand-in for the Mitsuba 3 / Dr.Jit API.  The control flow,
+ * masks, RNG draw order and gradient formulae then come from the reference files themselves; the
+ * upstream arithmetic (un-vendored Mitsuba branch: Medium::sample_interaction(_drt), GridVolume
+ * lookup + adjoint, box intersection, sensor, sphere warp) is supplied by the functions below,
+ * which wrap the same static functions the oracle's own path code uses.  Lane arrays of length n;
+ * masks are bytes; vectors are [n][3] row-major; positions and directions are in the medium's
+ * local space with distances in world units (the oracle's segment convention). */
+typedef struct uivr_oracle_shim uivr_oracle_shim;
+uivr_oracle_shim* uivr_oracle_shim_create(const uivr_oracle_scene* scene, const float* sigma_t, const float* albedo);
+void uivr_oracle_shim_destroy(uivr_oracle_shim* h);
+/* film position of pixel pix with jitter (Sensor::sample_ray's sample2) */
+void uivr_oracle_shim_film_uv(const uivr_oracle_shim* h, int n, const uint32_t* pix, const float* jx,
+                              const float* jy, float* u, float* v);
+/* Sensor::sample_ray_differential: primary ray through (u, v); frames == NULL: the scene's sensor,
+ * else frames[frame_idx[i]] (16 floats each, uivr_oracle_batch layout) */
+void uivr_oracle_shim_camera_ray(const uivr_oracle_shim* h, int n, const float* frames, const int32_t* frame_idx,
+                                 const float* u, const float* v, float* o, float* d);
+/* scene.ray_intersect for an origin not known to be inside: kind 0 miss, 1 entry at t, 2 far wall at t */
+void uivr_oracle_shim_box_entry(int n, const float* o, const float* d, float* t, int32_t* kind);
+/* si.spawn_ray into the medium: origin just inside the entry point */
+void uivr_oracle_shim_entry_spawn(int n, const float* o, const float* d, const float* t, float* o_new);
+/* scene.ray_intersect from inside the medium: distance to the box boundary; ok iff 0 < t < inf */
+void uivr_oracle_shim_exit(int n, const float* o, const float* d, float* t, uint8_t* ok);
+void uivr_oracle_shim_dir_to_local(const uivr_oracle_shim* h, int n, const float* w, float* d);
+/* Medium::sample_interaction(ray, u): DDA from the ray origin (restarted per call, as the
+ * reference does, volpathsimple.py:331-334); t relative to o; valid iff a collision precedes maxt */
+void uivr_oracle_shim_sample_interaction(const uivr_oracle_shim* h, int n, const float* o, const float* d,
+                                         const float* maxt, const float* u, const uint8_t* active,
+                                         float* t, float* sigma_t, float* sigma_bar, uint8_t* valid);
+/* Medium::sample_interaction_drt(ray, sampler): advances the lanes' PCG32 states in place */
+void uivr_oracle_shim_sample_interaction_drt(const uivr_oracle_shim* h, int n, const float* o, const float* d,
+                                             const float* maxt, uint64_t* rng_state, const uint64_t* rng_inc,
+                                             const uint8_t* active, float* t, float* sigma_t, float* weight,
+                                             uint8_t* valid);
+/* which = 0: sigma_t(p) = scale * grid (1 value), 1: albedo(p) (3 values), 2: majorant at p (1 value) */
+void uivr_oracle_shim_lookup(const uivr_oracle_shim* h, int which, int n, const float* p, float* out);
+/* adjoint of lookup 0 / 1: scatter-add g (1 or 3 floats per lane) into dgrid (doubles) where mask */
+void uivr_oracle_shim_scatter(const uivr_oracle_shim* h, int which, int n, const float* p, const float* g,
+                              const uint8_t* mask, double* dgrid);
+void uivr_oracle_shim_uniform_sphere(int n, const float* xi1, const float* xi2, float* w);
+void uivr_oracle_shim_fma(int n, const float* a, const float* b, const float* c, float* out); /* fmaf */
 
 /* ---- optimiser step ("next" row) ----
  * mi.ad.Adam.step() (python/opt_config.py:46-48, python/optimize.py:352; update rule SURVEY App.

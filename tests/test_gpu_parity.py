@@ -665,3 +665,74 @@ def test_upsample_params_in_the_loop(uivr, dev):
     losses = [uivr.optimization_step(scene, integ, opt, sensors, refs, 3 + it, spp) for it in range(3)]
     scene.ctx.check_watchdog()
     assert all(np.isfinite(losses)) and tuple(opt.params["m.sigma_t.data"].shape) == (16, 16, 16, 1)
+
+
+# ---------------------------------------------------------------------------------------
+# reference-generated vectors (tests/golden/refshim_*.npz, made by running the reference's own
+# volpathsimple.py / batched.py / opt_config.py through oracle/refshim.py in the build container)
+# ---------------------------------------------------------------------------------------
+
+REFSHIM_SAMPLE_TOL = 2e-5   # float32 rounding between the reference's per-collision DDA restart
+REFSHIM_GRAD_TOL = 1e-4     # and the carried DDA (see tests/test_refshim_golden.py)
+REFSHIM_ALBEDO_TOL = {"cube3": 2e-3}
+
+
+def _refshim_cases():
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import refshim_cases as RC
+    return RC, gdir
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("case", ["cube3", "hetero12", "hetero16"])
+def test_cuda_matches_reference_vectors(uivr, dev, variant, case):
+    """The CUDA path, through the plugin mirror created by the registry (get_int_config(...).create,
+    opt_config.py:83-169), against what the reference's own integrator file computes."""
+    import os
+    RC, gdir = _refshim_cases()
+    c = RC.CASES[case]
+    sig, alb, vol = RC.case_inputs(case)
+    g = np.load(os.path.join(gdir, f"refshim_{case}.npz"))
+    for integ, max_depth in c["runs"]:
+        props = RC.props_of(integ, max_depth)
+        key = f"{integ}@{max_depth}"
+        img, smp, _ = _run_forward(uivr, vol, props, sig, alb, c["seed"], c["spp"], dev, variant, counting=False)
+        assert np.max(np.abs(smp - g[f"{key}/samples"])) < REFSHIM_SAMPLE_TOL, key
+        assert np.max(np.abs(img - g[f"{key}/image"])) < REFSHIM_SAMPLE_TOL, key
+        ds, da, smp_g, _ = _run_backward(uivr, vol, props, sig, alb, g[f"{key}/grad_image"], c["seed_grad"],
+                                         c["spp"], dev, variant, counting=False)
+        assert np.max(np.abs(smp_g - g[f"{key}/samples_grad_pass"])) < REFSHIM_SAMPLE_TOL, key
+        assert rel_linf(ds, g[f"{key}/dsigma"]) < REFSHIM_GRAD_TOL, key
+        if np.abs(g[f"{key}/dalbedo"]).max() > 0:
+            assert rel_linf(da, g[f"{key}/dalbedo"]) < REFSHIM_ALBEDO_TOL.get(case, REFSHIM_GRAD_TOL), key
+        else:
+            assert np.abs(da).max() == 0, key
+
+
+def test_cuda_ray_batch_matches_reference_vectors(uivr, dev):
+    """uivr.render_batch (the drop-in for python/batched.py render_batch) against the output of the
+    reference's render_batch + _BatchedRenderOp.backward."""
+    import os
+    RC, gdir = _refshim_cases()
+    b = RC.BATCH
+    sig, alb, vol, tab = RC.batch_inputs()
+    g = np.load(os.path.join(gdir, "refshim_batch.npz"))
+    sensors = uivr.circle_sensors(b["n_sensors"], b["film"][0], b["film"][1])
+    assert np.array_equal(uivr.sensor_table(sensors), g["sensors"])
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.get_int_config(b["integrator"]).create(max_depth=b["max_depth"])
+    params = {"m.sigma_t.data": _gpu(sig, dev).requires_grad_(True),
+              "m.albedo.data": _gpu(alb, dev).requires_grad_(True)}
+    image, si, px = uivr.render_batch(b["batch_size"], scene, sensors, params, integ, seed=b["seed"],
+                                      spp=b["spp"], spp_grad=b["spp_grad"])
+    assert np.array_equal(np.asarray(si.cpu()), g["sensor_idx"])
+    assert np.array_equal(np.asarray(px.cpu()), g["pixels"])
+    assert np.max(np.abs(image.detach().cpu().numpy() - g["image"])) < REFSHIM_SAMPLE_TOL
+    image.backward(_gpu(RC.batch_loss_grad(g["image"]), dev))
+    torch.cuda.synchronize()
+    assert rel_linf(params["m.sigma_t.data"].grad.cpu().numpy(), g["dsigma"]) < REFSHIM_GRAD_TOL
+    assert rel_linf(params["m.albedo.data"].grad.cpu().numpy(), g["dalbedo"]) < REFSHIM_GRAD_TOL

@@ -30,6 +30,7 @@ def test_host_side_integer_helpers_match_the_oracle(uivr, oracle):
     rng = np.random.default_rng(0)
     for s in rng.integers(0, 1 << 32, size=50):
         assert uivr._native.lib().uivr_alt_seed(int(s)) == oracle.alt_seed(int(s))
+        assert uivr._native.lib().uivr_alt_seed_batch(int(s)) == oracle.alt_seed_batch(int(s))
 
 
 def test_no_cpu_fallback(uivr):

@@ -26,7 +26,7 @@ EXPORTS = [
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
     "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
-    "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed",
+    "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
         "uivr_get_majorant": ([vp, C.POINTER(C.c_int32), fp, vp], C.c_int),
         "uivr_tea32": ([u32, u32], u32),
         "uivr_alt_seed": ([u32], u32),
+        "uivr_alt_seed_batch": ([u32], u32),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)

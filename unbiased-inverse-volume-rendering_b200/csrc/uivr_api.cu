@@ -434,7 +434,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     cudaStream_t st = (cudaStream_t) stream;
     Params P;
     if ((rc = fill_params(ctx, P, shard, seed_grad, spp_grad))) return rc;
-    P.alt_seed = uivr_alt_seed(seed_grad);
+    P.alt_seed = ctx->batch_on ? uivr_alt_seed_batch(seed_grad) : uivr_alt_seed(seed_grad);
     if (ctx->batch_on) P.seed_offsets = uivr_tea32(ctx->batch.seed, 39);  // decorrelated offsets, same pixels (batched.py:69-75)
     P.albedo = d_albedo;
     P.grad_image = d_grad_image;
@@ -588,17 +588,23 @@ uint32_t uivr_tea32(uint32_t v0, uint32_t v1) {
     return a;
 }
 
-uint32_t uivr_alt_seed(uint32_t seed_grad) {
-    // volpathsimple.py:99-107: bits of lane 0's 4th sampler float, scrambled by TEA(.,1)
+static uint32_t alt_seed_after(uint32_t seed_grad, int skipped) {
+    // volpathsimple.py:99-107: bits of lane 0's `alt_seed_rnd` (the sampler float that follows the
+    // `skipped` draws made before :99), scrambled by TEA(.,1)
     Rng r;
     r.seed_sampler(seed_grad, 0);
-    r.next(); r.next(); r.next();
+    for (int i = 0; i < skipped; ++i) r.next();
     const uint32_t x = r.next();
     union { uint32_t u; float f; } c;
     c.u = (x >> 9) | 0x3f800000u;
     c.f = c.f - 1.0f;
     return uivr_tea32(c.u, 1);
 }
+
+// mi.render: 2 jitter draws + the burned draw of :71 precede alt_seed_rnd
+uint32_t uivr_alt_seed(uint32_t seed_grad) { return alt_seed_after(seed_grad, 3); }
+// render_batch: the path sampler draws no jitter (batched.py:390, :437), only :71 precedes it
+uint32_t uivr_alt_seed_batch(uint32_t seed_grad) { return alt_seed_after(seed_grad, 1); }
 
 int uivr_test_neg_log1m(uivr_ctx* ctx, const float* d_u, int n, float* d_out, void* stream) {
     if (!ctx || !d_u || !d_out || n < 0) return UIVR_ERR_INVALID;
