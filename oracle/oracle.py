@@ -309,3 +309,72 @@ def render_batch_backward(desc, props, sensors16, film_size, batch_size, sigma_t
     if rc != 0:
         raise RuntimeError(f"uivr_oracle_render_batch_backward failed ({rc})")
     return dsig, dalb, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+# ---- nerf integrator (python/integrators/nerf.py) ----
+
+class _Nerf(C.Structure):
+    _fields_ = [("queries_per_ray", C.c_int32), ("jittering_enabled", C.c_int32), ("activation", C.c_int32),
+                ("hide_emitters", C.c_int32)]
+
+
+def make_nerf(props: Dict) -> _Nerf:
+    """props: NeRFIntegrator properties (nerf.py:27-35)."""
+    n = _Nerf()
+    n.queries_per_ray = int(props.get("queries_per_ray", 128))
+    n.jittering_enabled = int(bool(props.get("jittering_enabled", True)))
+    act = str(props.get("activation", "identity")).lower()
+    if act not in ("identity", "relu"):
+        raise ValueError(f"Unsupported activation: {act}")  # nerf.py:44
+    n.activation = 1 if act == "relu" else 0
+    n.hide_emitters = int(bool(props.get("hide_emitters", False)))
+    return n
+
+
+def nerf_forward(desc, props, sigma_t, emission, seed: int, spp: int, shard=None,
+                 nthreads: Optional[int] = None, want_samples: bool = False):
+    """-> (image (H,W,3) f32, per-sample L (S,3) or None, counters dict)."""
+    sc = make_scene(desc, dict(max_depth=0))
+    nf = make_nerf(props)
+    sigma_t, emission = _check_grids(desc, sigma_t, emission)
+    h, w = sc.height, sc.width
+    image = np.zeros((h, w, 3), dtype=np.float32)
+    samples = np.zeros((h * w * spp, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib().uivr_oracle_nerf_forward(C.byref(sc), C.byref(nf), _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
+                                        C.c_uint32(seed & 0xFFFFFFFF), C.c_int32(spp), _shard(shard),
+                                        C.c_int(nthreads or os.cpu_count() or 1), _ptr(image, C.c_float),
+                                        _ptr(samples, C.c_float), _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_nerf_forward failed ({rc})")
+    return image, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def nerf_backward(desc, props, sigma_t, emission, grad_image, seed_grad: int, spp_grad: int, shard=None,
+                  nthreads: Optional[int] = None, want_samples: bool = False):
+    """-> (d sigma_t (Z,Y,X,1) f64, d emission (Z,Y,X,3) f64, per-sample primal L or None, counters)."""
+    sc = make_scene(desc, dict(max_depth=0))
+    nf = make_nerf(props)
+    sigma_t, emission = _check_grids(desc, sigma_t, emission)
+    x, y, z = desc["res"]
+    h, w = sc.height, sc.width
+    grad_image = _f32(grad_image).reshape(h, w, 3)
+    dsig = np.zeros((z, y, x, 1), dtype=np.float64)
+    dem = np.zeros((z, y, x, 3), dtype=np.float64)
+    samples = np.zeros((h * w * spp_grad, 3), dtype=np.float32) if want_samples else None
+    counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    rc = lib().uivr_oracle_nerf_backward(C.byref(sc), C.byref(nf), _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
+                                         _ptr(grad_image, C.c_float), C.c_uint32(seed_grad & 0xFFFFFFFF),
+                                         C.c_int32(spp_grad), _shard(shard), C.c_int(nthreads or os.cpu_count() or 1),
+                                         _ptr(dsig, C.c_double), _ptr(dem, C.c_double), _ptr(samples, C.c_float),
+                                         _ptr(counters, C.c_uint64))
+    if rc != 0:
+        raise RuntimeError(f"uivr_oracle_nerf_backward failed ({rc})")
+    return dsig, dem, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
+
+
+def exp_exact(x) -> np.ndarray:
+    x = _f32(x)
+    out = np.zeros_like(x)
+    lib().uivr_oracle_exp(_ptr(x, C.c_float), x.size, _ptr(out, C.c_float))
+    return out

@@ -348,9 +348,15 @@ class _Int:
     def __setitem__(self, k, val):
         self.v = np.where(_M(k).v, type(self)(val).v, self.v).astype(self.DT)
 
-    def __add__(self, o): return type(self)((self.v.astype(np.int64) + self._o(o)))
+    def __add__(self, o):
+        if isinstance(o, (Float, float)):
+            return Float(self) + o
+        return type(self)((self.v.astype(np.int64) + self._o(o)))
     __radd__ = __add__
-    def __sub__(self, o): return type(self)((self.v.astype(np.int64) - self._o(o)))
+    def __sub__(self, o):
+        if isinstance(o, (Float, float)):
+            return Float(self) - o
+        return type(self)((self.v.astype(np.int64) - self._o(o)))
     def __mul__(self, o):
         if isinstance(o, (Float, float)):
             return Float(self) * o
@@ -691,6 +697,9 @@ class SurfaceInteraction3f(Interaction3f):
     def emitter(self, scene):
         return EmitterPtr(~self.is_valid())
 
+    def target_medium(self, d):
+        return MediumPtr(self.is_valid())
+
 
 class MediumInteraction3f(Interaction3f):
     FIELDS = {"t": Float, "p": Point3f, "mint": Float, "sigma_s": Color3f, "sigma_n": Color3f,
@@ -794,12 +803,26 @@ def _minmax(fn):
             r = type(proto).__new__(type(proto))
             r.c = [g(x, y) for x, y in zip(ac, bc)]
             return r
-        return _raw(fn(_F(a).v, _F(b).v))  # only ever used on detached values by the reference
+        a, b = _F(a), _F(b)
+        r = _raw(fn(a.v, b.v))
+        if _AD.enabled and (a.node is not None or b.node is not None):
+            pick_a = (r.v == a.v)
+            ps = []
+            if a.node is not None:
+                ps.append((a.node, pick_a.astype(F64)))
+            if b.node is not None:
+                ps.append((b.node, (~pick_a).astype(F64)))
+            r.node = _Node(ps)
+        return r
     return g
 
 
 minimum = _minmax(np.minimum)
 maximum = _minmax(np.maximum)
+
+
+def exp(a):
+    return _un(a, np.exp, lambda v: np.exp(v))
 
 
 def hmax(a):
@@ -1055,7 +1078,7 @@ def _make_drjit():
     m = types.ModuleType("drjit")
     m.__dict__.update(dict(
         ADMode=ADMode, width=width, select=select, rcp=rcp, sqr=sqr, minimum=minimum, maximum=maximum,
-        max=hmax, mean=mean, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
+        max=hmax, mean=mean, exp=exp, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
         zeros=zeros, empty=empty, full=full, arange=arange, gather=gather, resume_grad=resume_grad,
         suspend_grad=suspend_grad, backward_from=backward_from, enable_grad=enable_grad, grad=grad,
         set_grad=set_grad, enqueue=enqueue, traverse=traverse, CustomOp=CustomOp, custom=custom,
@@ -1275,6 +1298,10 @@ class Medium:
         pts, m, n = self._points(mei.p, _M(active).v)
         return self._lookup(1, pts, m, n)
 
+    def get_emission(self, mei, active=True):
+        """RGB emission grid (the session's second grid), trilinear, unscaled"""
+        return self.get_albedo(mei, active)
+
     def sample_interaction(self, ray, sample, channel, active=True):
         S = _S()
         n = max(width(ray), len(_F(sample)), len(_M(active)))
@@ -1330,6 +1357,16 @@ class Medium:
         mei.sigma_t = Color3f(sig, sig, sig)
         w = _raw(wt)
         return mei, Color3f(w, w, w)
+
+
+class MediumPtr(_Ptr):
+    """per-lane pointer to the scene's single medium (nerf.py:70-73)"""
+
+    def get_scattering_coefficients(self, mei, active=True):
+        return Medium().get_scattering_coefficients(mei, _M(active) & self.valid)
+
+    def get_emission(self, mei, active=True):
+        return Medium().get_emission(mei, _M(active) & self.valid)
 
 
 class Shape:
@@ -1577,7 +1614,7 @@ def _make_mitsuba():
         Ray3f=Ray3f, RayDifferential3f=Ray3f, Interaction3f=Interaction3f,
         SurfaceInteraction3f=SurfaceInteraction3f, MediumInteraction3f=MediumInteraction3f,
         DirectionSample3f=DirectionSample3f, PhaseFunctionContext=PhaseFunctionContext,
-        PhaseFunctionPtr=PhaseFunctionPtr, EmitterPtr=EmitterPtr, SensorPtr=SensorPtr, MediumPtr=_Ptr,
+        PhaseFunctionPtr=PhaseFunctionPtr, EmitterPtr=EmitterPtr, SensorPtr=SensorPtr, MediumPtr=MediumPtr,
         Properties=Properties, Loop=Loop, Scene=Scene, Sampler=Sampler, Integrator=Integrator,
         SamplingIntegrator=Integrator, Film=Film, Bitmap=_Bitmap, FilmFlags=_FilmFlags, TensorXf=Tensor,
         SceneParameters=dict, has_flag=lambda flags, f: bool(flags & f), is_spectral=False,
@@ -1617,8 +1654,8 @@ def load_reference(ref_root: str = REF_ROOT):
     sys.dont_write_bytecode = True  # /root/reference is read-only
     try:
         mods = {}
-        for name, rel in (("volpathsimple", "integrators/volpathsimple.py"), ("batched", "batched.py"),
-                          ("opt_config", "opt_config.py")):
+        for name, rel in (("volpathsimple", "integrators/volpathsimple.py"), ("nerf", "integrators/nerf.py"),
+                          ("batched", "batched.py"), ("opt_config", "opt_config.py")):
             spec = importlib.util.spec_from_file_location("refshim_ref_" + name, os.path.join(pydir, rel))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)

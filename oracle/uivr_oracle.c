@@ -160,6 +160,29 @@ void uivr_oracle_sincos2pi(const float* x, int n, float* s, float* c) {
     for (int i = 0; i < n; ++i) sincos2pi(x[i], &s[i], &c[i]);
 }
 
+/* exp(x): n = rint(x log2 e), r = x - n ln2 (two-part), degree-5 polynomial on r (Cephes expf
+ * coefficients), scaled by 2^n through the exponent bits.  x clamped to [-87, 88]. */
+static inline float exp_exact(float x) {
+    x = x < -87.0f ? -87.0f : (x > 88.0f ? 88.0f : x);
+    float n = rintf(x * 0x1.715476p+0f);
+    float r = FMA(n, -0x1.62e400p-1f, x);
+    r = FMA(n, -0x1.7f7d1cp-20f, r);
+    float q = 1.9875691500e-4f;
+    q = FMA(q, r, 1.3981999507e-3f);
+    q = FMA(q, r, 8.3334519073e-3f);
+    q = FMA(q, r, 4.1665795894e-2f);
+    q = FMA(q, r, 1.6666665459e-1f);
+    q = FMA(q, r, 5.0000001201e-1f);
+    float e = FMA(q, r * r, r) + 1.0f;
+    union { uint32_t u; float f; } sc;
+    sc.u = (uint32_t) ((int) n + 127) << 23;
+    return e * sc.f;
+}
+
+void uivr_oracle_exp(const float* x, int n, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = exp_exact(x[i]);
+}
+
 /* warp::square_to_uniform_sphere [UPSTREAM, SURVEY App. B.7] */
 static inline void uniform_sphere(float xi1, float xi2, float w[3]) {
     float z = FMA(-2.0f, xi2, 1.0f);
@@ -179,6 +202,7 @@ static inline void uniform_sphere(float xi1, float xi2, float w[3]) {
 typedef struct {
     const uivr_oracle_scene* sc;
     const uivr_oracle_batch* batch; /* ray-batch mode (batched.py), else NULL */
+    const uivr_oracle_nerf* nerf;   /* emission-absorption ray marching (nerf.py), else NULL; `albedo` = emission grid */
     const float* sigma_t;  /* (Z,Y,X)   */
     const float* albedo;   /* (Z,Y,X,3) */
     int32_t mres[3];
@@ -879,6 +903,81 @@ static void sample_from_camera(const ctx_t* C, counters_t* K, int adjoint, uint3
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* NeRFIntegrator.sample (python/integrators/nerf.py:47-147): emission-absorption ray      */
+/* marching, `queries_per_ray` forward-looking steps, one jitter draw per ray; the         */
+/* adjoint replays the steps with path replay and backpropagates per step (:117-124).      */
+/* ------------------------------------------------------------------------------------ */
+
+static void nerf_sample(const ctx_t* C, counters_t* K, int adjoint, uint32_t seed, uint32_t idx,
+                        uint32_t spp, const float dL[3], float R[3]) {
+    const uivr_oracle_scene* sc = C->sc;
+    const uivr_oracle_nerf* N = C->nerf;
+    rng_t rng;
+    sampler_seed(&rng, seed, idx);
+    seg_t seg;
+    int status;
+    if (C->batch) {
+        status = batch_segment(C, idx, spp, &seg);
+    } else {
+        float jx = rng_f(&rng), jy = rng_f(&rng);
+        status = camera_segment(C, idx / spp, jx, jy, &seg);
+    }
+    const int active = (status == 1), escaped = (status == 0); /* :69-77 */
+    float wsum = 0.0f, T = 1.0f;
+    if (active) {
+        if (!adjoint) K->c[UIVR_ORC_CAMERA_HITS]++;
+        const int Q = N->queries_per_ray;
+        /* :6-18 step_size_for_marching / query_t_for_step with mint = 0 */
+        const float step = N->jittering_enabled ? seg.tmax / (float) Q : seg.tmax / (float) (Q - 1);
+        const float jit = rng_f(&rng); /* :87, drawn even when jittering is off */
+        float t_a = 0.0f;
+        for (int j = 0; j < Q; ++j) {
+            const float sj = (float) (j + 1);
+            const float t_b = N->jittering_enabled ? step * (sj + jit) : step * sj;
+            const float dt = t_b - t_a;
+            float p[3], em[3];
+            seg_point(&seg, t_b, p);
+            const float raw = eval_sigma_t(C, K, p);                   /* :152-155 */
+            const float sigma = (N->activation == 1 && !(raw > 0.0f)) ? 0.0f : raw;
+            eval_albedo(C, K, p, em);                                  /* get_emission :160 */
+            const int last = !(j + 1 < Q);
+            const float a = last ? 1.0f : exp_exact(-(sigma * dt));    /* :103-105 */
+            const float weight = (1.0f - a) * T;
+            const float safe = a + 1e-10f;
+            for (int c = 0; c < 3; ++c) {
+                const float we = weight * em[c];
+                R[c] = adjoint ? R[c] - we : R[c] + we;                /* :109-112 */
+            }
+            if (adjoint && !last) {
+                /* :117-124  d/d emission_c = dL_c weight;
+                 * d/d sigma = sum_c dL_c (em_c dt a T - (R_c / safe) dt a) */
+                const float da = dt * a;
+                float gs = 0.0f, ge[3];
+                for (int c = 0; c < 3; ++c) {
+                    ge[c] = dL[c] * weight;
+                    const float inner = FMA(em[c], da * T, -((R[c] / safe) * da));
+                    gs = FMA(dL[c], inner, gs);
+                }
+                if (N->activation == 1 && !(raw > 0.0f)) gs = 0.0f;
+                scatter_sigma(C, K, p, gs);
+                scatter_albedo(C, K, p, ge);
+            }
+            t_a = t_b;
+            if (!last) { /* :114-120: masked by the updated still_walking */
+                T *= safe;
+                wsum += weight;
+            }
+        }
+    }
+    /* :134-143 composite with the background emitter (in both modes) */
+    int active_e = escaped || active;
+    if (N->hide_emitters) active_e = active_e && (wsum > 0.0f);
+    if (active_e)
+        for (int c = 0; c < 3; ++c) R[c] += (1.0f - wsum) * sc->radiance[c];
+    K->c[UIVR_ORC_RNG_DRAWS] += rng.draws;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Threaded entry points                                                                 */
 /* ------------------------------------------------------------------------------------ */
 
@@ -909,7 +1008,8 @@ static void* worker(void* arg) {
         for (uint32_t s = 0; s < J->spp; ++s) {
             uint32_t idx = pix * J->spp + s;
             float L[3] = {0, 0, 0};
-            sample_from_camera(J->C, &J->K, 0, J->seed, 0, idx, J->spp, NULL, L);
+            if (J->C->nerf) nerf_sample(J->C, &J->K, 0, J->seed, idx, J->spp, NULL, L);
+            else sample_from_camera(J->C, &J->K, 0, J->seed, 0, idx, J->spp, NULL, L);
             J->K.c[UIVR_ORC_SAMPLES]++;
             if (J->sample_L) memcpy(J->sample_L + 3 * (size_t) idx, L, sizeof(L));
             if (!J->backward) {
@@ -918,7 +1018,8 @@ static void* worker(void* arg) {
                 /* batched.py:272-306: box film => dL = grad_image[pixel] / spp */
                 float dL[3];
                 for (int c = 0; c < 3; ++c) dL[c] = J->grad_image[3 * (size_t) pix + c] * inv_spp;
-                sample_from_camera(J->C, &J->K, 1, J->seed, J->alt_seed, idx, J->spp, dL, L);
+                if (J->C->nerf) nerf_sample(J->C, &J->K, 1, J->seed, idx, J->spp, dL, L);
+                else sample_from_camera(J->C, &J->K, 1, J->seed, J->alt_seed, idx, J->spp, dL, L);
             }
         }
         if (!J->backward)
@@ -1064,6 +1165,51 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
     C.dalbedo = dalbedo_out;
     if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * (size_t) spp_grad);
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, NULL, nthreads, grad_image, NULL, sample_L_out, counters);
+    free(C.majorant);
+    return rc;
+}
+
+/* nerf entry points: the same drivers with C.nerf set; `emission` takes the albedo slot */
+int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                             const float* sigma_t, const float* emission, uint32_t seed, int32_t spp,
+                             const uivr_oracle_shard* shard, int nthreads, float* image_out,
+                             float* sample_L_out, uint64_t* counters) {
+    if (!scene || !nerf || nerf->queries_per_ray < 2 || !sigma_t || !emission || !image_out || spp < 1) return -1;
+    ctx_t C;
+    if (setup_ctx(&C, scene, sigma_t, emission)) return -1;
+    C.nerf = nerf;
+    size_t n = (size_t) scene->width * scene->height * 3;
+    double* acc = (double*) calloc(n, sizeof(double));
+    if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * n * (size_t) spp);
+    int rc = acc ? run(&C, 0, seed, (uint32_t) spp, shard, nthreads, NULL, acc, sample_L_out, counters) : -1;
+    if (!rc) {
+        float inv_spp = 1.0f / (float) spp;
+        for (size_t i = 0; i < n; ++i) image_out[i] = (float) acc[i] * inv_spp;
+    }
+    free(acc);
+    free(C.majorant);
+    return rc;
+}
+
+int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                              const float* sigma_t, const float* emission, const float* grad_image,
+                              uint32_t seed_grad, int32_t spp_grad, const uivr_oracle_shard* shard,
+                              int nthreads, double* dsigma_out, double* demission_out,
+                              float* sample_L_out, uint64_t* counters) {
+    if (!scene || !nerf || nerf->queries_per_ray < 2 || !sigma_t || !emission || !grad_image || !dsigma_out ||
+        !demission_out || spp_grad < 1)
+        return -1;
+    ctx_t C;
+    if (setup_ctx(&C, scene, sigma_t, emission)) return -1;
+    C.nerf = nerf;
+    size_t nvox = (size_t) scene->res[0] * scene->res[1] * scene->res[2];
+    memset(dsigma_out, 0, sizeof(double) * nvox);
+    memset(demission_out, 0, sizeof(double) * nvox * 3);
+    C.dsigma = dsigma_out;
+    C.dalbedo = demission_out;
+    if (sample_L_out)
+        memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * scene->height * (size_t) spp_grad);
+    int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, shard, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
     return rc;
 }

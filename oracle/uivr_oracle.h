@@ -65,6 +65,15 @@ typedef struct {
     uint32_t seed_pixels, seed_offsets;
 } uivr_oracle_batch;
 
+/* NeRFIntegrator properties (python/integrators/nerf.py:27-35; "next" row SURVEY 8f rank 4).
+ * density_noise_std is not restated: the reference flags it incorrect itself (nerf.py:157). */
+typedef struct {
+    int32_t queries_per_ray;    /* 128 */
+    int32_t jittering_enabled;  /* True */
+    int32_t activation;         /* 0 identity, 1 relu */
+    int32_t hide_emitters;
+} uivr_oracle_nerf;
+
 /* Pixel sharding: pixel p belongs to this call iff (p / shard_block) % shard_count == shard_rank. */
 typedef struct {
     int32_t shard_rank, shard_count, shard_block;
@@ -129,6 +138,19 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
                                       float* sample_L_out, uint64_t* counters);
 /* the (sensor, pixel x, pixel y) triple of batch element b (host-side check of the index sampler) */
 void uivr_oracle_batch_element(const uivr_oracle_batch* batch, uint32_t b, uint32_t out[3]);
+
+/* ---- nerf integrator (python/integrators/nerf.py): emission-absorption ray marching over the
+ * sigma_t grid and an RGB emission grid (Z,Y,X,3); same drivers, film and seeds as above ---- */
+int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                             const float* sigma_t, const float* emission, uint32_t seed, int32_t spp,
+                             const uivr_oracle_shard* shard, int nthreads, float* image_out,
+                             float* sample_L_out, uint64_t* counters);
+int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                              const float* sigma_t, const float* emission, const float* grad_image,
+                              uint32_t seed_grad, int32_t spp_grad, const uivr_oracle_shard* shard,
+                              int nthreads, double* dsigma_out, double* demission_out,
+                              float* sample_L_out, uint64_t* counters);
+void uivr_oracle_exp(const float* x, int n, float* out); /* the exact-op exp both sides use */
 
 /* ---- upstream primitives for oracle/refshim.py ----
  * refshim runs the reference's UNMODIFIED python/integrators/volpathsimple.py (and the drivers of

@@ -729,8 +729,9 @@ def test_cuda_ray_batch_matches_reference_vectors(uivr, dev):
               "m.albedo.data": _gpu(alb, dev).requires_grad_(True)}
     image, si, px = uivr.render_batch(b["batch_size"], scene, sensors, params, integ, seed=b["seed"],
                                       spp=b["spp"], spp_grad=b["spp_grad"])
-    assert np.array_equal(np.asarray(si.cpu()), g["sensor_idx"])
-    assert np.array_equal(np.asarray(px.cpu()), g["pixels"])
+    _np = lambda t: t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+    assert np.array_equal(_np(si), g["sensor_idx"])
+    assert np.array_equal(_np(px), g["pixels"])
     assert np.max(np.abs(image.detach().cpu().numpy() - g["image"])) < REFSHIM_SAMPLE_TOL
     image.backward(_gpu(RC.batch_loss_grad(g["image"]), dev))
     torch.cuda.synchronize()
