@@ -149,6 +149,29 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
                               const uivr_shard* shard, float* h_dsigma_t, float* h_dalbedo,
                               void* stream);
 
+/* ---- `nerf` integrator ("next" row): python/integrators/nerf.py ----
+ * NeRFIntegrator(props) (nerf.py:27-35, registered at :168, registry entry opt_config.py:162-169):
+ * emission-absorption ray marching, `queries_per_ray` forward-looking steps per ray with one jitter
+ * draw, over the sigma_t grid of uivr_update_medium and an RGB emission grid d_emission [Z,Y,X,3]
+ * (medium.get_emission).  Same film, seeds, shards and ray-batch mode as the calls above;
+ * uivr_set_integrator is not needed.  `density_noise_std` is not offered: the reference marks it
+ * incorrect (nerf.py:157). */
+enum { UIVR_NERF_IDENTITY = 0, UIVR_NERF_RELU = 1 };  /* 'activation' (nerf.py:38-45) */
+typedef struct {
+    int32_t queries_per_ray;    /* 128 */
+    int32_t jittering_enabled;  /* True */
+    int32_t activation;         /* UIVR_NERF_IDENTITY */
+    int32_t hide_emitters;      /* False */
+} uivr_nerf_props;
+/* NeRFIntegrator.sample(Primal) under mi.render: image[H,W,3] (nerf.py:47-147) */
+int uivr_nerf_forward(uivr_ctx* ctx, const uivr_nerf_props* props, const float* d_emission, uint32_t seed,
+                      int32_t spp, const uivr_shard* shard, float* d_image, float* d_sample_L, void* stream);
+/* dr.backward(loss): primal replay at seed_grad + sample(Backward) (nerf.py:109-124).
+ * d_dsigma_t [Z,Y,X] and d_demission [Z,Y,X,3] are OVERWRITTEN. */
+int uivr_nerf_backward(uivr_ctx* ctx, const uivr_nerf_props* props, const float* d_emission,
+                       const float* d_grad_image, uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard,
+                       float* d_dsigma_t, float* d_demission, float* d_sample_L, void* stream);
+
 /* ---- optimisation step ("next" row after the path itself) ----
  * opt.step() of mi.ad.Adam (python/opt_config.py:46-48, python/optimize.py:352) fused with
  * enforce_valid_params (python/optimize.py:169-179, :353): for every element
@@ -191,6 +214,7 @@ int uivr_set_variant(uivr_ctx* ctx, int variant);
 /* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */
 /* out[0:n] = -ln(1-u);  s,c = sin/cos(2 pi x);  sampler floats of stream (seed, idx) */
 int uivr_test_neg_log1m(uivr_ctx* ctx, const float* d_u, int n, float* d_out, void* stream);
+int uivr_test_exp(uivr_ctx* ctx, const float* d_x, int n, float* d_out, void* stream); /* exp(x), nerf.py:104 */
 int uivr_test_sincos2pi(uivr_ctx* ctx, const float* d_x, int n, float* d_s, float* d_c, void* stream);
 int uivr_test_sampler(uivr_ctx* ctx, uint32_t seed, uint32_t idx0, int nstreams, int ndraws,
                       float* d_out, void* stream);

@@ -1,8 +1,9 @@
 """ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- not the product).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  PARITY UNPINNED at the upstream (Mitsuba 3 / Dr.Jit) boundary: see
-oracle/uivr_oracle.h.
+import this module.  Pinned against the reference's own Python files through oracle/refshim.py
+(tests/golden/refshim_*.npz); PARITY UNPINNED only for the arithmetic inside the un-vendored
+Mitsuba 3 branch: see oracle/uivr_oracle.h.
 """
 from __future__ import annotations
 
@@ -331,17 +332,30 @@ def make_nerf(props: Dict) -> _Nerf:
     return n
 
 
+def _nerf_batch(desc, batch, seed, i_offsets):
+    """batch = (sensors16, film_size, batch_size, seed of render_batch) or None"""
+    if batch is None:
+        return desc, None, None
+    sensors16, film_size, batch_size, bseed = batch
+    d = dict(desc)
+    d["width"], d["height"] = int(batch_size), 1
+    b, keep = _make_batch(sensors16, film_size, tea(bseed, 5)[0], tea(bseed, i_offsets)[0])
+    return d, b, keep
+
+
 def nerf_forward(desc, props, sigma_t, emission, seed: int, spp: int, shard=None,
-                 nthreads: Optional[int] = None, want_samples: bool = False):
-    """-> (image (H,W,3) f32, per-sample L (S,3) or None, counters dict)."""
+                 nthreads: Optional[int] = None, want_samples: bool = False, batch=None):
+    """-> (image (H,W,3) [or (B,3) in ray-batch mode] f32, per-sample L (S,3) or None, counters dict)."""
+    sigma_t, emission = _check_grids(desc, sigma_t, emission)
+    desc, b, keep = _nerf_batch(desc, batch, seed, 22)
     sc = make_scene(desc, dict(max_depth=0))
     nf = make_nerf(props)
-    sigma_t, emission = _check_grids(desc, sigma_t, emission)
     h, w = sc.height, sc.width
-    image = np.zeros((h, w, 3), dtype=np.float32)
+    image = np.zeros((h, w, 3) if batch is None else (w, 3), dtype=np.float32)
     samples = np.zeros((h * w * spp, 3), dtype=np.float32) if want_samples else None
     counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
-    rc = lib().uivr_oracle_nerf_forward(C.byref(sc), C.byref(nf), _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
+    rc = lib().uivr_oracle_nerf_forward(C.byref(sc), C.byref(nf), None if b is None else C.byref(b),
+                                        _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
                                         C.c_uint32(seed & 0xFFFFFFFF), C.c_int32(spp), _shard(shard),
                                         C.c_int(nthreads or os.cpu_count() or 1), _ptr(image, C.c_float),
                                         _ptr(samples, C.c_float), _ptr(counters, C.c_uint64))
@@ -351,19 +365,21 @@ def nerf_forward(desc, props, sigma_t, emission, seed: int, spp: int, shard=None
 
 
 def nerf_backward(desc, props, sigma_t, emission, grad_image, seed_grad: int, spp_grad: int, shard=None,
-                  nthreads: Optional[int] = None, want_samples: bool = False):
+                  nthreads: Optional[int] = None, want_samples: bool = False, batch=None):
     """-> (d sigma_t (Z,Y,X,1) f64, d emission (Z,Y,X,3) f64, per-sample primal L or None, counters)."""
-    sc = make_scene(desc, dict(max_depth=0))
-    nf = make_nerf(props)
     sigma_t, emission = _check_grids(desc, sigma_t, emission)
     x, y, z = desc["res"]
+    desc, b, keep = _nerf_batch(desc, batch, seed_grad, 39)
+    sc = make_scene(desc, dict(max_depth=0))
+    nf = make_nerf(props)
     h, w = sc.height, sc.width
     grad_image = _f32(grad_image).reshape(h, w, 3)
     dsig = np.zeros((z, y, x, 1), dtype=np.float64)
     dem = np.zeros((z, y, x, 3), dtype=np.float64)
     samples = np.zeros((h * w * spp_grad, 3), dtype=np.float32) if want_samples else None
     counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
-    rc = lib().uivr_oracle_nerf_backward(C.byref(sc), C.byref(nf), _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
+    rc = lib().uivr_oracle_nerf_backward(C.byref(sc), C.byref(nf), None if b is None else C.byref(b),
+                                         _ptr(sigma_t, C.c_float), _ptr(emission, C.c_float),
                                          _ptr(grad_image, C.c_float), C.c_uint32(seed_grad & 0xFFFFFFFF),
                                          C.c_int32(spp_grad), _shard(shard), C.c_int(nthreads or os.cpu_count() or 1),
                                          _ptr(dsig, C.c_double), _ptr(dem, C.c_double), _ptr(samples, C.c_float),

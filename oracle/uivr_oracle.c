@@ -1171,13 +1171,16 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
 
 /* nerf entry points: the same drivers with C.nerf set; `emission` takes the albedo slot */
 int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                             const uivr_oracle_batch* batch,
                              const float* sigma_t, const float* emission, uint32_t seed, int32_t spp,
                              const uivr_oracle_shard* shard, int nthreads, float* image_out,
                              float* sample_L_out, uint64_t* counters) {
     if (!scene || !nerf || nerf->queries_per_ray < 2 || !sigma_t || !emission || !image_out || spp < 1) return -1;
+    if (batch && (!batch->sensors || batch->n_sensors < 1 || scene->height != 1)) return -1;
     ctx_t C;
     if (setup_ctx(&C, scene, sigma_t, emission)) return -1;
     C.nerf = nerf;
+    C.batch = batch;
     size_t n = (size_t) scene->width * scene->height * 3;
     double* acc = (double*) calloc(n, sizeof(double));
     if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * n * (size_t) spp);
@@ -1192,6 +1195,7 @@ int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_n
 }
 
 int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                              const uivr_oracle_batch* batch,
                               const float* sigma_t, const float* emission, const float* grad_image,
                               uint32_t seed_grad, int32_t spp_grad, const uivr_oracle_shard* shard,
                               int nthreads, double* dsigma_out, double* demission_out,
@@ -1199,9 +1203,11 @@ int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_
     if (!scene || !nerf || nerf->queries_per_ray < 2 || !sigma_t || !emission || !grad_image || !dsigma_out ||
         !demission_out || spp_grad < 1)
         return -1;
+    if (batch && (!batch->sensors || batch->n_sensors < 1 || scene->height != 1)) return -1;
     ctx_t C;
     if (setup_ctx(&C, scene, sigma_t, emission)) return -1;
     C.nerf = nerf;
+    C.batch = batch;
     size_t nvox = (size_t) scene->res[0] * scene->res[1] * scene->res[2];
     memset(dsigma_out, 0, sizeof(double) * nvox);
     memset(demission_out, 0, sizeof(double) * nvox * 3);

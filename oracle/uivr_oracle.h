@@ -5,15 +5,19 @@
  * the `volpathsimple` integrator (python/integrators/volpathsimple.py) driven the way
  * RBIntegrator.render / render_backward drive it (restated in python/batched.py:134-326).
  *
- * PARITY UNPINNED at the third-party boundary: the arithmetic of the path (Medium::
- * sample_interaction, GridVolume lookup, PCG32 sampler, perspective sensor ...) lives in an
- * un-vendored, un-pinned Mitsuba 3 branch + Dr.Jit (README.md:97-104) which cannot be
- * imported or built here, and the reference's own tests hold no golden vectors for this
- * path (tests/test_integrators.py:343-347 is disabled).  This oracle therefore follows the
- * reference's control flow line by line (citations at each function) and DEFINES the
- * upstream arithmetic itself (DESIGN.md "Arithmetic contract").  It is pinned by:
- * PCG32 public known-answer vectors, analytic known answers (KA1-KA3) and finite
- * differences (KA4, the reference's own methodology, python/fd.py) -- see tests/.
+ * How it is pinned: the reference cannot be installed here (un-vendored, un-pinned Mitsuba 3
+ * branch + Dr.Jit, README.md:97-104) and its tests hold no golden vectors for this path
+ * (tests/test_integrators.py:343-347 is disabled), but its Python FILES can be imported:
+ * oracle/refshim.py runs volpathsimple.py / nerf.py / batched.py / opt_config.py unmodified on a
+ * numpy stand-in for the Mitsuba / Dr.Jit API and tests/golden/refshim_*.npz hold their outputs.
+ * Those vectors pin everything the reference's files decide (state machine, masks, RNG draw order,
+ * gradient formulae, film, sub-seeds); this file is tested against them to 1e-6.
+ * PARITY UNPINNED only for the arithmetic INSIDE the upstream Mitsuba branch (Medium::
+ * sample_interaction(_drt), GridVolume lookup, PCG32 stream assignment, perspective sensor ...):
+ * this oracle DEFINES it (DESIGN.md "Arithmetic contract") and the stand-in borrows it from the
+ * uivr_oracle_shim_* wrappers below.  Further pins: PCG32 public known-answer vectors, analytic
+ * known answers (KA1-KA3) and finite differences (KA4, the reference's own methodology,
+ * python/fd.py) -- see tests/.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (csrc/) never links or calls it.
@@ -142,10 +146,12 @@ void uivr_oracle_batch_element(const uivr_oracle_batch* batch, uint32_t b, uint3
 /* ---- nerf integrator (python/integrators/nerf.py): emission-absorption ray marching over the
  * sigma_t grid and an RGB emission grid (Z,Y,X,3); same drivers, film and seeds as above ---- */
 int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                             const uivr_oracle_batch* batch, /* NULL: the scene's sensor; else ray-batch mode */
                              const float* sigma_t, const float* emission, uint32_t seed, int32_t spp,
                              const uivr_oracle_shard* shard, int nthreads, float* image_out,
                              float* sample_L_out, uint64_t* counters);
 int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_nerf* nerf,
+                              const uivr_oracle_batch* batch,
                               const float* sigma_t, const float* emission, const float* grad_image,
                               uint32_t seed_grad, int32_t spp_grad, const uivr_oracle_shard* shard,
                               int nthreads, double* dsigma_out, double* demission_out,

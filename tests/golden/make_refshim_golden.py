@@ -59,8 +59,34 @@ def run_batch():
     return res
 
 
+def run_nerf():
+    c = RC.NERF
+    out = {}
+    for name, (props, offset) in c["runs"].items():
+        sig, em, vol = RC.nerf_inputs(offset)
+        desc = vol.as_dict()
+        integ = R.make_integrator("nerf", max_depth=4, **props)  # opt_config.py:162-169 registry entry
+        img, samples = R.render_forward(desc, integ, sig, em, c["seed"], c["spp"])
+        gimg = loss_grad(img)
+        ds, de, samples_g = R.render_backward(desc, integ, sig, em, gimg, c["seed_grad"], c["spp"])
+        out.update({f"{name}/image": img, f"{name}/samples": samples, f"{name}/grad_image": gimg,
+                    f"{name}/samples_grad_pass": samples_g, f"{name}/dsigma": ds, f"{name}/demission": de})
+    # the same integrator under python/batched.py render_batch
+    b = c["batch"]
+    sig, em, vol = RC.nerf_inputs()
+    tab = RC.batch_inputs()[3]
+    integ = R.make_integrator("nerf", max_depth=4, **b["props"])
+    res = R.render_batch(vol.as_dict(), integ, sig, em, tab, b["film"], b["batch_size"], b["seed"], b["spp"],
+                         spp_grad=b["spp_grad"], grad_image_fn=RC.batch_loss_grad)
+    out.update({"batch/image": res["image"], "batch/dsigma": res["dsigma"], "batch/demission": res["dalbedo"],
+                "batch/sensors": tab})
+    return out
+
+
 def main():
     O.build()
+    np.savez_compressed(os.path.join(HERE, "refshim_nerf.npz"), **run_nerf())
+    print("nerf written")
     for name in RC.CASES:
         np.savez_compressed(os.path.join(HERE, f"refshim_{name}.npz"), **run_case(name))
         print(name, "written")

@@ -44,6 +44,25 @@ BATCH = dict(n=12, scale=6.0, factor=4, film=(16, 12), n_sensors=5, batch_size=6
              seed=4321, integrator="volpathsimple-drt", max_depth=16)
 
 
+# nerf integrator (python/integrators/nerf.py): name -> (properties, offset added to the sigma_t grid;
+# a negative offset gives negative raw densities, which is what `activation` is about)
+NERF = dict(n=12, w=16, h=12, spp=4, scale=6.0, seed=5, seed_grad=9,
+            runs={"default32": (dict(queries_per_ray=32), 0.0),
+                  "nojitter17": (dict(queries_per_ray=17, jittering_enabled=False), 0.0),
+                  "relu32": (dict(queries_per_ray=32, activation="relu"), -0.1),
+                  "identity-negative": (dict(queries_per_ray=32), -0.1),
+                  "hide128": (dict(queries_per_ray=128, hide_emitters=True), 0.0)},
+            batch=dict(props=dict(queries_per_ray=24), film=(16, 12), n_sensors=5, batch_size=64, spp=8, spp_grad=4,
+                       seed=4321))
+
+
+def nerf_inputs(offset=0.0):
+    c = NERF
+    sig, em = hetero_grids(c["n"], seed=c["n"])
+    vol = u.cube_test_scene(c["w"], c["h"], density_scale=c["scale"], res=(c["n"],) * 3)
+    return (sig + np.float32(offset)).astype(np.float32), em, vol
+
+
 def case_inputs(name):
     c = CASES[name]
     if name == "cube3":

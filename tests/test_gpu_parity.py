@@ -737,3 +737,136 @@ def test_cuda_ray_batch_matches_reference_vectors(uivr, dev):
     torch.cuda.synchronize()
     assert rel_linf(params["m.sigma_t.data"].grad.cpu().numpy(), g["dsigma"]) < REFSHIM_GRAD_TOL
     assert rel_linf(params["m.albedo.data"].grad.cpu().numpy(), g["dalbedo"]) < REFSHIM_GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------
+# nerf integrator (python/integrators/nerf.py)
+# ---------------------------------------------------------------------------------------
+
+def test_exp_bit_exact(uivr, oracle, dev):
+    ctx = uivr._native.Context(0)
+    x = np.concatenate([np.linspace(-90.0, 89.0, 200001), -np.random.default_rng(0).random(1 << 18) * 10.0,
+                        [0.0, -0.0, 1e-30, -1e-30]]).astype(np.float32)
+    dx = _gpu(x, dev)
+    out = torch.empty_like(dx)
+    ctx.test_exp(dx.data_ptr(), x.size, out.data_ptr())
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), oracle.exp_exact(x).view(np.uint32))
+
+
+def _nerf_scene(uivr, n, w, h, scale, seed):
+    sig, em = hetero_grids(n, seed=seed)
+    vol = uivr.benchmark_scene(n, w, h, scale=scale, majorant_resolution_factor=0)
+    return sig, em, vol
+
+
+@pytest.mark.parametrize("props,offset,spp", [(dict(queries_per_ray=128), 0.0, 8),
+                                              (dict(queries_per_ray=33, jittering_enabled=False), 0.0, 5),
+                                              (dict(queries_per_ray=64, activation="relu", hide_emitters=True), -0.1, 32),
+                                              (dict(queries_per_ray=2), -0.1, 3)])
+def test_nerf_matches_oracle(uivr, oracle, dev, props, offset, spp):
+    """k_nerf_forward / k_nerf_backward through the plugin mirror vs the oracle: per-sample radiance
+    and event counters bit-exact, gradients to atomic summation order."""
+    n = 24
+    sig, em, vol = _nerf_scene(uivr, n, 48, 40, 8.0, n)
+    sig = (sig + np.float32(offset)).astype(np.float32)
+    desc = vol.as_dict()
+    img_o, smp_o, cnt_o = oracle.nerf_forward(desc, props, sig, em, 1234, spp, want_samples=True)
+    scene = uivr.Scene(vol, device=0)
+    scene.ctx.set_counting(True)
+    integ = uivr.get_int_config("nerf").create(max_depth=4, **props)
+    params = {"m.sigma_t.data": _gpu(sig, dev), "m.emission.data": _gpu(em, dev)}
+    S = desc["width"] * desc["height"] * spp
+    smp = torch.zeros((S, 3), device=dev)
+    scene.ctx.reset_counters()
+    img = integ.render(scene, params, seed=1234, spp=spp, sample_out=smp)
+    torch.cuda.synchronize()
+    assert np.array_equal(smp.cpu().numpy().view(np.uint32), smp_o.view(np.uint32))
+    assert scene.ctx.get_counters() == cnt_o
+    assert np.max(np.abs(img.cpu().numpy() - img_o)) < IMAGE_TOL
+    gimg = loss_grad(img_o)
+    sg = uivr.tea32(1234, 1)
+    ds_o, de_o, smp_bo, cnt_bo = oracle.nerf_backward(desc, props, sig, em, gimg, sg, spp, want_samples=True)
+    smp_b = torch.zeros((S, 3), device=dev)
+    scene.ctx.reset_counters()
+    ds, de = integ.render_backward(scene, params, _gpu(gimg, dev), seed=sg, spp=spp, sample_out=smp_b)
+    torch.cuda.synchronize()
+    assert np.array_equal(smp_b.cpu().numpy().view(np.uint32), smp_bo.view(np.uint32))
+    assert scene.ctx.get_counters() == cnt_bo
+    assert rel_linf(ds.cpu().numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(de.cpu().numpy(), de_o) < GRAD_TOL
+
+
+def test_nerf_autograd_sharding_and_batch(uivr, oracle, dev):
+    """uivr.render(...) with a nerf integrator (mi.render + dr.backward), pixel shards, and the
+    C-ABI in ray-batch mode."""
+    n, spp = 16, 4
+    sig, em, vol = _nerf_scene(uivr, n, 32, 24, 6.0, 5)
+    desc = vol.as_dict()
+    props = dict(queries_per_ray=40)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.NeRFIntegrator(props)
+    params = {"m.sigma_t.data": _gpu(sig, dev).requires_grad_(True), "m.emission.data": _gpu(em, dev).requires_grad_(True)}
+    image = uivr.render(scene, params, integ, spp=spp, seed=77)
+    img_o, _, _ = oracle.nerf_forward(desc, props, sig, em, 77, spp)
+    assert np.max(np.abs(image.detach().cpu().numpy() - img_o)) < IMAGE_TOL
+    ((image - 0.5) ** 2).mean().backward()
+    torch.cuda.synchronize()
+    ds_o, de_o, _, _ = oracle.nerf_backward(desc, props, sig, em, loss_grad(img_o), uivr.tea32(77, 1), spp)
+    assert rel_linf(params["m.sigma_t.data"].grad.cpu().numpy(), ds_o) < GRAD_TOL
+    assert rel_linf(params["m.emission.data"].grad.cpu().numpy(), de_o) < GRAD_TOL
+    # shards partition the image and the gradient
+    p = {k: v.detach() for k, v in params.items()}
+    parts = [integ.render(scene, p, seed=77, spp=spp, shard=(r, 3, 1)).cpu().numpy() for r in range(3)]
+    assert np.max(np.abs(sum(parts) - img_o)) < IMAGE_TOL
+    g = _gpu(loss_grad(img_o), dev)
+    dsum = sum(integ.render_backward(scene, p, g, seed=5, spp=spp, shard=(r, 3, 1))[0].cpu().numpy().astype(np.float64)
+               for r in range(3))
+    ds_5, _, _, _ = oracle.nerf_backward(desc, props, sig, em, loss_grad(img_o), 5, spp)
+    assert rel_linf(dsum, ds_5) < GRAD_TOL
+    # ray-batch mode through the C-ABI
+    sensors = uivr.circle_sensors(4, 20, 14)
+    tab = uivr.sensor_table(sensors)
+    B, bseed = 300, 2024
+    batch = (tab, (20, 14), B, bseed)
+    img_bo, smp_bo, _ = oracle.nerf_forward(desc, props, sig, em, bseed, spp, batch=batch, want_samples=True)
+    scene.ctx.set_batch(tab, 20, 14, B, bseed)
+    try:
+        img_b = torch.empty((B, 3), device=dev)
+        smp_b = torch.zeros((B * spp, 3), device=dev)
+        np_props = integ.props()
+        scene.ctx.nerf_forward(np_props, p["m.emission.data"].data_ptr(), bseed, spp, img_b.data_ptr(), smp_b.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(smp_b.cpu().numpy().view(np.uint32), smp_bo.view(np.uint32))
+        assert np.max(np.abs(img_b.cpu().numpy() - img_bo)) < IMAGE_TOL
+        gb = (2.0 * (img_bo.astype(np.float64) - 0.5) / img_bo.size).astype(np.float32)
+        sg = uivr.tea32(bseed, 1)
+        ds_bo, de_bo, _, _ = oracle.nerf_backward(desc, props, sig, em, gb, sg, spp, batch=batch)
+        ds_b, de_b = torch.empty_like(p["m.sigma_t.data"]), torch.empty_like(p["m.emission.data"])
+        scene.ctx.nerf_backward(np_props, p["m.emission.data"].data_ptr(), _gpu(gb, dev).data_ptr(), sg, spp,
+                                ds_b.data_ptr(), de_b.data_ptr())
+        torch.cuda.synchronize()
+        assert rel_linf(ds_b.cpu().numpy(), ds_bo) < GRAD_TOL
+        assert rel_linf(de_b.cpu().numpy(), de_bo) < GRAD_TOL
+    finally:
+        scene.ctx.set_batch(None)
+
+
+def test_nerf_matches_reference_vectors(uivr, dev):
+    """CUDA nerf path vs the vectors python/integrators/nerf.py itself produced (refshim)."""
+    import os
+    RC, gdir = _refshim_cases()
+    c = RC.NERF
+    g = np.load(os.path.join(gdir, "refshim_nerf.npz"))
+    for run, (props, offset) in c["runs"].items():
+        sig, em, vol = RC.nerf_inputs(offset)
+        scene = uivr.Scene(vol, device=0)
+        integ = uivr.get_int_config("nerf").create(max_depth=4, **props)
+        params = {"m.sigma_t.data": _gpu(sig, dev), "m.emission.data": _gpu(em, dev)}
+        S = c["w"] * c["h"] * c["spp"]
+        smp = torch.zeros((S, 3), device=dev)
+        img = integ.render(scene, params, seed=c["seed"], spp=c["spp"], sample_out=smp)
+        assert np.max(np.abs(smp.cpu().numpy() - g[f"{run}/samples"])) < REFSHIM_SAMPLE_TOL, run
+        assert np.max(np.abs(img.cpu().numpy() - g[f"{run}/image"])) < REFSHIM_SAMPLE_TOL, run
+        ds, de = integ.render_backward(scene, params, _gpu(g[f"{run}/grad_image"], dev), seed=c["seed_grad"], spp=c["spp"])
+        assert rel_linf(ds.cpu().numpy(), g[f"{run}/dsigma"]) < REFSHIM_GRAD_TOL, run
+        assert rel_linf(de.cpu().numpy(), g[f"{run}/demission"]) < REFSHIM_GRAD_TOL, run

@@ -82,8 +82,17 @@ def test_integrator_config_create(uivr):
     assert integ.hide_emitters is False and integ.aovs() == []
     basic = uivr.get_int_config("volpathsimple-basic").create(max_depth=3)
     assert basic.use_drt is False
+    nerf = uivr.get_int_config("nerf").create(max_depth=3)   # opt_config.py:162-169, nerf.py:27-35
+    assert isinstance(nerf, uivr.NeRFIntegrator)
+    assert (nerf.queries_per_ray, nerf.jittering_enabled, nerf.activation_type, nerf.hide_emitters) == \
+        (128, True, "identity", False)
+    assert nerf.rr_depth == 1003 and nerf.aovs() == []
+    with pytest.raises(ValueError, match="Unsupported activation"):
+        uivr.NeRFIntegrator({"activation": "softplus"}).props()          # nerf.py:44
     with pytest.raises(NotImplementedError):
-        uivr.get_int_config("nerf").create(max_depth=3)      # outside the hot path
+        uivr.NeRFIntegrator({"density_noise_std": 0.1})                   # nerf.py:157
+    with pytest.raises(NotImplementedError):
+        uivr.load_dict({"type": "path"})
     # cfg objects handed out are copies (get_int_config deep-copies)
     cfg.params["use_drt"] = False
     assert uivr.get_int_config("volpathsimple-drt").params["use_drt"] is True

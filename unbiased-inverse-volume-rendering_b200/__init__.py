@@ -2,7 +2,7 @@
 integrator-plugin surface (hot path of rgl-epfl/unbiased-inverse-volume-rendering)."""
 from . import _native
 from ._native import NativeError, tea32
-from .integrator import (INTEGRATORS, Scene, VolpathSimpleIntegrator, load_dict,
+from .integrator import (INTEGRATORS, NeRFIntegrator, Scene, VolpathSimpleIntegrator, load_dict,
                          register_integrator, render)
 from .opt_config import IntegratorConfig, add_int_config, get_int_config
 from .batched import gather_ref_values, render_batch, sample_batch_pixels, sensor_table
@@ -13,7 +13,7 @@ from .scene import (Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_t
                     cube_test_scene, look_at, synthetic_grids)
 
 __all__ = [
-    "NativeError", "tea32", "INTEGRATORS", "Scene", "VolpathSimpleIntegrator", "load_dict",
+    "NativeError", "tea32", "INTEGRATORS", "NeRFIntegrator", "Scene", "VolpathSimpleIntegrator", "load_dict",
     "register_integrator", "render", "IntegratorConfig", "add_int_config", "get_int_config",
     "Sensor", "VolumeScene", "benchmark_scene", "circle_sensors", "cube_test_grids",
     "cube_test_scene", "look_at", "synthetic_grids",

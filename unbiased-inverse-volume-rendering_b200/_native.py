@@ -27,6 +27,7 @@ EXPORTS = [
     "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
+    "uivr_nerf_forward", "uivr_nerf_backward", "uivr_test_exp",
 ]
 
 
@@ -53,6 +54,11 @@ class IntegratorProps(C.Structure):
 class BatchDesc(C.Structure):
     _fields_ = [("n_sensors", C.c_int32), ("sensors", C.POINTER(C.c_float)), ("film_w", C.c_int32),
                 ("film_h", C.c_int32), ("batch_size", C.c_int32), ("seed", C.c_uint32)]
+
+
+class NerfProps(C.Structure):
+    _fields_ = [("queries_per_ray", C.c_int32), ("jittering_enabled", C.c_int32), ("activation", C.c_int32),
+                ("hide_emitters", C.c_int32)]
 
 
 class Shard(C.Structure):
@@ -111,6 +117,9 @@ def lib():
         "uivr_tea32": ([u32, u32], u32),
         "uivr_alt_seed": ([u32], u32),
         "uivr_alt_seed_batch": ([u32], u32),
+        "uivr_nerf_forward": ([vp, C.POINTER(NerfProps), fp, u32, i32, C.POINTER(Shard), fp, fp, vp], C.c_int),
+        "uivr_nerf_backward": ([vp, C.POINTER(NerfProps), fp, fp, u32, i32, C.POINTER(Shard), fp, fp, fp, vp], C.c_int),
+        "uivr_test_exp": ([vp, fp, C.c_int, fp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)
@@ -231,6 +240,25 @@ class Context:
                                                       self._shard(shard), dsigma_ptr, dalbedo_ptr, stream),
                     "uivr_render_backward_host")
 
+    @staticmethod
+    def _nerf(props: dict):
+        p = NerfProps()
+        p.queries_per_ray = int(props.get("queries_per_ray", 128))
+        p.jittering_enabled = int(bool(props.get("jittering_enabled", True)))
+        p.activation = {"identity": 0, "relu": 1}[str(props.get("activation", "identity")).lower()]
+        p.hide_emitters = int(bool(props.get("hide_emitters", False)))
+        return C.byref(p)
+
+    def nerf_forward(self, props, emission_ptr, seed, spp, image_ptr, sample_ptr=None, shard=None, stream=0):
+        self._check(self._L.uivr_nerf_forward(self._h, self._nerf(props), emission_ptr, seed & 0xFFFFFFFF, int(spp),
+                                              self._shard(shard), image_ptr, sample_ptr, stream), "uivr_nerf_forward")
+
+    def nerf_backward(self, props, emission_ptr, grad_image_ptr, seed_grad, spp_grad, dsigma_ptr, demission_ptr,
+                      sample_ptr=None, shard=None, stream=0):
+        self._check(self._L.uivr_nerf_backward(self._h, self._nerf(props), emission_ptr, grad_image_ptr,
+                                               seed_grad & 0xFFFFFFFF, int(spp_grad), self._shard(shard), dsigma_ptr,
+                                               demission_ptr, sample_ptr, stream), "uivr_nerf_backward")
+
     def adam_step(self, param_ptr, grad_ptr, m_ptr, v_ptr, n, lr, beta1, beta2, eps, t, lo, hi, stream=0):
         self._check(self._L.uivr_adam_step(self._h, param_ptr, grad_ptr, m_ptr, v_ptr, int(n), float(lr), float(beta1),
                                            float(beta2), float(eps), int(t), float(lo), float(hi), stream),
@@ -268,6 +296,9 @@ class Context:
     # -- primitive tests --
     def test_neg_log1m(self, u_ptr, n, out_ptr, stream=0):
         self._check(self._L.uivr_test_neg_log1m(self._h, u_ptr, n, out_ptr, stream), "uivr_test_neg_log1m")
+
+    def test_exp(self, x_ptr, n, out_ptr, stream=0):
+        self._check(self._L.uivr_test_exp(self._h, x_ptr, n, out_ptr, stream), "uivr_test_exp")
 
     def test_sincos2pi(self, x_ptr, n, s_ptr, c_ptr, stream=0):
         self._check(self._L.uivr_test_sincos2pi(self._h, x_ptr, n, s_ptr, c_ptr, stream), "uivr_test_sincos2pi")

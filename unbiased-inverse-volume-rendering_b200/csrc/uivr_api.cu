@@ -11,6 +11,7 @@
 #include "uivr_kernels.cuh"
 #include "uivr_mega.cuh"
 #include "uivr_pool.cuh"
+#include "uivr_nerf.cuh"
 
 using namespace uivr;
 
@@ -499,6 +500,103 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
     ctx->ev_valid[1] = true;
     ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// `nerf` integrator (python/integrators/nerf.py)
+// ---------------------------------------------------------------------------------------
+static int nerf_params(uivr_ctx* ctx, const uivr_nerf_props* np, Params& P, const uivr_shard* shard, uint32_t seed,
+                       int32_t spp) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, UIVR_ERR_STATE, "uivr_set_scene has not been called");
+    if (!ctx->have_medium) return fail(ctx, UIVR_ERR_STATE, "uivr_update_medium has not been called");
+    if (!np) return fail(ctx, UIVR_ERR_INVALID, "null nerf properties");
+    if (np->queries_per_ray < 2) return fail(ctx, UIVR_ERR_INVALID, "queries_per_ray must be >= 2");
+    if (np->activation != UIVR_NERF_IDENTITY && np->activation != UIVR_NERF_RELU)
+        return fail(ctx, UIVR_ERR_INVALID, "Unsupported activation (nerf.py:44)");
+    const int rc = fill_params(ctx, P, shard, seed, spp);
+    if (rc) return rc;
+    P.nerf_queries = np->queries_per_ray;
+    P.nerf_jitter = np->jittering_enabled ? 1 : 0;
+    P.nerf_activation = np->activation;
+    P.hide_emitters = np->hide_emitters ? 1 : 0;
+    return UIVR_OK;
+}
+
+int uivr_nerf_forward(uivr_ctx* ctx, const uivr_nerf_props* props, const float* d_emission, uint32_t seed, int32_t spp,
+                      const uivr_shard* shard, float* d_image, float* d_sample_L, void* stream) {
+    Params P;
+    int rc = nerf_params(ctx, props, P, shard, seed, spp);
+    if (rc) return rc;
+    if (!d_emission || !d_image) return fail(ctx, UIVR_ERR_INVALID, "null device pointer");
+    if (ctx->batch_on && seed != ctx->batch.seed)
+        return fail(ctx, UIVR_ERR_INVALID, "ray-batch mode: the forward seed must be the seed of uivr_set_batch");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    P.albedo = d_emission;
+    P.image = d_image;
+    P.sample_L = d_sample_L;
+    const size_t nimg = (size_t) P.npix * 3;
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_image, 0, nimg * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
+    int grid = 0;
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
+    if (ctx->counting) {
+        if ((rc = persistent_grid(ctx, k_nerf_forward<true>, kBlock, &grid))) return rc;
+        k_nerf_forward<true><<<grid, kBlock, 0, st>>>(P);
+    } else {
+        if ((rc = persistent_grid(ctx, k_nerf_forward<false>, kBlock, &grid))) return rc;
+        k_nerf_forward<false><<<grid, kBlock, 0, st>>>(P);
+    }
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
+    ctx->ev_valid[0] = true;
+    k_scale<<<ctx->num_sms * 4, kBlock, 0, st>>>(d_image, nimg, P.inv_spp);
+    ctx->launches += 2;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_nerf_backward(uivr_ctx* ctx, const uivr_nerf_props* props, const float* d_emission, const float* d_grad_image,
+                       uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard, float* d_dsigma_t,
+                       float* d_demission, float* d_sample_L, void* stream) {
+    Params P;
+    int rc = nerf_params(ctx, props, P, shard, seed_grad, spp_grad);
+    if (rc) return rc;
+    if (!d_emission || !d_grad_image || !d_dsigma_t || !d_demission) return fail(ctx, UIVR_ERR_INVALID, "null device pointer");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t) stream;
+    if (ctx->batch_on) P.seed_offsets = uivr_tea32(ctx->batch.seed, 39);  // decorrelated offsets (batched.py:69-75)
+    P.albedo = d_emission;
+    P.grad_image = d_grad_image;
+    P.dsigma = d_dsigma_t;
+    P.dalbedo = d_demission;
+    P.sample_L = d_sample_L;
+    const size_t vox = (size_t) P.res[0] * P.res[1] * P.res[2];
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_dsigma_t, 0, vox * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(d_demission, 0, vox * 3 * sizeof(float), st));
+    UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
+    int grid = 0;
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
+    if (ctx->counting) {
+        if ((rc = persistent_grid(ctx, k_nerf_backward<true>, kBlock, &grid))) return rc;
+        k_nerf_backward<true><<<grid, kBlock, 0, st>>>(P);
+    } else {
+        if ((rc = persistent_grid(ctx, k_nerf_backward<false>, kBlock, &grid))) return rc;
+        k_nerf_backward<false><<<grid, kBlock, 0, st>>>(P);
+    }
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
+    ctx->ev_valid[1] = true;
+    ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_test_exp(uivr_ctx* ctx, const float* d_x, int n, float* d_out, void* stream) {
+    if (!ctx || !d_x || !d_out || n < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > 0) k_test_exp<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(d_x, n, d_out);
     UIVR_CUDA(ctx, cudaGetLastError());
     return UIVR_OK;
 }

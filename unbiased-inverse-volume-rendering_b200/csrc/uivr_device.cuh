@@ -43,6 +43,7 @@ struct Params {
     uint32_t seed_pixels, seed_offsets;
     // integrator
     int max_depth, hide_emitters, use_nee, use_drt, use_drt_subsampling, use_drt_mis;
+    int nerf_queries, nerf_jitter, nerf_activation;  // `nerf` integrator (nerf.py:27-35); albedo = emission grid
     // launch
     uint32_t seed, alt_seed, spp;
     float inv_spp;

@@ -22,6 +22,7 @@ from .scene import Sensor, VolumeScene
 
 SIGMA_T_SUFFIX = "sigma_t.data"
 ALBEDO_SUFFIX = "albedo.data"
+EMISSION_SUFFIX = "emission.data"
 
 
 def _find_key(params: Dict[str, torch.Tensor], suffix: str) -> str:
@@ -50,11 +51,12 @@ class Scene:
         self._props_key = None
 
     # mi.traverse(scene) equivalent for the two optimised grids
-    def check_params(self, params: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    def check_params(self, params: Dict[str, torch.Tensor],
+                     second_suffix: str = ALBEDO_SUFFIX) -> Tuple[torch.Tensor, torch.Tensor]:
         x, y, z = self.volume.res
         sig = params[_find_key(params, SIGMA_T_SUFFIX)]
-        alb = params[_find_key(params, ALBEDO_SUFFIX)]
-        for name, t, shape in (("sigma_t", sig, (z, y, x, 1)), ("albedo", alb, (z, y, x, 3))):
+        alb = params[_find_key(params, second_suffix)]
+        for name, t, shape in (("sigma_t", sig, (z, y, x, 1)), (second_suffix.split(".")[0], alb, (z, y, x, 3))):
             if tuple(t.shape) != shape and not (name == "sigma_t" and tuple(t.shape) == (z, y, x)):
                 raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
             if t.dtype != torch.float32 or not t.is_cuda or t.device.index != self.device:
@@ -74,8 +76,8 @@ class Scene:
             self._medium_inputs = (desc["res"], float(desc["scale"]), desc["majorant_factor"])
             if old_medium_inputs != self._medium_inputs:
                 self._medium_key = None
-        pkey = tuple(sorted(props.items()))
-        if pkey != self._props_key:
+        pkey = None if props is None else tuple(sorted(props.items()))
+        if pkey is not None and pkey != self._props_key:
             self.ctx.set_integrator(props)
             self._props_key = pkey
         return desc
@@ -97,6 +99,8 @@ class Scene:
 
 class VolpathSimpleIntegrator:
     """Same property names / defaults as python/integrators/volpathsimple.py:19-34."""
+
+    second_suffix = ALBEDO_SUFFIX  # the RGB grid differentiated next to sigma_t
 
     def __init__(self, props: Optional[dict] = None):
         props = dict(props or {})
@@ -164,7 +168,75 @@ class VolpathSimpleIntegrator:
         return dsig, dalb
 
 
-INTEGRATORS = {"volpathsimple": VolpathSimpleIntegrator}
+class NeRFIntegrator:
+    """python/integrators/nerf.py: emission-absorption ray marching over the sigma_t grid and an RGB
+    emission grid (`...emission.data`, (Z,Y,X,3)); same property names / defaults as nerf.py:27-35."""
+
+    second_suffix = EMISSION_SUFFIX
+
+    def __init__(self, props: Optional[dict] = None):
+        props = dict(props or {})
+        props.pop("type", None)
+        # RBIntegrator base-class properties (unused by this integrator, accepted like the reference)
+        self.max_depth = int(props.pop("max_depth", 6))
+        self.rr_depth = int(props.pop("rr_depth", 5))
+        self.hide_emitters = bool(props.pop("hide_emitters", False))
+        self.queries_per_ray = int(props.pop("queries_per_ray", 128))
+        self.density_noise_std = float(props.pop("density_noise_std", 0.0))
+        self.jittering_enabled = bool(props.pop("jittering_enabled", True))
+        self.activation_type = str(props.pop("activation", "identity")).lower()
+        if props:
+            raise ValueError(f"unknown integrator properties: {sorted(props)}")
+        if self.density_noise_std > 0:
+            # nerf.py:156-158: "Incorrect for now: noise rnd is wrong on second loop of adjoint"
+            raise NotImplementedError("density_noise_std > 0 is marked incorrect by the reference (nerf.py:157)")
+
+    def props(self) -> dict:
+        if self.activation_type not in ("identity", "relu"):
+            raise ValueError(f"Unsupported activation: {self.activation_type}")  # nerf.py:44
+        return {"queries_per_ray": self.queries_per_ray, "jittering_enabled": self.jittering_enabled,
+                "activation": self.activation_type, "hide_emitters": self.hide_emitters}
+
+    def aovs(self):
+        return []
+
+    def render(self, scene: Scene, params: Dict[str, torch.Tensor], sensor: Optional[Sensor] = None,
+               seed: int = 0, spp: int = 0, develop: bool = True, evaluate: bool = True,
+               shard: Optional[Sequence[int]] = None, sample_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not develop:
+            raise Exception("develop=True must be specified when invoking AD integrators")  # batched.py:145-147
+        if spp <= 0:
+            raise ValueError("spp must be positive")
+        props = self.props()
+        sig, em = scene.check_params(params, EMISSION_SUFFIX)
+        desc = scene.bind(sensor, None)
+        scene.update_medium(sig.detach())
+        image = torch.empty((desc["height"], desc["width"], 3), dtype=torch.float32, device=sig.device)
+        scene.ctx.nerf_forward(props, em.detach().data_ptr(), seed, spp, image.data_ptr(),
+                               None if sample_out is None else sample_out.data_ptr(), shard, _stream())
+        return image
+
+    def render_backward(self, scene: Scene, params: Dict[str, torch.Tensor], grad_in: torch.Tensor,
+                        sensor: Optional[Sensor] = None, seed: int = 0, spp: int = 0,
+                        shard: Optional[Sequence[int]] = None, sample_out: Optional[torch.Tensor] = None,
+                        out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        if spp <= 0:
+            raise ValueError("spp must be positive")
+        props = self.props()
+        sig, em = scene.check_params(params, EMISSION_SUFFIX)
+        desc = scene.bind(sensor, None)
+        if tuple(grad_in.shape) != (desc["height"], desc["width"], 3):
+            raise ValueError(f"grad_in must have shape {(desc['height'], desc['width'], 3)}")
+        grad_in = grad_in.to(dtype=torch.float32).contiguous()
+        scene.update_medium(sig.detach())
+        dsig, dem = (torch.empty_like(sig), torch.empty_like(em)) if out is None else out
+        scene.ctx.nerf_backward(props, em.detach().data_ptr(), grad_in.data_ptr(), seed, spp, dsig.data_ptr(),
+                                dem.data_ptr(), None if sample_out is None else sample_out.data_ptr(), shard,
+                                _stream())
+        return dsig, dem
+
+
+INTEGRATORS = {"volpathsimple": VolpathSimpleIntegrator, "nerf": NeRFIntegrator}
 
 
 def register_integrator(name: str, factory):
@@ -177,7 +249,7 @@ def load_dict(d: dict):
     if "type" not in d:
         raise ValueError("integrator dictionary needs a 'type'")
     if d["type"] not in INTEGRATORS:
-        raise NotImplementedError(f"integrator type '{d['type']}' is outside the hot path of this build")
+        raise NotImplementedError(f"integrator type '{d['type']}' is not part of this build")
     return INTEGRATORS[d["type"]](d)
 
 
@@ -218,6 +290,6 @@ def render(scene: Scene, params: Dict[str, torch.Tensor], integrator: VolpathSim
     elif seed_grad == seed:
         raise Exception("The primal and differential seed should be different "
                         "to ensure unbiased gradient computation!")  # batched.py:122-124
-    k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, ALBEDO_SUFFIX)
+    k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, integrator.second_suffix)
     return _RenderOp.apply(params[k_sig], params[k_alb], scene, integrator, sensor, seed, seed_grad,
                            spp, spp_grad, (k_sig, k_alb), shard, reducer)

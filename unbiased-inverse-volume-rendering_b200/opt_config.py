@@ -68,8 +68,7 @@ for _name, _pretty, _params, _extra in (
     ("volpathsimple-drt-quadratic", "Differential Ratio Tracking (quadratic)",
      _vps(use_drt=True, use_drt_subsampling=False, use_drt_mis=True), {}),
     ("volpathsimple-basic", "Free-flight based", _vps(use_drt=False), {}),
-    # emission-only ray marcher: a different estimator, outside this build's hot path;
-    # load_dict raises NotImplementedError for it
+    # emission-absorption ray marcher (python/integrators/nerf.py), the reference's warm-start integrator
     ("nerf", "NeRF (grid-backed)", {"type": "nerf", "queries_per_ray": 128}, {}),
 ):
     add_int_config(_name, pretty_name=_pretty, params=_params, **_extra)
