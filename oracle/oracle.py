@@ -31,6 +31,9 @@ class _Scene(C.Structure):
         ("radiance", C.c_float * 3),
         ("max_depth", C.c_int32), ("hide_emitters", C.c_int32), ("use_nee", C.c_int32),
         ("use_drt", C.c_int32), ("use_drt_subsampling", C.c_int32), ("use_drt_mis", C.c_int32),
+        ("local_to_world", C.c_float * 9), ("env_data", C.POINTER(C.c_float)), ("env_w", C.c_int32),
+        ("env_h", C.c_int32), ("env_scale", C.c_float), ("env_marg", C.POINTER(C.c_float)),
+        ("env_cond", C.POINTER(C.c_float)), ("env_to_world", C.c_float * 9), ("world_to_env", C.c_float * 9),
     ]
 
 
@@ -107,6 +110,17 @@ def make_scene(desc: Dict, props: Dict) -> _Scene:
     s.use_drt = int(bool(props.get("use_drt", True)))
     s.use_drt_subsampling = int(bool(props.get("use_drt_subsampling", True)))
     s.use_drt_mis = int(bool(props.get("use_drt_mis", True)))
+    l2w = desc.get("local_to_world")
+    if l2w is None:  # linear part of the inverse of to_local
+        l2w = np.linalg.inv(np.asarray(desc["to_local"], dtype=np.float64).reshape(3, 4)[:, :3]).reshape(-1)
+    s.local_to_world[:] = [float(v) for v in np.asarray(l2w).reshape(-1)]
+    if desc.get("env_data") is not None:
+        keep = [_f32(desc[k]) for k in ("env_data", "env_marg", "env_cond")]
+        s._keepalive = keep  # the struct only holds raw pointers
+        s.env_data, s.env_marg, s.env_cond = (_ptr(a, C.c_float) for a in keep)
+        s.env_w, s.env_h, s.env_scale = int(desc["env_w"]), int(desc["env_h"]), float(desc["env_scale"])
+        s.env_to_world[:] = [float(v) for v in desc["env_to_world"]]
+        s.world_to_env[:] = [float(v) for v in desc["world_to_env"]]
     return s
 
 

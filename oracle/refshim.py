@@ -79,6 +79,9 @@ def _lib():
         L.uivr_oracle_shim_scatter.argtypes = [vp, C.c_int, C.c_int, fp, fp, u8p, dp]
         L.uivr_oracle_shim_uniform_sphere.argtypes = [C.c_int, fp, fp, fp]
         L.uivr_oracle_shim_fma.argtypes = [C.c_int, fp, fp, fp, fp]
+        L.uivr_oracle_shim_env_eval.argtypes = [vp, C.c_int, fp, fp, fp]
+        L.uivr_oracle_shim_env_sample.argtypes = [vp, C.c_int, fp, fp, fp, fp, fp]
+        L.uivr_oracle_shim_env_eval.restype = L.uivr_oracle_shim_env_sample.restype = None
         for f in ("destroy", "film_uv", "camera_ray", "box_entry", "entry_spawn", "exit", "dir_to_local",
                   "sample_interaction", "sample_interaction_drt", "lookup", "scatter", "uniform_sphere", "fma"):
             getattr(L, "uivr_oracle_shim_" + f).restype = None
@@ -121,6 +124,7 @@ class _Session:
         self.dsigma = np.zeros((z, y, x, 1), dtype=F64)
         self.dalbedo = np.zeros((z, y, x, 3), dtype=F64)
         self.radiance = np.asarray(desc["radiance"], dtype=F32)
+        self.envmap = desc.get("env_data") is not None
         self.draws = 0
 
     def close(self):
@@ -721,6 +725,8 @@ class DirectionSample3f(Struct):
 
     def __init__(self, *a):
         Struct.__init__(self, a[0] if len(a) == 1 else None)
+        if len(a) == 3:  # DirectionSample3f(scene, si, ref): direction of the ray that produced `si`
+            self.d = a[1].rd
 
 
 class _Ptr:
@@ -1217,14 +1223,30 @@ class PhaseFunctionPtr(_Ptr):
         return select(_M(active) & self.valid, Float(INV_4PI), 0.0)
 
 
+def _env_eval(d: Vec):
+    """envmap radiance and solid-angle density for rays leaving along local direction d"""
+    n = width(d)
+    dd = _c32(d.numpy(), n)
+    le = np.empty((n, 3), dtype=F32)
+    pdf = np.empty(n, dtype=F32)
+    _lib().uivr_oracle_shim_env_eval(_S().h, n, _p(dd, C.c_float), _p(le, C.c_float), _p(pdf, C.c_float))
+    return Color3f(le), _raw(pdf)
+
+
 class EmitterPtr(_Ptr):
-    """constant environment emitter"""
+    """the scene's environment emitter: `constant`, or `envmap` when the session has one"""
 
     def pdf_direction(self, it, ds, active=True):
-        return select(_M(active) & self.valid, Float(INV_4PI), 0.0)
+        m = _M(active) & self.valid
+        if _S().envmap:
+            return select(m, _env_eval(ds.d)[1], 0.0)
+        return select(m, Float(INV_4PI), 0.0)
 
     def eval(self, si, active=True):
-        return select(_M(active) & self.valid, Color3f(list(_S().radiance)), 0.0)
+        m = _M(active) & self.valid
+        if _S().envmap:
+            return select(m, _env_eval(si.rd)[0], 0.0)
+        return select(m, Color3f(list(_S().radiance)), 0.0)
 
 
 class _SigmaLeaf:
@@ -1422,6 +1444,17 @@ class Scene:
         m = _M(active)
         n = max(width(sample), len(m))
         ds = DirectionSample3f()
+        if _S().envmap:
+            a, b = _c32(sample.c[0].v, n), _c32(sample.c[1].v, n)
+            d = np.empty((n, 3), dtype=F32)
+            pdf = np.empty(n, dtype=F32)
+            le = np.empty((n, 3), dtype=F32)
+            _lib().uivr_oracle_shim_env_sample(_S().h, n, _p(a, C.c_float), _p(b, C.c_float), _p(d, C.c_float),
+                                               _p(pdf, C.c_float), _p(le, C.c_float))
+            ds.d = Vector3f(d)
+            ds.pdf = select(m, _raw(pdf), 0.0)
+            ok = m & (ds.pdf > 0.0)
+            return ds, select(ok, Color3f(le) / ds.pdf, 0.0)
         ds.d = Vector3f(_uniform_sphere_local(sample, n))
         ds.pdf = select(m, Float(INV_4PI), 0.0)
         val = select(m, Color3f(list(_S().radiance)) / Float(INV_4PI), 0.0)

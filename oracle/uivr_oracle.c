@@ -405,6 +405,129 @@ static inline void seg_point(const seg_t* s, float t, float p[3]) {
     for (int a = 0; a < 3; ++a) p[a] = FMA(t, s->d[a], s->o[a]);
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* envmap emitter [UPSTREAM envmap.cpp as recalled; conventions defined in scene.py EnvMap] */
+/* ------------------------------------------------------------------------------------ */
+
+#define INV_4PI 0.07957747154594767f
+#define INV_2PI2 0.05066059182116889f      /* 1 / (2 pi^2) */
+#define ENV_EPS2 3.5527137e-15f            /* (2^-24)^2 */
+#define ONE_MINUS_EPS 0.99999994f
+
+/* atan2(y, x) / (2 pi) in [-0.5, 0.5]: octant reduction + Cephes atanf polynomial, exact ops only */
+static inline float atan2_turns(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float hi = ax > ay ? ax : ay, lo = ax > ay ? ay : ax;
+    float a = hi > 0.0f ? lo / hi : 0.0f;
+    float off = 0.0f, t = a;
+    if (a > 0.41421356f) {
+        t = (a - 1.0f) / (a + 1.0f);
+        off = 0.78539816f;
+    }
+    float z = t * t;
+    float p = 8.05374449538e-2f;
+    p = FMA(p, z, -1.38776856032e-1f);
+    p = FMA(p, z, 1.99777106478e-1f);
+    p = FMA(p, z, -3.33329491539e-1f);
+    float r = (FMA(p * z, t, t) + off) * 0.15915494f;
+    if (ay > ax) r = 0.25f - r;
+    if (x < 0.0f) r = 0.5f - r;
+    if (y < 0.0f) r = -r;
+    return r;
+}
+
+void uivr_oracle_atan2_turns(const float* y, const float* x, int n, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = atan2_turns(y[i], x[i]);
+}
+
+static inline void mat3_apply(const float M[9], const float v[3], float o[3]) {
+    for (int a = 0; a < 3; ++a) o[a] = FMA(M[3 * a + 0], v[0], FMA(M[3 * a + 1], v[1], M[3 * a + 2] * v[2]));
+}
+
+/* eval_spectrum(uv) * scale and the sampling density of the patch containing uv */
+static void env_lookup(const uivr_oracle_scene* sc, float tu, float tv, float le[3], float* pdf_uv) {
+    const int W = sc->env_w, H = sc->env_h;
+    float fx = tu * (float) W, fy = tv * (float) (H - 1);
+    int px = (int) fx, py = (int) fy;
+    px = px > W - 1 ? W - 1 : (px < 0 ? 0 : px);
+    py = py > H - 2 ? H - 2 : (py < 0 ? 0 : py);
+    float w1x = fx - (float) px, w1y = fy - (float) py, w0x = 1.0f - w1x, w0y = 1.0f - w1y;
+    const float* v00 = sc->env_data + 4 * ((size_t) py * (W + 1) + px);
+    const float* v10 = v00 + 4;
+    const float* v01 = v00 + 4 * (size_t) (W + 1);
+    const float* v11 = v01 + 4;
+    for (int c = 0; c < 3; ++c) {
+        float s0 = FMA(w0x, v00[c], w1x * v10[c]);
+        float s1 = FMA(w0x, v01[c], w1x * v11[c]);
+        le[c] = FMA(w0y, s0, w1y * s1) * sc->env_scale;
+    }
+    *pdf_uv = v00[3];
+}
+
+static inline float env_inv_sin_theta(const float d[3]) {
+    float s2 = FMA(d[0], d[0], d[2] * d[2]);
+    return 1.0f / sqrtf(s2 > ENV_EPS2 ? s2 : ENV_EPS2);
+}
+
+/* Emitter::eval(si) and Emitter::pdf_direction for a ray leaving along `d_local` (segment direction) */
+static void env_eval(const uivr_oracle_scene* sc, const float d_local[3], float le[3], float* pdf_dir) {
+    float w[3], d[3];
+    mat3_apply(sc->local_to_world, d_local, w);
+    mat3_apply(sc->world_to_env, w, d);
+    float u = atan2_turns(d[0], -d[2]);
+    float cy = d[1];
+    float sy = sqrtf(FMA(-cy, cy, 1.0f) > 0.0f ? FMA(-cy, cy, 1.0f) : 0.0f);
+    float tv = 2.0f * atan2_turns(sy, cy);
+    float tu = u - 0.5f / (float) sc->env_w;
+    tu -= floorf(tu);
+    tv = tv < 0.0f ? 0.0f : (tv > 1.0f ? 1.0f : tv);
+    float pdf_uv;
+    env_lookup(sc, tu, tv, le, &pdf_uv);
+    *pdf_dir = (pdf_uv * env_inv_sin_theta(d)) * INV_2PI2;
+}
+
+/* upper bound in a CDF table: smallest i in [0, n) with cdf[i] > x, clamped to n - 1; returns the
+ * position of x inside that bin in *frac */
+static inline int cdf_find(const float* cdf, int n, float x, float* frac) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] > x) hi = mid; else lo = mid + 1;
+    }
+    float a = lo > 0 ? cdf[lo - 1] : 0.0f, den = cdf[lo] - a;
+    float f = den > 0.0f ? (x - a) / den : 0.5f;
+    *frac = f < 0.0f ? 0.0f : (f > ONE_MINUS_EPS ? ONE_MINUS_EPS : f);
+    return lo;
+}
+
+/* Scene::sample_emitter_direction: world direction, solid-angle pdf, radiance */
+static void env_sample(const uivr_oracle_scene* sc, float xi1, float xi2, float w[3], float* pdf_dir, float le[3]) {
+    const int W = sc->env_w, H = sc->env_h;
+    float f1, f2;
+    int r = cdf_find(sc->env_marg, H - 1, xi2, &f2);
+    int c = cdf_find(sc->env_cond + (size_t) r * W, W, xi1, &f1);
+    float tu = ((float) c + f1) / (float) W, tv = ((float) r + f2) / (float) (H - 1);
+    float pdf_uv;
+    env_lookup(sc, tu, tv, le, &pdf_uv);
+    pdf_uv = sc->env_data[4 * ((size_t) r * (W + 1) + c) + 3];
+    float du = tu + 0.5f / (float) W;
+    du -= floorf(du);
+    float sp, cp, st, ct, d[3];
+    sincos2pi(du, &sp, &cp);
+    sincos2pi(0.5f * tv, &st, &ct);
+    d[0] = sp * st;
+    d[1] = ct;
+    d[2] = -(cp * st);
+    *pdf_dir = (pdf_uv * env_inv_sin_theta(d)) * INV_2PI2;
+    mat3_apply(sc->env_to_world, d, w);
+}
+
+/* mi.ad.common.mis_weight: power heuristic */
+static inline float mis_power(float a, float b) {
+    float a2 = a * a;
+    return a > 0.0f ? a2 / FMA(b, b, a2) : 0.0f;
+}
+
 /* Medium::sample_interaction with supergrid DDA [UPSTREAM App. B.5, a14]; the DDA state is
  * carried along the segment instead of being restarted per call (same distribution). */
 typedef struct {
@@ -509,13 +632,24 @@ static float ratio_track(const ctx_t* C, counters_t* K, const seg_t* s, rng_t* r
 static void nee(const ctx_t* C, counters_t* K, const float p[3], const float beta[3],
                 rng_t* rng, const float* dL, float contrib[3]) {
     float xi1 = rng_f(rng), xi2 = rng_f(rng);
-    float w[3];
-    uniform_sphere(xi1, xi2, w);
+    float w[3], wgt[3];
+    int worked = 1;
+    if (C->sc->env_data) {
+        /* envmap: throughput * phase_val * mis_weight(ds.pdf, phase_pdf) * (Le / ds.pdf) * T  (:385-391, :419-423) */
+        float pdf, le[3];
+        env_sample(C->sc, xi1, xi2, w, &pdf, le);
+        worked = pdf != 0.0f; /* sampling_worked (:421-423): no shadow ray, no draws */
+        float mis = mis_power(pdf, INV_4PI);
+        for (int c = 0; c < 3; ++c) wgt[c] = worked ? ((beta[c] * INV_4PI) * mis) * (le[c] / pdf) : 0.0f;
+    } else {
+        uniform_sphere(xi1, xi2, w);
+        for (int c = 0; c < 3; ++c) wgt[c] = beta[c] * C->half_le[c];
+    }
     seg_t s;
-    int valid = make_segment(C, p, w, &s);
+    int valid = worked && make_segment(C, p, w, &s);
     rng_t clone = *rng;
     float T = valid ? ratio_track(C, K, &s, rng, NULL) : 0.0f;
-    for (int c = 0; c < 3; ++c) contrib[c] = (beta[c] * C->half_le[c]) * T;
+    for (int c = 0; c < 3; ++c) contrib[c] = wgt[c] * T;
     if (dL && valid) {
         float adj[3];
         for (int c = 0; c < 3; ++c) adj[c] = dL[c] * contrib[c];
@@ -718,8 +852,18 @@ static void path_loop(const ctx_t* C, counters_t* K, int adjoint, rng_t* rng, rn
 
     /* :263-285 envmap (primal only) */
     if (!adjoint && escaped && !(depth <= 0 && sc->hide_emitters)) {
-        float wmis = (sc->use_nee && has_scattered) ? 0.5f : 1.0f;
-        for (int c = 0; c < 3; ++c) R[c] = FMA(beta[c] * wmis, sc->radiance[c], R[c]);
+        if (sc->env_data) {
+            /* :270-285 emitter.eval(si) with hit_mis_weight = mis_weight(last_scatter_direction_pdf,
+             * has_scattered ? emitter.pdf_direction : 0) */
+            float le[3], pdf;
+            env_eval(sc, seg.d, le, &pdf);
+            float wmis = 1.0f;
+            if (sc->use_nee) wmis = mis_power(has_scattered ? INV_4PI : 1.0f, has_scattered ? pdf : 0.0f);
+            for (int c = 0; c < 3; ++c) R[c] = R[c] + (beta[c] * wmis) * le[c];
+        } else {
+            float wmis = (sc->use_nee && has_scattered) ? 0.5f : 1.0f;
+            for (int c = 0; c < 3; ++c) R[c] = FMA(beta[c] * wmis, sc->radiance[c], R[c]);
+        }
     }
 }
 
@@ -865,11 +1009,11 @@ static inline void entry_spawn(const float ol[3], const float dl[3], float tn, f
 static int camera_segment_frame(const ctx_t* C, const float* F, float u, float v, seg_t* s) {
     float ol[3], dl[3], tn = 0.0f;
     camera_ray_local(C, F, u, v, ol, dl);
+    for (int a = 0; a < 3; ++a) s->d[a] = dl[a]; /* also for rays that miss: the envmap lookup needs it */
     /* reach_medium (volpathsimple.py:292-319) */
     int hit = box_entry(ol, dl, &tn);
     if (hit != 1) return hit; /* 2: origin inside, the re-spawned ray misses */
     entry_spawn(ol, dl, tn, s->o);
-    for (int a = 0; a < 3; ++a) s->d[a] = dl[a];
     s->tmax = exit_distance(s);
     return (s->tmax > 0.0f && s->tmax < UIVR_INF) ? 1 : 2;
 }
@@ -972,8 +1116,11 @@ static void nerf_sample(const ctx_t* C, counters_t* K, int adjoint, uint32_t see
     /* :134-143 composite with the background emitter (in both modes) */
     int active_e = escaped || active;
     if (N->hide_emitters) active_e = active_e && (wsum > 0.0f);
-    if (active_e)
-        for (int c = 0; c < 3; ++c) R[c] += (1.0f - wsum) * sc->radiance[c];
+    if (active_e) {
+        float le[3] = {sc->radiance[0], sc->radiance[1], sc->radiance[2]}, pdf;
+        if (sc->env_data) env_eval(sc, seg.d, le, &pdf);
+        for (int c = 0; c < 3; ++c) R[c] += (1.0f - wsum) * le[c];
+    }
     K->c[UIVR_ORC_RNG_DRAWS] += rng.draws;
 }
 
@@ -1378,6 +1525,19 @@ void uivr_oracle_shim_scatter(const uivr_oracle_shim* h, int which, int n, const
         } else {
             scatter(dgrid, h->sc.res, 3, p + 3 * i, g + 3 * i);
         }
+    }
+}
+
+void uivr_oracle_shim_env_eval(const uivr_oracle_shim* h, int n, const float* d, float* le, float* pdf) {
+    for (int i = 0; i < n; ++i) env_eval(&h->sc, d + 3 * i, le + 3 * i, pdf + i);
+}
+
+void uivr_oracle_shim_env_sample(const uivr_oracle_shim* h, int n, const float* xi1, const float* xi2,
+                                 float* d, float* pdf, float* le) {
+    for (int i = 0; i < n; ++i) {
+        float w[3];
+        env_sample(&h->sc, xi1[i], xi2[i], w, pdf + i, le + 3 * i);
+        dir_to_local(h->sc.to_local, w, d + 3 * i);
     }
 }
 

@@ -51,6 +51,18 @@ typedef struct {
     int32_t use_drt;
     int32_t use_drt_subsampling;
     int32_t use_drt_mis;
+    /* emitter = lat-long environment map instead of the constant `radiance` when env_data != NULL
+     * ("next" row SURVEY 8f rank 4; Mitsuba `envmap`, volpathsimple.py:262-285, :419).  Tables as
+     * built by the host (scene.py EnvMap.tables): vertices (env_h, env_w + 1, 4) = RGB radiance +
+     * sampling density of the bilinear patch (y, x); row marginal CDF (env_h - 1); per-row
+     * conditional CDFs (env_h - 1, env_w).  Rotations are row-major 3x3. */
+    float   local_to_world[9];   /* linear part of medium-local -> world */
+    const float* env_data;
+    int32_t env_w, env_h;
+    float   env_scale;
+    const float* env_marg;
+    const float* env_cond;
+    float   env_to_world[9], world_to_env[9];
 } uivr_oracle_scene;
 
 /* Ray-batch rendering (python/batched.py:88-131, "next" row SURVEY 8f rank 2): instead of the
@@ -199,6 +211,12 @@ void uivr_oracle_shim_lookup(const uivr_oracle_shim* h, int which, int n, const 
 /* adjoint of lookup 0 / 1: scatter-add g (1 or 3 floats per lane) into dgrid (doubles) where mask */
 void uivr_oracle_shim_scatter(const uivr_oracle_shim* h, int which, int n, const float* p, const float* g,
                               const uint8_t* mask, double* dgrid);
+/* envmap emitter: Emitter::eval + pdf_direction for a ray leaving along local direction d;
+ * Scene::sample_emitter_direction (direction in local space, solid-angle pdf, radiance) */
+void uivr_oracle_shim_env_eval(const uivr_oracle_shim* h, int n, const float* d, float* le, float* pdf);
+void uivr_oracle_shim_env_sample(const uivr_oracle_shim* h, int n, const float* xi1, const float* xi2,
+                                 float* d, float* pdf, float* le);
+void uivr_oracle_atan2_turns(const float* y, const float* x, int n, float* out); /* atan2(y,x)/(2 pi) */
 void uivr_oracle_shim_uniform_sphere(int n, const float* xi1, const float* xi2, float* w);
 void uivr_oracle_shim_fma(int n, const float* a, const float* b, const float* c, float* out); /* fmaf */
 

@@ -59,6 +59,27 @@ def run_batch():
     return res
 
 
+def run_envmap():
+    e = RC.ENVMAP
+    c = RC.CASES[e["case"]]
+    sig, alb, vol = RC.envmap_inputs()
+    desc = vol.as_dict()
+    out = {}
+    for integ_name, max_depth in e["runs"]:
+        reg, over = RC.INTEGRATORS[integ_name]
+        integ = R.make_integrator(reg, max_depth=max_depth, **over)
+        key = f"{integ_name}@{max_depth}"
+        img, samples = R.render_forward(desc, integ, sig, alb, c["seed"], c["spp"])
+        gimg = loss_grad(img)
+        ds, da, samples_g = R.render_backward(desc, integ, sig, alb, gimg, c["seed_grad"], c["spp"])
+        out.update({f"{key}/image": img, f"{key}/samples": samples, f"{key}/grad_image": gimg,
+                    f"{key}/samples_grad_pass": samples_g, f"{key}/dsigma": ds, f"{key}/dalbedo": da})
+    integ = R.make_integrator("nerf", max_depth=4, **e["nerf_props"])
+    img, samples = R.render_forward(desc, integ, sig, alb, c["seed"], c["spp"])
+    out.update({"nerf/image": img, "nerf/samples": samples})
+    return out
+
+
 def run_nerf():
     c = RC.NERF
     out = {}
@@ -85,6 +106,8 @@ def run_nerf():
 
 def main():
     O.build()
+    np.savez_compressed(os.path.join(HERE, "refshim_envmap.npz"), **run_envmap())
+    print("envmap written")
     np.savez_compressed(os.path.join(HERE, "refshim_nerf.npz"), **run_nerf())
     print("nerf written")
     for name in RC.CASES:

@@ -63,6 +63,30 @@ def nerf_inputs(offset=0.0):
     return (sig + np.float32(offset)).astype(np.float32), em, vol
 
 
+# envmap emitter: the hetero12 case lit by a small lat-long map with a "sun",
+# rotated about +Y; volpathsimple flag combos + the nerf integrator
+ENVMAP = dict(case="hetero12", runs=[("volpathsimple-drt", 16), ("volpathsimple-basic", 16), ("no-nee", 16),
+                                     ("volpathsimple-drt-quadratic", 3)],
+              nerf_props=dict(queries_per_ray=16))
+
+
+def test_envmap():
+    from importlib import import_module
+    S = import_module(u.__name__ + ".scene")
+    rng = np.random.default_rng(3)
+    img = (rng.random((9, 16, 3)) ** 3 * 2.0).astype(np.float32)
+    img[2, 5] = (30.0, 25.0, 10.0)
+    th = 0.7
+    rot = ((np.cos(th), 0.0, np.sin(th)), (0.0, 1.0, 0.0), (-np.sin(th), 0.0, np.cos(th)))
+    return S.EnvMap(img, scale=1.5, to_world=rot)
+
+
+def envmap_inputs():
+    sig, alb, vol = case_inputs(ENVMAP["case"])
+    vol.envmap = test_envmap()
+    return sig, alb, vol
+
+
 def case_inputs(name):
     c = CASES[name]
     if name == "cube3":

@@ -69,6 +69,57 @@ def circle_sensors(n: int, width: int, height: int, center=(0.5, 0.5, 0.5), radi
 
 
 @dataclass
+class EnvMap:
+    """Lat-long environment emitter (Mitsuba `envmap`; every scene of python/scene_config.py:102-340
+    uses one): `image` (H, W, 3) float32, row 0 = +Y pole, radiance = `scale` x bilinear lookup.
+
+    Conventions (upstream envmap.cpp as recalled in SURVEY App. B, defined here where it cannot be
+    checked): a direction d in the emitter's frame has texture coordinates
+    u = atan2(d.x, -d.z) / 2pi - 0.5 / W (wrapped), v = acos(d.y) / pi; the texel grid is
+    (H, W + 1) vertices (first column repeated at the end) joined by W x (H - 1) bilinear patches.
+    Importance sampling: piecewise-constant density over the patches, proportional to the patch mean
+    of luminance x sin(theta) (marginal over rows, conditional over columns; tables built here in
+    float64 and shared verbatim by the CUDA path and the test oracle)."""
+    image: np.ndarray
+    scale: float = 1.0
+    to_world: Tuple[Tuple[float, float, float], ...] = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
+
+    def tables(self) -> Dict[str, object]:
+        img = np.asarray(self.image, dtype=np.float64)
+        if img.ndim != 3 or img.shape[2] != 3 or img.shape[0] < 2 or img.shape[1] < 1:
+            raise ValueError("envmap image must have shape (H >= 2, W >= 1, 3)")
+        if not np.all(np.isfinite(img)) or np.any(img < 0):
+            raise ValueError("envmap radiance must be finite and non-negative")
+        h, w = img.shape[:2]
+        verts = np.concatenate([img, img[:, :1]], axis=1)                      # (H, W+1, 3)
+        lum = verts @ np.array([0.212671, 0.715160, 0.072169])                 # Rec.709 luminance
+        theta = np.arange(h, dtype=np.float64) * (np.pi / (h - 1))
+        f = lum * np.sin(theta)[:, None]
+        patch = 0.25 * (f[:-1, :-1] + f[:-1, 1:] + f[1:, :-1] + f[1:, 1:])     # (H-1, W)
+        total = patch.sum()
+        if not total > 0:
+            raise ValueError("envmap is black: nothing to importance-sample")
+        pdf = patch * (patch.size / total)                                     # density over [0,1]^2
+        rows = patch.sum(axis=1)
+        marg = np.cumsum(rows) / total
+        marg[-1] = 1.0
+        cond = np.cumsum(patch, axis=1)
+        cond = np.where(rows[:, None] > 0, cond / np.maximum(rows[:, None], 1e-300),
+                        (np.arange(w) + 1.0)[None, :] / w)
+        cond[:, -1] = 1.0
+        data = np.zeros((h, w + 1, 4), dtype=np.float32)
+        data[..., :3] = verts
+        data[:-1, :-1, 3] = pdf                                                # patch (y, x) -> its density
+        r = np.asarray(self.to_world, dtype=np.float64).reshape(3, 3)
+        return {"env_data": np.ascontiguousarray(data), "env_w": int(w), "env_h": int(h),
+                "env_scale": np.float32(self.scale),
+                "env_marg": np.ascontiguousarray(marg, dtype=np.float32),
+                "env_cond": np.ascontiguousarray(cond, dtype=np.float32),
+                "env_to_world": r.astype(np.float32).reshape(-1),
+                "world_to_env": np.linalg.inv(r).astype(np.float32).reshape(-1)}
+
+
+@dataclass
 class VolumeScene:
     """One heterogeneous medium in a box + one sensor + a constant emitter."""
     res: Tuple[int, int, int]                      # (X, Y, Z); tensors are (Z, Y, X, C)
@@ -78,7 +129,8 @@ class VolumeScene:
     bbox_extent: Tuple[float, float, float] = (2.0, 2.0, 2.0)
     scale: float = 1.0                             # medium 'scale' (density_scale)
     majorant_resolution_factor: int = 0            # scene_config.py:36; <=1 disables supergrid
-    radiance: Tuple[float, float, float] = (1.0, 0.8, 0.2)
+    radiance: Tuple[float, float, float] = (1.0, 0.8, 0.2)     # `constant` emitter ...
+    envmap: "EnvMap" = None                                    # ... or an `envmap` emitter (then radiance is unused)
 
     def to_local(self) -> np.ndarray:
         m = np.zeros((3, 4), dtype=np.float64)
@@ -118,8 +170,12 @@ class VolumeScene:
             "scale": np.float32(self.scale),
             "majorant_factor": self.effective_majorant_factor(),
             "radiance": np.asarray(self.radiance, dtype=np.float32),
+            # linear part of local -> world (directions of escaped rays are looked up in the envmap)
+            "local_to_world": np.diag(np.asarray(self.bbox_extent, dtype=np.float64)).astype(np.float32).reshape(-1),
         }
         d.update(self.sensor.frame())
+        if self.envmap is not None:
+            d.update(self.envmap.tables())
         return d
 
 
