@@ -117,6 +117,27 @@ int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props);   /*
  * uivr_set_scene are ignored; shards split the batch elements.  Needs kernel variant >= 2. */
 int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch);
 
+/* The scene's emitter is an `envmap` (lat-long environment map; every scene of
+ * python/scene_config.py:102-340) instead of the `constant` emitter of uivr_scene_desc.radiance:
+ * Emitter::eval + pdf_direction on escape (python/integrators/volpathsimple.py:262-285),
+ * Scene::sample_emitter_direction for next-event estimation (:419).  All pointers are HOST memory,
+ * copied by the call; tables as produced by the host mirror's EnvMap.tables() (scene.py):
+ *   data  [env_h][env_w + 1][4]  vertex radiance RGB (first column repeated at the end) and, in .w,
+ *                                the sampling density over [0,1]^2 of the bilinear patch (y, x)
+ *   marg  [env_h - 1]            CDF over patch rows;   cond [env_h - 1][env_w]  per-row CDFs
+ * Rotations are row-major 3x3; local_to_world is the linear part of the inverse of
+ * uivr_scene_desc.to_local.  NULL returns to the constant emitter.  Envmap scenes are rendered by
+ * the one-sample-per-lane kernels this round (the slot-pool kernels serve the constant emitter). */
+typedef struct {
+    int32_t env_w, env_h;     /* resolution of the source image (H >= 2) */
+    float   scale;
+    const float* data;
+    const float* marg;
+    const float* cond;
+    float   env_to_world[9], world_to_env[9], local_to_world[9];
+} uivr_envmap_desc;
+int uivr_set_envmap(uivr_ctx* ctx, const uivr_envmap_desc* env);
+
 /* params.update(): rebuild the device-side lookup structures derived from sigma_t -- the
  * corner-octet tap layout and the majorant supergrid (upstream does the latter on
  * params.update(), triggered at optimize.py:165, :251, :354).  Must be called after every
@@ -215,6 +236,7 @@ int uivr_set_variant(uivr_ctx* ctx, int variant);
 /* out[0:n] = -ln(1-u);  s,c = sin/cos(2 pi x);  sampler floats of stream (seed, idx) */
 int uivr_test_neg_log1m(uivr_ctx* ctx, const float* d_u, int n, float* d_out, void* stream);
 int uivr_test_exp(uivr_ctx* ctx, const float* d_x, int n, float* d_out, void* stream); /* exp(x), nerf.py:104 */
+int uivr_test_atan2_turns(uivr_ctx* ctx, const float* d_y, const float* d_x, int n, float* d_out, void* stream); /* atan2/(2 pi) */
 int uivr_test_sincos2pi(uivr_ctx* ctx, const float* d_x, int n, float* d_s, float* d_c, void* stream);
 int uivr_test_sampler(uivr_ctx* ctx, uint32_t seed, uint32_t idx0, int nstreams, int ndraws,
                       float* d_out, void* stream);

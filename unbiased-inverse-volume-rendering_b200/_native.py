@@ -27,7 +27,7 @@ EXPORTS = [
     "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
-    "uivr_nerf_forward", "uivr_nerf_backward", "uivr_test_exp",
+    "uivr_nerf_forward", "uivr_nerf_backward", "uivr_test_exp", "uivr_set_envmap", "uivr_test_atan2_turns",
 ]
 
 
@@ -59,6 +59,12 @@ class BatchDesc(C.Structure):
 class NerfProps(C.Structure):
     _fields_ = [("queries_per_ray", C.c_int32), ("jittering_enabled", C.c_int32), ("activation", C.c_int32),
                 ("hide_emitters", C.c_int32)]
+
+
+class EnvMapDesc(C.Structure):
+    _fields_ = [("env_w", C.c_int32), ("env_h", C.c_int32), ("scale", C.c_float), ("data", C.POINTER(C.c_float)),
+                ("marg", C.POINTER(C.c_float)), ("cond", C.POINTER(C.c_float)), ("env_to_world", C.c_float * 9),
+                ("world_to_env", C.c_float * 9), ("local_to_world", C.c_float * 9)]
 
 
 class Shard(C.Structure):
@@ -120,6 +126,8 @@ def lib():
         "uivr_nerf_forward": ([vp, C.POINTER(NerfProps), fp, u32, i32, C.POINTER(Shard), fp, fp, vp], C.c_int),
         "uivr_nerf_backward": ([vp, C.POINTER(NerfProps), fp, fp, u32, i32, C.POINTER(Shard), fp, fp, fp, vp], C.c_int),
         "uivr_test_exp": ([vp, fp, C.c_int, fp, vp], C.c_int),
+        "uivr_set_envmap": ([vp, C.POINTER(EnvMapDesc)], C.c_int),
+        "uivr_test_atan2_turns": ([vp, fp, fp, C.c_int, fp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)
@@ -197,6 +205,21 @@ class Context:
         d.sensors = a.ctypes.data_as(C.POINTER(C.c_float))
         d.film_w, d.film_h, d.batch_size, d.seed = int(film_w), int(film_h), int(batch_size), seed & 0xFFFFFFFF
         self._check(self._L.uivr_set_batch(self._h, C.byref(d)), "uivr_set_batch")
+
+    def set_envmap(self, desc: Optional[dict]):
+        """Switch the emitter to the envmap described by `desc` (the env_* / *_to_* entries of
+        VolumeScene.as_dict()) or back to the constant emitter (desc without env_data / None)."""
+        if desc is None or desc.get("env_data") is None:
+            self._check(self._L.uivr_set_envmap(self._h, None), "uivr_set_envmap")
+            return
+        import numpy as np
+        keep = [np.ascontiguousarray(desc[k], dtype=np.float32) for k in ("env_data", "env_marg", "env_cond")]
+        e = EnvMapDesc()
+        e.env_w, e.env_h, e.scale = int(desc["env_w"]), int(desc["env_h"]), float(desc["env_scale"])
+        e.data, e.marg, e.cond = (a.ctypes.data_as(C.POINTER(C.c_float)) for a in keep)
+        for k in ("env_to_world", "world_to_env", "local_to_world"):
+            getattr(e, k)[:] = [float(v) for v in np.asarray(desc[k]).reshape(-1)]
+        self._check(self._L.uivr_set_envmap(self._h, C.byref(e)), "uivr_set_envmap")
 
     def set_variant(self, variant: int):
         self._check(self._L.uivr_set_variant(self._h, int(variant)), "uivr_set_variant")
@@ -296,6 +319,9 @@ class Context:
     # -- primitive tests --
     def test_neg_log1m(self, u_ptr, n, out_ptr, stream=0):
         self._check(self._L.uivr_test_neg_log1m(self._h, u_ptr, n, out_ptr, stream), "uivr_test_neg_log1m")
+
+    def test_atan2_turns(self, y_ptr, x_ptr, n, out_ptr, stream=0):
+        self._check(self._L.uivr_test_atan2_turns(self._h, y_ptr, x_ptr, n, out_ptr, stream), "uivr_test_atan2_turns")
 
     def test_exp(self, x_ptr, n, out_ptr, stream=0):
         self._check(self._L.uivr_test_exp(self._h, x_ptr, n, out_ptr, stream), "uivr_test_exp")

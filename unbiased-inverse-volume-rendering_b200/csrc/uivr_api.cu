@@ -42,6 +42,13 @@ struct uivr_ctx {
     uivr_batch_desc batch{};
     float* d_sensors = nullptr;
     int d_sensors_cap = 0;
+    // envmap emitter (uivr_set_envmap)
+    bool env_on = false;
+    bool nerf_call = false;  // fill_params is serving a uivr_nerf_* entry point
+    uivr_envmap_desc env{};
+    float4* d_env_data = nullptr;
+    float* d_env_marg = nullptr;
+    float* d_env_cond = nullptr;
     int counting = 0;
     uint64_t launches = 0;
     // staging for the *_host entry points
@@ -127,6 +134,19 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
         P.film_h = ctx->batch.film_h;
         P.seed_pixels = uivr_tea32(ctx->batch.seed, 5);    // batched.py:409-413: sub_seed_i = tea32(seed, 17 i + 5)
         P.seed_offsets = uivr_tea32(ctx->batch.seed, 22);  // primal offsets; the backward entry switches to i = 2
+    }
+    if (ctx->env_on) {
+        if (ctx->batch_on && !ctx->nerf_call)
+            return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering of envmap-lit scenes is not available for volpathsimple yet");
+        P.env_data = ctx->d_env_data;
+        P.env_marg = ctx->d_env_marg;
+        P.env_cond = ctx->d_env_cond;
+        P.env_w = ctx->env.env_w;
+        P.env_h = ctx->env.env_h;
+        P.env_scale = ctx->env.scale;
+        memcpy(P.env_to_world, ctx->env.env_to_world, sizeof(P.env_to_world));
+        memcpy(P.world_to_env, ctx->env.world_to_env, sizeof(P.world_to_env));
+        memcpy(P.local_to_world, ctx->env.local_to_world, sizeof(P.local_to_world));
     }
     P.max_depth = ip.max_depth;
     P.hide_emitters = ip.hide_emitters;
@@ -228,6 +248,7 @@ int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
     for (int i = 0; i < 2; ++i)
@@ -277,6 +298,32 @@ int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch) {
     ctx->batch = *batch;
     ctx->batch.sensors = nullptr;
     ctx->batch_on = true;
+    return UIVR_OK;
+}
+
+int uivr_set_envmap(uivr_ctx* ctx, const uivr_envmap_desc* env) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    if (!env) {
+        ctx->env_on = false;
+        return UIVR_OK;
+    }
+    if (env->env_w < 1 || env->env_h < 2 || env->env_w > 16384 || env->env_h > 8192 || !env->data || !env->marg || !env->cond)
+        return fail(ctx, UIVR_ERR_INVALID, "invalid envmap descriptor");
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->env_on = false;
+    cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
+    ctx->d_env_data = nullptr; ctx->d_env_marg = ctx->d_env_cond = nullptr;
+    const size_t nv = (size_t) env->env_h * (env->env_w + 1), nr = (size_t) env->env_h - 1, nc = nr * env->env_w;
+    UIVR_CUDA(ctx, cudaMalloc(&ctx->d_env_data, nv * sizeof(float4)));
+    UIVR_CUDA(ctx, cudaMalloc(&ctx->d_env_marg, nr * sizeof(float)));
+    UIVR_CUDA(ctx, cudaMalloc(&ctx->d_env_cond, nc * sizeof(float)));
+    // (synchronous copies: set once per scene, and the host arrays need not outlive the call)
+    UIVR_CUDA(ctx, cudaMemcpy(ctx->d_env_data, env->data, nv * sizeof(float4), cudaMemcpyHostToDevice));
+    UIVR_CUDA(ctx, cudaMemcpy(ctx->d_env_marg, env->marg, nr * sizeof(float), cudaMemcpyHostToDevice));
+    UIVR_CUDA(ctx, cudaMemcpy(ctx->d_env_cond, env->cond, nc * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->env = *env;
+    ctx->env.data = ctx->env.marg = ctx->env.cond = nullptr;
+    ctx->env_on = true;
     return UIVR_OK;
 }
 
@@ -404,7 +451,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
-    if (ctx->variant == 1) {
+    if (ctx->variant == 1 || ctx->env_on) {  // envmap scenes: one-sample-per-lane kernels (uivr_set_envmap)
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_forward_v1<true>, kBlock, &grid))) return rc;
             k_forward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -450,7 +497,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
     const bool quadratic = ctx->props.use_drt && !ctx->props.use_drt_subsampling;
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    if (ctx->variant == 1 || quadratic) {
+    if (ctx->variant == 1 || quadratic || ctx->env_on) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -516,7 +563,9 @@ static int nerf_params(uivr_ctx* ctx, const uivr_nerf_props* np, Params& P, cons
     if (np->queries_per_ray < 2) return fail(ctx, UIVR_ERR_INVALID, "queries_per_ray must be >= 2");
     if (np->activation != UIVR_NERF_IDENTITY && np->activation != UIVR_NERF_RELU)
         return fail(ctx, UIVR_ERR_INVALID, "Unsupported activation (nerf.py:44)");
+    ctx->nerf_call = true;
     const int rc = fill_params(ctx, P, shard, seed, spp);
+    ctx->nerf_call = false;
     if (rc) return rc;
     P.nerf_queries = np->queries_per_ray;
     P.nerf_jitter = np->jittering_enabled ? 1 : 0;
@@ -589,6 +638,14 @@ int uivr_nerf_backward(uivr_ctx* ctx, const uivr_nerf_props* props, const float*
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
     ctx->ev_valid[1] = true;
     ctx->launches += 1;
+    UIVR_CUDA(ctx, cudaGetLastError());
+    return UIVR_OK;
+}
+
+int uivr_test_atan2_turns(uivr_ctx* ctx, const float* d_y, const float* d_x, int n, float* d_out, void* stream) {
+    if (!ctx || !d_y || !d_x || !d_out || n < 0) return UIVR_ERR_INVALID;
+    UIVR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > 0) k_test_atan2_turns<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>>(d_y, d_x, n, d_out);
     UIVR_CUDA(ctx, cudaGetLastError());
     return UIVR_OK;
 }

@@ -44,6 +44,13 @@ struct Params {
     // integrator
     int max_depth, hide_emitters, use_nee, use_drt, use_drt_subsampling, use_drt_mis;
     int nerf_queries, nerf_jitter, nerf_activation;  // `nerf` integrator (nerf.py:27-35); albedo = emission grid
+    // envmap emitter (uivr_set_envmap; NULL env_data = the constant emitter `radiance`); see uivr_env.cuh
+    const float4* __restrict__ env_data;   // (env_h, env_w + 1): RGB vertex radiance, w = density of patch (y, x)
+    const float* __restrict__ env_marg;    // env_h - 1
+    const float* __restrict__ env_cond;    // (env_h - 1, env_w)
+    int   env_w, env_h;
+    float env_scale;
+    float env_to_world[9], world_to_env[9], local_to_world[9];
     // launch
     uint32_t seed, alt_seed, spp;
     float inv_spp;
@@ -369,6 +376,7 @@ UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, f
     ol[1] = fmaf(M[4], o0, fmaf(M[5], o1, fmaf(M[6], o2, M[7])));
     ol[2] = fmaf(M[8], o0, fmaf(M[9], o1, fmaf(M[10], o2, M[11])));
     dir_to_local(P, d0, d1, d2, dl[0], dl[1], dl[2]);
+    s.dx = dl[0]; s.dy = dl[1]; s.dz = dl[2];  // also for rays that miss the box: the envmap lookup needs it
     float tn = -UIVR_INF, tf = UIVR_INF;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -389,7 +397,6 @@ UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, f
     s.ox = e0 < lo ? lo : (e0 > hi ? hi : e0);
     s.oy = e1 < lo ? lo : (e1 > hi ? hi : e1);
     s.oz = e2 < lo ? lo : (e2 > hi ? hi : e2);
-    s.dx = dl[0]; s.dy = dl[1]; s.dz = dl[2];
     s.tmax = exit_distance(s);
     return (s.tmax > 0.0f && s.tmax < UIVR_INF) ? 1 : 2;
 }

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "uivr_kernels.cuh"
+#include "uivr_env.cuh"
 
 namespace uivr {
 
@@ -101,8 +102,10 @@ UIVR_DEV void nerf_sample(const Params& P, uint32_t pix, uint32_t idx, const flo
     bool active_e = escaped || active;
     if (P.hide_emitters) active_e = active_e && (wsum > 0.0f);
     if (active_e) {
+        float le[3] = {P.radiance[0], P.radiance[1], P.radiance[2]}, pdf;
+        if (P.env_data) env_eval(P, seg.dx, seg.dy, seg.dz, le, pdf);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) R[c] += (1.0f - wsum) * P.radiance[c];
+        for (int c = 0; c < 3; ++c) R[c] += (1.0f - wsum) * le[c];
     }
 }
 

@@ -6,6 +6,7 @@
 #pragma once
 
 #include "uivr_device.cuh"
+#include "uivr_env.cuh"
 
 namespace uivr {
 
@@ -42,14 +43,27 @@ template <bool ADJ, bool COUNT>
 UIVR_DEV void nee(const Params& P, float px, float py, float pz, const float beta[3], Rng& rng,
                   const float dL[3], float contrib[3], Counters<COUNT>& K) {
     const float xi1 = draw(rng, K), xi2 = draw(rng, K);
-    float wx, wy, wz;
-    uniform_sphere(xi1, xi2, wx, wy, wz);
+    float wx, wy, wz, wgt[3];
+    bool worked = true;
+    if (P.env_data) {
+        // envmap: throughput * phase_val * mis_weight(ds.pdf, phase_pdf) * (Le / ds.pdf) * T  (:385-391, :419-423)
+        float pdf, le[3];
+        env_sample(P, xi1, xi2, wx, wy, wz, pdf, le);
+        worked = pdf != 0.0f;  // sampling_worked (:421-423): no shadow ray, no draws
+        const float mis = mis_power(pdf, UIVR_INV_4PI);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wgt[c] = worked ? ((beta[c] * UIVR_INV_4PI) * mis) * (le[c] / pdf) : 0.0f;
+    } else {
+        uniform_sphere(xi1, xi2, wx, wy, wz);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) wgt[c] = beta[c] * P.half_le[c];
+    }
     Seg s;
-    const bool valid = make_segment(P, px, py, pz, wx, wy, wz, s);
+    const bool valid = worked && make_segment(P, px, py, pz, wx, wy, wz, s);
     Rng clone = rng;
     const float T = valid ? ratio_track<false, COUNT>(P, s, rng, 0.0f, K) : 0.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) contrib[c] = (beta[c] * P.half_le[c]) * T;
+    for (int c = 0; c < 3; ++c) contrib[c] = wgt[c] * T;
     if (ADJ && valid) {
         const float asum = (dL[0] * contrib[0] + dL[1] * contrib[1]) + dL[2] * contrib[2];
         ratio_track<true, COUNT>(P, s, clone, asum, K);
@@ -240,9 +254,20 @@ UIVR_DEV void path_loop(const Params& P, Rng& rng, Rng& alt, Seg seg, int depth,
 
     // :263-285 envmap (primal only)
     if (!ADJ && escaped && !(depth <= 0 && P.hide_emitters)) {
-        const float wmis = (P.use_nee && has_scattered) ? 0.5f : 1.0f;
+        if (P.env_data) {
+            // :270-285 emitter.eval(si), hit_mis_weight = mis_weight(last_scatter_direction_pdf,
+            // has_scattered ? emitter.pdf_direction : 0)
+            float le[3], pdf;
+            env_eval(P, seg.dx, seg.dy, seg.dz, le, pdf);
+            float wmis = 1.0f;
+            if (P.use_nee) wmis = mis_power(has_scattered ? UIVR_INV_4PI : 1.0f, has_scattered ? pdf : 0.0f);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) R[c] = fmaf(beta[c] * wmis, P.radiance[c], R[c]);
+            for (int c = 0; c < 3; ++c) R[c] = R[c] + (beta[c] * wmis) * le[c];
+        } else {
+            const float wmis = (P.use_nee && has_scattered) ? 0.5f : 1.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[c] = fmaf(beta[c] * wmis, P.radiance[c], R[c]);
+        }
     }
 }
 

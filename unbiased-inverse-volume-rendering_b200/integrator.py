@@ -68,10 +68,13 @@ class Scene:
     def bind(self, sensor: Optional[Sensor], props: dict):
         vol = self.volume if sensor is None else self.volume.with_sensor(sensor)
         desc = vol.as_dict()
-        key = tuple((k, tuple(map(float, v.reshape(-1))) if hasattr(v, "reshape") else v) for k, v in sorted(desc.items()))
+        env_keys = ("env_data", "env_marg", "env_cond")  # big tables: keyed by identity of the EnvMap object
+        key = tuple((k, tuple(map(float, v.reshape(-1))) if hasattr(v, "reshape") else v)
+                    for k, v in sorted(desc.items()) if k not in env_keys) + (id(vol.envmap),)
         if key != self._scene_key:
             old_medium_inputs = None if self._scene_key is None else self._medium_inputs
             self.ctx.set_scene(desc)
+            self.ctx.set_envmap(desc)
             self._scene_key = key
             self._medium_inputs = (desc["res"], float(desc["scale"]), desc["majorant_factor"])
             if old_medium_inputs != self._medium_inputs:
