@@ -126,8 +126,8 @@ int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch);
  *                                the sampling density over [0,1]^2 of the bilinear patch (y, x)
  *   marg  [env_h - 1]            CDF over patch rows;   cond [env_h - 1][env_w]  per-row CDFs
  * Rotations are row-major 3x3; local_to_world is the linear part of the inverse of
- * uivr_scene_desc.to_local.  NULL returns to the constant emitter.  Envmap scenes are rendered by
- * the one-sample-per-lane kernels this round (the slot-pool kernels serve the constant emitter). */
+ * uivr_scene_desc.to_local.  NULL returns to the constant emitter.  The slot-pool kernels have
+ * envmap template instances; the constant-emitter instances are unaffected. */
 typedef struct {
     int32_t env_w, env_h;     /* resolution of the source image (H >= 2) */
     float   scale;

@@ -908,11 +908,12 @@ def _env_scene(uivr, n, w, h, factor):
     return sig, alb, vol
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("combo", ["volpathsimple-drt", "volpathsimple-basic", "volpathsimple-drt-quadratic"])
 def test_envmap_matches_oracle(uivr, oracle, dev, variant, combo):
-    """Envmap-lit scene: per-sample radiance and counters bit-exact, gradients to summation order
-    (whatever variant is selected, envmap scenes run on the one-sample-per-lane kernels)."""
+    """Envmap-lit scene: per-sample radiance and counters bit-exact, gradients to summation order,
+    on the slot-pool kernels (variants 2, 3: ENV template instances) and the one-sample-per-lane
+    kernels (variant 1; variant 0 has no envmap path and is routed there)."""
     n, spp = 24, 6
     sig, alb, vol = _env_scene(uivr, n, 40, 32, 4)
     props = dict(max_depth=6 if "quadratic" in combo else 24, **FLAG_COMBOS[combo])
@@ -953,13 +954,24 @@ def test_envmap_nerf_switching_and_errors(uivr, oracle, dev):
     _, smp_c, _ = oracle.nerf_forward(vol2.as_dict(), props, sig, em, 3, spp, want_samples=True)
     assert np.array_equal(smp.cpu().numpy().view(np.uint32), smp_c.view(np.uint32))
     assert not np.array_equal(smp_c, smp_o)
-    # ray batches of envmap-lit scenes: not offered for volpathsimple this round -> loud error
+    # ray batches of the envmap-lit scene through render_batch (slot-pool kernels, ENV instances)
     scene.volume = vol
     vps = uivr.get_int_config("volpathsimple-drt").create(max_depth=8)
-    p2 = {"m.sigma_t.data": params["m.sigma_t.data"], "m.albedo.data": params["m.emission.data"]}
-    vps.render(scene, p2, seed=1, spp=2)
-    with pytest.raises(uivr.NativeError, match="envmap"):
-        uivr.render_batch(64, scene, uivr.circle_sensors(3, 16, 16), p2, vps, seed=9, spp=2)
+    p2 = {"m.sigma_t.data": params["m.sigma_t.data"].clone().requires_grad_(True),
+          "m.albedo.data": params["m.emission.data"].clone().requires_grad_(True)}
+    sensors = uivr.circle_sensors(3, 16, 16)
+    B = 200
+    image, si, px = uivr.render_batch(B, scene, sensors, p2, vps, seed=9, spp=4, spp_grad=2)
+    tab = uivr.sensor_table(sensors)
+    img_bo, _, _ = oracle.render_batch_forward(desc, vps.props(), tab, (16, 16), B, sig, em, 9, 4)
+    assert np.max(np.abs(image.detach().cpu().numpy() - img_bo)) < IMAGE_TOL * max(1.0, float(img_bo.max()))
+    gb = (2.0 * (img_bo.astype(np.float64) - 0.5) / img_bo.size).astype(np.float32)
+    image.backward(_gpu(gb, dev))
+    torch.cuda.synchronize()
+    ds_bo, da_bo, _, _ = oracle.render_batch_backward(desc, vps.props(), tab, (16, 16), B, sig, em, gb, 9,
+                                                      uivr.tea32(9, 1), 2)
+    assert rel_linf(p2["m.sigma_t.data"].grad.cpu().numpy(), ds_bo) < GRAD_TOL
+    assert rel_linf(p2["m.albedo.data"].grad.cpu().numpy(), da_bo) < GRAD_TOL
     with pytest.raises(ValueError):
         import importlib
         importlib.import_module(uivr.__name__ + ".scene").EnvMap(np.zeros((4, 4, 3), np.float32)).tables()

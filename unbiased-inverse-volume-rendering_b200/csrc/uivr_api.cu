@@ -136,8 +136,6 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
         P.seed_offsets = uivr_tea32(ctx->batch.seed, 22);  // primal offsets; the backward entry switches to i = 2
     }
     if (ctx->env_on) {
-        if (ctx->batch_on && !ctx->nerf_call)
-            return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering of envmap-lit scenes is not available for volpathsimple yet");
         P.env_data = ctx->d_env_data;
         P.env_marg = ctx->d_env_marg;
         P.env_cond = ctx->d_env_cond;
@@ -451,7 +449,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
-    if (ctx->variant == 1 || ctx->env_on) {  // envmap scenes: one-sample-per-lane kernels (uivr_set_envmap)
+    if (ctx->variant == 1 || (ctx->env_on && !pool_ok(ctx))) {  // (the lane-refill megakernel has no envmap path)
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_forward_v1<true>, kBlock, &grid))) return rc;
             k_forward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -497,7 +495,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
     const bool quadratic = ctx->props.use_drt && !ctx->props.use_drt_subsampling;
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    if (ctx->variant == 1 || quadratic || ctx->env_on) {
+    if (ctx->variant == 1 || quadratic || (ctx->env_on && !pool_ok(ctx))) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);

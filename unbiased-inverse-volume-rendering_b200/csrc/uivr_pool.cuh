@@ -26,6 +26,7 @@
 #pragma once
 
 #include "uivr_kernels.cuh"
+#include "uivr_env.cuh"
 
 namespace uivr {
 
@@ -152,17 +153,20 @@ struct PoolCtl {
 enum : int { KIND_FWD = 0, KIND_BWD = 1, KIND_ADJ = 2, KIND_DRT = 3 };
 constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) alt seq(1) depth(1) pad(2)
 
-template <bool BWD, int NSLOT>
+// ENV (envmap emitter, uivr_env.cuh): three more fields per slot hold the NEE weight
+// throughput * phase * mis * Le / pdf of the direction sampled at Q_SPAWN until Q_NEE_END
+template <bool BWD, int NSLOT, bool ENV = false>
 constexpr size_t pool_smem_bytes() {
     return 128 + (size_t) Q_NUM * NSLOT * sizeof(unsigned) +
-           (size_t) (BWD ? F_NUM_BWD : F_NUM_FWD) * NSLOT * sizeof(uint32_t);
+           (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT * sizeof(uint32_t);
 }
 
 // BLOCK threads per CTA (one CTA per SM), of which the first HANDLERS warps serve the transition
 // queues and the rest walk
-template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS>
+template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS, bool ENV = false>
 __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     constexpr bool BWD = KIND != KIND_FWD;                            // any gradient work
+    constexpr int F_NW0 = BWD ? F_NUM_BWD : F_NUM_FWD;                // ENV only: NEE weight (3 words)
     constexpr bool HAS_PRIMAL = KIND == KIND_FWD || KIND == KIND_BWD; // sample(Primal) from the camera
     constexpr bool HAS_ADJ = KIND == KIND_BWD || KIND == KIND_ADJ;    // adjoint replay (reservoir, NEE adjoint)
     constexpr bool HAS_DRT = KIND == KIND_BWD || KIND == KIND_DRT;    // DRT walk, DRT vertex, recursive path
@@ -665,9 +669,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const int pass = (int) (fl & FL_PASS_MASK);
                     const float Tn = PF(F_T, s);
                     float contrib[3];
-                    contrib[0] = (PF(F_B0, s) * P.half_le[0]) * Tn;
-                    contrib[1] = (PF(F_B1, s) * P.half_le[1]) * Tn;
-                    contrib[2] = (PF(F_B2, s) * P.half_le[2]) * Tn;
+                    if (ENV) {
+                        contrib[0] = PF(F_NW0 + 0, s) * Tn;
+                        contrib[1] = PF(F_NW0 + 1, s) * Tn;
+                        contrib[2] = PF(F_NW0 + 2, s) * Tn;
+                    } else {
+                        contrib[0] = (PF(F_B0, s) * P.half_le[0]) * Tn;
+                        contrib[1] = (PF(F_B1, s) * P.half_le[1]) * Tn;
+                        contrib[2] = (PF(F_B2, s) * P.half_le[2]) * Tn;
+                    }
                     next = Q_SPAWN;
                     if (HAS_DRT && pass == PP_DRTV) {
                         PSET(F_LI0, s, contrib[0]); PSET(F_LI1, s, contrib[1]); PSET(F_LI2, s, contrib[2]);
@@ -702,9 +712,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (pass == PP_PRIMAL || (HAS_DRT && pass == PP_REC)) {
                         // :263-285 envmap
                         if ((fl & FL_ESCAPED) && !(depth <= 0 && P.hide_emitters)) {
-                            const float wmis = (P.use_nee && (fl & FL_HAS_SCATTERED)) ? 0.5f : 1.0f;
+                            if (ENV) {
+                                // emitter.eval(si) with hit_mis_weight (:270-285); the slot still holds the last segment
+                                float le[3], pdf;
+                                env_eval(P, PF(F_DX, s), PF(F_DY, s), PF(F_DZ, s), le, pdf);
+                                const bool hs = (fl & FL_HAS_SCATTERED) != 0u;
+                                float wmis = 1.0f;
+                                if (P.use_nee) wmis = mis_power(hs ? UIVR_INV_4PI : 1.0f, hs ? pdf : 0.0f);
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) R[c] = fmaf(PF(F_B0 + c, s) * wmis, P.radiance[c], R[c]);
+                                for (int c = 0; c < 3; ++c) R[c] = R[c] + (PF(F_B0 + c, s) * wmis) * le[c];
+                            } else {
+                                const float wmis = (P.use_nee && (fl & FL_HAS_SCATTERED)) ? 0.5f : 1.0f;
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) R[c] = fmaf(PF(F_B0 + c, s) * wmis, P.radiance[c], R[c]);
+                            }
                         }
                     }
                     next = Q_FREE;
@@ -797,9 +818,21 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (phase) draw(r, K);
                     const float xi1 = draw(r, K), xi2 = draw(r, K);
                     float wx, wy, wz;
-                    uniform_sphere(xi1, xi2, wx, wy, wz);
+                    bool worked = true;
+                    if (ENV && !phase) {
+                        // scene.sample_emitter_direction on the envmap; the NEE weight waits in the slot (:385-391, :419-423)
+                        float pdf, le[3];
+                        env_sample(P, xi1, xi2, wx, wy, wz, pdf, le);
+                        worked = pdf != 0.0f;
+                        const float mis = mis_power(pdf, UIVR_INV_4PI);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            PSET(F_NW0 + c, s, worked ? ((PF(F_B0 + c, s) * UIVR_INV_4PI) * mis) * (le[c] / pdf) : 0.0f);
+                    } else {
+                        uniform_sphere(xi1, xi2, wx, wy, wz);
+                    }
                     Seg sg;
-                    const bool ok = make_segment(P, PF(F_VPX, s), PF(F_VPY, s), PF(F_VPZ, s), wx, wy, wz, sg);
+                    const bool ok = make_segment(P, PF(F_VPX, s), PF(F_VPY, s), PF(F_VPZ, s), wx, wy, wz, sg) && worked;
                     PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
                     PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
                     PSET(F_TMAX, s, sg.tmax);
@@ -970,8 +1003,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             // the ray misses the medium: finish the sample right here
                             float R[3] = {0.0f, 0.0f, 0.0f};
                             if (escaped && !P.hide_emitters) {
+                                if (ENV) {
+                                    float pdf;
+                                    env_eval(P, sg.dx, sg.dy, sg.dz, R, pdf);  // no scattering: MIS weight 1
+                                } else {
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                                    for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                                }
                             }
                             if (P.sample_L) {
                                 P.sample_L[3 * (size_t) idx + 0] = R[0];
@@ -1043,16 +1081,21 @@ constexpr int kPoolSlotsFwd = UIVR_POOL_SLOTS_FWD;
 // kind: KIND_FWD / KIND_BWD / KIND_ADJ / KIND_DRT
 inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
-#define UIVR_POOL_LAUNCH(KD, C, N, T, H)                                                                \
+    const bool env = P.env_data != nullptr;
+#define UIVR_POOL_LAUNCH(KD, C, N, T, H, E)                                                             \
     do {                                                                                                \
-        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N>();                                     \
-        e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N, E>();                                  \
+        e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
-        k_pool<KD, C, N, T, H><<<num_sms, T, smem, st>>>(P);                                            \
+        k_pool<KD, C, N, T, H, E><<<num_sms, T, smem, st>>>(P);                                         \
     } while (0)
 #define UIVR_POOL_LAUNCH2(KD, N, T, H)                                                                  \
     do {                                                                                                \
-        if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H); else UIVR_POOL_LAUNCH(KD, false, N, T, H);   \
+        if (env) {                                                                                      \
+            if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H, true); else UIVR_POOL_LAUNCH(KD, false, N, T, H, true); \
+        } else {                                                                                        \
+            if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H, false); else UIVR_POOL_LAUNCH(KD, false, N, T, H, false); \
+        }                                                                                               \
     } while (0)
     switch (kind) {
         case KIND_FWD: UIVR_POOL_LAUNCH2(KIND_FWD, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD); break;
