@@ -26,3 +26,28 @@ image.mean().backward()
 torch.cuda.synchronize()
 scene.ctx.check_watchdog()
 print("batch", float(image.mean()), float(p2["m.sigma_t.data"].grad.abs().sum()))
+# nerf integrator + envmap emitter (slot-pool ENV instances, one-sample-per-lane kernels, nerf kernels)
+from importlib import import_module
+S = import_module(u.__name__ + ".scene")
+rng = np.random.default_rng(0)
+envimg = (rng.random((17, 32, 3)) ** 3).astype(np.float32)
+envimg[4, 7] = (50.0, 40.0, 30.0)
+vol_e = u.benchmark_scene(n, w, h, scale=8.0, majorant_resolution_factor=4)
+vol_e.envmap = S.EnvMap(envimg, scale=0.8)
+for variant in (3, 2, 1):
+    scene = u.Scene(vol_e, 0)
+    scene.ctx.set_variant(variant)
+    img = integ.render(scene, params, seed=1, spp=spp)
+    g = 2 * (img - 0.5) / img.numel()
+    ds, da = integ.render_backward(scene, params, g, seed=2, spp=spp)
+    torch.cuda.synchronize()
+    scene.ctx.check_watchdog()
+    print("envmap variant", variant, float(img.mean()), float(ds.abs().sum()), float(da.abs().sum()))
+nerf = u.get_int_config("nerf").create(max_depth=4, queries_per_ray=48)
+pn = {"m.sigma_t.data": params["m.sigma_t.data"], "m.emission.data": params["m.albedo.data"]}
+for v in (vol, vol_e):
+    scene = u.Scene(v, 0)
+    img = nerf.render(scene, pn, seed=1, spp=spp)
+    ds, de = nerf.render_backward(scene, pn, 2 * (img - 0.5) / img.numel(), seed=2, spp=spp)
+    torch.cuda.synchronize()
+    print("nerf", "envmap" if v.envmap is not None else "constant", float(img.mean()), float(ds.abs().sum()), float(de.abs().sum()))

@@ -85,6 +85,14 @@ class EnvMap:
     to_world: Tuple[Tuple[float, float, float], ...] = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
 
     def tables(self) -> Dict[str, object]:
+        """Built once per EnvMap object (the image is treated as immutable)."""
+        cached = getattr(self, "_tables", None)
+        if cached is None:
+            cached = self._build_tables()
+            object.__setattr__(self, "_tables", cached)
+        return cached
+
+    def _build_tables(self) -> Dict[str, object]:
         img = np.asarray(self.image, dtype=np.float64)
         if img.ndim != 3 or img.shape[2] != 3 or img.shape[0] < 2 or img.shape[1] < 1:
             raise ValueError("envmap image must have shape (H >= 2, W >= 1, 3)")
