@@ -829,27 +829,33 @@ def test_nerf_autograd_sharding_and_batch(uivr, oracle, dev):
     B, bseed = 300, 2024
     batch = (tab, (20, 14), B, bseed)
     img_bo, smp_bo, _ = oracle.nerf_forward(desc, props, sig, em, bseed, spp, batch=batch, want_samples=True)
+    pb = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    image_b, si, px = uivr.render_batch(B, scene, sensors, pb, integ, seed=bseed, spp=spp)
+    assert np.max(np.abs(image_b.detach().cpu().numpy() - img_bo)) < IMAGE_TOL
+    gb = (2.0 * (img_bo.astype(np.float64) - 0.5) / img_bo.size).astype(np.float32)
+    image_b.backward(_gpu(gb, dev))
+    torch.cuda.synchronize()
+    ds_bo, de_bo, _, _ = oracle.nerf_backward(desc, props, sig, em, gb, uivr.tea32(bseed, 1), spp, batch=batch)
+    assert rel_linf(pb["m.sigma_t.data"].grad.cpu().numpy(), ds_bo) < GRAD_TOL
+    assert rel_linf(pb["m.emission.data"].grad.cpu().numpy(), de_bo) < GRAD_TOL
+    # per-sample bits in batch mode, straight through the C-ABI
     scene.ctx.set_batch(tab, 20, 14, B, bseed)
     try:
         img_b = torch.empty((B, 3), device=dev)
         smp_b = torch.zeros((B * spp, 3), device=dev)
-        np_props = integ.props()
-        scene.ctx.nerf_forward(np_props, p["m.emission.data"].data_ptr(), bseed, spp, img_b.data_ptr(), smp_b.data_ptr())
+        scene.ctx.nerf_forward(integ.props(), p["m.emission.data"].data_ptr(), bseed, spp, img_b.data_ptr(), smp_b.data_ptr())
         torch.cuda.synchronize()
         assert np.array_equal(smp_b.cpu().numpy().view(np.uint32), smp_bo.view(np.uint32))
-        assert np.max(np.abs(img_b.cpu().numpy() - img_bo)) < IMAGE_TOL
-        gb = (2.0 * (img_bo.astype(np.float64) - 0.5) / img_bo.size).astype(np.float32)
-        sg = uivr.tea32(bseed, 1)
-        ds_bo, de_bo, _, _ = oracle.nerf_backward(desc, props, sig, em, gb, sg, spp, batch=batch)
-        ds_b, de_b = torch.empty_like(p["m.sigma_t.data"]), torch.empty_like(p["m.emission.data"])
-        dgb = _gpu(gb, dev)
-        scene.ctx.nerf_backward(np_props, p["m.emission.data"].data_ptr(), dgb.data_ptr(), sg, spp,
-                                ds_b.data_ptr(), de_b.data_ptr())
-        torch.cuda.synchronize()
-        assert rel_linf(ds_b.cpu().numpy(), ds_bo) < GRAD_TOL
-        assert rel_linf(de_b.cpu().numpy(), de_bo) < GRAD_TOL
     finally:
         scene.ctx.set_batch(None)
+    # one optimisation step of the multi-view loop with the nerf integrator (warm start of the reference)
+    opt = uivr.Adam(5e-2, {k: v.clone() for k, v in p.items()})
+    views = uivr.circle_sensors(2, 32, 24)
+    refs = [integ.render(scene, p, sensor=s_, seed=50 + i, spp=spp) * 0.5 for i, s_ in enumerate(views)]
+    l0 = uivr.optimization_step(scene, integ, opt, views, refs, 0, spp)
+    for it in range(1, 6):
+        l1 = uivr.optimization_step(scene, integ, opt, views, refs, it, spp)
+    assert l1 < l0
 
 
 def test_nerf_matches_reference_vectors(uivr, dev):
@@ -996,3 +1002,61 @@ def test_envmap_matches_reference_vectors(uivr, dev):
         assert np.max(np.abs(smp_g - g[f"{key}/samples_grad_pass"])) < REFSHIM_SAMPLE_TOL * scale, key
         assert rel_linf(ds, g[f"{key}/dsigma"]) < REFSHIM_GRAD_TOL, key
         assert rel_linf(da, g[f"{key}/dalbedo"]) < REFSHIM_GRAD_TOL, key
+
+
+# ---------------------------------------------------------------------------------------
+# randomized sweep + geometric edge cases
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", range(16))
+def test_randomized_parity_sweep(uivr, oracle, dev, case):
+    """Seeded random scenes (anisotropic grid / box, any film, camera, supergrid factor, flag set,
+    emitter, kernel variant): per-sample radiance and counters bit-exact, gradients < 1e-3."""
+    from helpers import random_case
+    c = random_case(uivr, case)
+    vol, sig, alb, props, spp = c["vol"], c["sig"], c["alb"], c["props"], c["spp"]
+    desc = vol.as_dict()
+    img_o, smp_o, cnt_o = oracle.render_forward(desc, props, sig, alb, c["seed"], spp, want_samples=True)
+    img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, c["seed"], spp, dev, c["variant"])
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32)), (case, props)
+    assert cnt_g == cnt_o
+    gimg = loss_grad(img_o)
+    ds_o, da_o, smp_bo, cnt_bo = oracle.render_backward(desc, props, sig, alb, gimg, c["seed_grad"], spp, want_samples=True)
+    ds_g, da_g, smp_bg, cnt_bg = _run_backward(uivr, vol, props, sig, alb, gimg, c["seed_grad"], spp, dev, c["variant"])
+    assert np.array_equal(smp_bg.view(np.uint32), smp_bo.view(np.uint32)), (case, props)
+    assert cnt_bg == cnt_bo
+    if np.abs(ds_o).max() > 0:
+        assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    if np.abs(da_o).max() > 0:
+        assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_camera_inside_and_grazing(uivr, oracle, dev, variant):
+    """reach_medium corner cases (volpathsimple.py:292-319): a sensor inside the medium box (the first
+    hit is the far wall and the re-spawned ray misses: every sample dies) and a sensor looking along a
+    box face from outside (grazing rays, zero direction components)."""
+    n = 8
+    sig, alb = hetero_grids(n, seed=2)
+    props = dict(max_depth=8)
+    for sensor in (uivr.Sensor(origin=(0.5, 0.5, 0.5), target=(2.0, 0.6, 0.4), width=12, height=9),
+                   uivr.Sensor(origin=(-3.0, 1.5, 0.5), target=(1.0, 1.5, 0.5), fov=40.0, width=16, height=16),
+                   uivr.Sensor(origin=(0.5, 5.0, 0.5), target=(0.5, 0.0, 0.5), up=(1.0, 0.0, 0.0), width=9, height=9)):
+        vol = uivr.VolumeScene(res=(n, n, n), sensor=sensor, scale=6.0, majorant_resolution_factor=2)
+        desc = vol.as_dict()
+        img_o, smp_o, cnt_o = oracle.render_forward(desc, props, sig, alb, 3, 4, want_samples=True)
+        img_g, smp_g, cnt_g = _run_forward(uivr, vol, props, sig, alb, 3, 4, dev, variant)
+        assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+        assert cnt_g == cnt_o
+        ds_o, da_o, _, cnt_bo = oracle.render_backward(desc, props, sig, alb, np.ones_like(img_o), 4, 4)
+        ds_g, da_g, _, cnt_bg = _run_backward(uivr, vol, props, sig, alb, np.ones_like(img_o), 4, 4, dev, variant)
+        assert cnt_bg == cnt_bo
+        if np.abs(ds_o).max() > 0:
+            assert rel_linf(ds_g, ds_o) < GRAD_TOL
+        else:
+            assert np.abs(ds_g).max() == 0
+    # the sensor inside the box produced a black image (status "dead", not "escaped")
+    vol = uivr.VolumeScene(res=(n, n, n), sensor=uivr.Sensor(origin=(0.5, 0.5, 0.5), target=(2.0, 0.6, 0.4), width=12, height=9),
+                           scale=6.0, majorant_resolution_factor=2)
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 3, 4)
+    assert img.max() == 0.0

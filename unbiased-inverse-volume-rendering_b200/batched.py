@@ -22,7 +22,8 @@ import numpy as np
 import torch
 
 from . import _native
-from .integrator import ALBEDO_SUFFIX, SIGMA_T_SUFFIX, Scene, VolpathSimpleIntegrator, _find_key, _stream
+from .integrator import (ALBEDO_SUFFIX, SIGMA_T_SUFFIX, NeRFIntegrator, Scene, VolpathSimpleIntegrator, _find_key,
+                         _stream)
 from .scene import Sensor
 
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -123,22 +124,31 @@ class _BatchedRenderOp(torch.autograd.Function):
 
 def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, seed, spp, grad_image, sample_out):
     table, film_size, batch_size, batch_seed = batch
-    sig, alb = scene.check_params(params)
-    scene.bind(None, integrator.props())
+    nerf = isinstance(integrator, NeRFIntegrator)  # render_batch takes any registered integrator (batched.py:110-112)
+    sig, alb = scene.check_params(params, integrator.second_suffix)
+    props = integrator.props()
+    scene.bind(None, None if nerf else props)
     scene.update_medium(sig.detach())
     scene.ctx.set_batch(table, film_size[0], film_size[1], batch_size, batch_seed)
     try:
         sp = None if sample_out is None else sample_out.data_ptr()
         if grad_image is None:
             image = torch.empty((batch_size, 3), dtype=torch.float32, device=sig.device)
-            scene.ctx.render_forward(alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, None, _stream())
+            if nerf:
+                scene.ctx.nerf_forward(props, alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, None, _stream())
+            else:
+                scene.ctx.render_forward(alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, None, _stream())
             return image
         g = grad_image.to(dtype=torch.float32).contiguous()
         if tuple(g.shape) != (batch_size, 3):
             raise ValueError(f"grad_in must have shape {(batch_size, 3)}")
         dsig, dalb = torch.empty_like(sig), torch.empty_like(alb)
-        scene.ctx.render_backward(alb.detach().data_ptr(), g.data_ptr(), seed, spp, dsig.data_ptr(), dalb.data_ptr(),
-                                  sp, None, _stream())
+        if nerf:
+            scene.ctx.nerf_backward(props, alb.detach().data_ptr(), g.data_ptr(), seed, spp, dsig.data_ptr(),
+                                    dalb.data_ptr(), sp, None, _stream())
+        else:
+            scene.ctx.render_backward(alb.detach().data_ptr(), g.data_ptr(), seed, spp, dsig.data_ptr(),
+                                      dalb.data_ptr(), sp, None, _stream())
         return dsig, dalb
     finally:
         scene.ctx.set_batch(None)
@@ -162,7 +172,7 @@ def render_batch(batch_size: int, scene: Scene, sensors: Sequence[Sensor], param
     film_size = (sensors[0].width, sensors[0].height)
     table = sensor_table(sensors)
     sensor_idx, pixels = sample_batch_pixels(batch_size, len(sensors), film_size, seed)
-    k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, ALBEDO_SUFFIX)
+    k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, integrator.second_suffix)
     batch = (table, film_size, int(batch_size), seed & 0xFFFFFFFF)
     image = _BatchedRenderOp.apply(params[k_sig], params[k_alb], scene, integrator, batch, seed, seed_grad,
                                    spp, spp_grad, (k_sig, k_alb))

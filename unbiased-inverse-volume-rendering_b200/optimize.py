@@ -119,7 +119,7 @@ def optimization_step(scene: Scene, integrator: VolpathSimpleIntegrator, opt: Ad
     """Loop body of run_optimization (optimize.py:325-354) over the given views.  Returns the mean loss."""
     params = opt.params
     k_sig = next(k for k in params if k.endswith(SIGMA_T_SUFFIX))
-    k_alb = next(k for k in params if k.endswith(ALBEDO_SUFFIX))
+    k_alb = next(k for k in params if k.endswith(integrator.second_suffix))  # albedo, or emission for `nerf`
     spp_grad = spp_grad or spp
     if grads is None:
         grads = {k: torch.zeros_like(p) for k, p in params.items()}
