@@ -1060,3 +1060,66 @@ def test_camera_inside_and_grazing(uivr, oracle, dev, variant):
                            scale=6.0, majorant_resolution_factor=2)
     img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 3, 4)
     assert img.max() == 0.0
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own gradient tests, through the drop-in surface (tests/test_integrators.py)
+# ---------------------------------------------------------------------------------------
+
+def _loss_fn(image):
+    # tests/test_integrators.py:119-120; accumulated in float64 so that forward differences of
+    # ~1e-8 are not lost in the float32 rounding of a loss of ~0.1
+    return ((image.double() - 0.5) ** 2).mean()
+
+
+def test_02_nerf_correctness(uivr, dev):
+    """tests/test_integrators.py:155-218 -- the one gradient assertion the reference's suite keeps
+    enabled: finite differences (eps 5e-3, spp 32) vs path-replay gradients (spp 4) of the default
+    `nerf` integrator on `cube_test_scene`, same thresholds (rtol 3e-2 with at most 3 bad entries per
+    channel, rtol 0.75 on all)."""
+    sig, em = uivr.cube_test_grids()                       # emission grid == albedo grid of the fixture (:30-37)
+    scene = uivr.Scene(uivr.cube_test_scene(), device=0)   # 128 x 128, density_scale 1
+    integrator = uivr.load_dict({"type": "nerf"})
+    params = {"cube.interior_medium.sigma_t.data": _gpu(sig, dev), "cube.interior_medium.emission.data": _gpu(em, dev)}
+    fd = uivr.fd_gradients(scene, params, _loss_fn, eps=5e-3, spp=32, integrator=integrator)
+    for v in params.values():
+        v.requires_grad_(True)
+    img = uivr.render(scene, params, integrator, seed=1234, spp=4)
+    _loss_fn(img).backward()
+    rb = {k: v.grad.cpu().numpy() for k, v in params.items()}
+    rtol = 3e-2
+    for k, g in rb.items():
+        for c in range(g.shape[-1]):
+            a, b = g[..., c], fd[k][..., c]
+            bad = int(np.sum(np.abs(a - b) >= rtol * np.abs(b)))
+            assert bad <= 3, (k, c, bad)
+            assert np.allclose(a, b, rtol=0.75), (k, c)
+
+
+@pytest.mark.parametrize("config", ["volpathsimple-basic", "volpathsimple-drt"])
+def test_04_volpathsimple_gradients_vs_fd(uivr, dev, config):
+    """tests/test_integrators.py:262-347 (the reference disables its final assertion, :343-347): FD
+    through the `fd-forward` configuration vs the adjoint of the configuration under test on
+    `cube_test_scene(density_scale=2)`.  Both sides are Monte Carlo here, so the bar is statistical:
+    relative L2 distance of the gradient tensors (looser for the free-flight estimator, whose
+    1/sigma_t factor is the variance problem DRT removes, volpathsimple.py:159-161)."""
+    sig, alb = uivr.cube_test_grids()
+    scene = uivr.Scene(uivr.cube_test_scene(64, 64, density_scale=2.0), device=0)
+    fd_cfg = uivr.get_int_config("fd-forward")
+    assert fd_cfg.uses_fd and fd_cfg.fd_epsilon == 5e-3
+    keys = ("cube.interior_medium.sigma_t.data", "cube.interior_medium.albedo.data")
+    params = {keys[0]: _gpu(sig, dev), keys[1]: _gpu(alb, dev)}
+    spp = 1024
+    fd = uivr.fd_gradients(scene, params, _loss_fn, eps=fd_cfg.fd_epsilon * 4, spp=spp * fd_cfg.fd_spp_multiplier,
+                           integrator=fd_cfg.create(max_depth=16))
+    integ = uivr.get_int_config(config).create(max_depth=16)
+    acc = {k: np.zeros(tuple(v.shape)) for k, v in params.items()}
+    reps = 8 if "drt" in config else 16
+    for r in range(reps):
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        _loss_fn(uivr.render(scene, p, integ, seed=1234 + 7 * r, spp=spp)).backward()
+        for k in p:
+            acc[k] += p[k].grad.cpu().numpy() / reps
+    for k in keys:
+        num = np.linalg.norm(acc[k] - fd[k]) / np.linalg.norm(fd[k])
+        assert num < (0.15 if "drt" in config else 0.4), (config, k, num)

@@ -8,6 +8,7 @@ from .opt_config import IntegratorConfig, add_int_config, get_int_config
 from .batched import gather_ref_values, render_batch, sample_batch_pixels, sensor_table
 from .multires import (adjust_majorant_res_factor, read_vol, save_params, upsample_grid, upsample_iterations,
                        upsample_params, write_vol)
+from .fd import fd_gradients
 from .optimize import Adam, l1_loss_grad, learning_rates, optimization_step, param_bounds
 from .scene import (Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_test_grids,
                     cube_test_scene, look_at, synthetic_grids)
@@ -20,5 +21,5 @@ __all__ = [
     "gather_ref_values", "render_batch", "sample_batch_pixels", "sensor_table",
     "adjust_majorant_res_factor", "read_vol", "save_params", "upsample_grid", "upsample_iterations",
     "upsample_params", "write_vol",
-    "Adam", "l1_loss_grad", "learning_rates", "optimization_step", "param_bounds",
+    "fd_gradients", "Adam", "l1_loss_grad", "learning_rates", "optimization_step", "param_bounds",
 ]
