@@ -44,7 +44,6 @@ struct uivr_ctx {
     int d_sensors_cap = 0;
     // envmap emitter (uivr_set_envmap)
     bool env_on = false;
-    bool nerf_call = false;  // fill_params is serving a uivr_nerf_* entry point
     uivr_envmap_desc env{};
     float4* d_env_data = nullptr;
     float* d_env_marg = nullptr;
@@ -93,7 +92,7 @@ bool pool_ok(const uivr_ctx* ctx) {
            ctx->mres[2] <= 512;
 }
 
-int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed, int32_t spp) {
+int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed, int32_t spp, bool volpath = true) {
     const uivr_scene_desc& s = ctx->scene;
     const uivr_integrator_props& ip = ctx->props;
     if (spp < 1) return fail(ctx, UIVR_ERR_INVALID, "spp must be >= 1");
@@ -127,7 +126,8 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.inv_w = 1.0f / (float) P.width;
     P.inv_h = 1.0f / (float) P.height;
     if (ctx->batch_on) {
-        if (!pool_ok(ctx)) return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering needs the slot-pool kernels (variant >= 2)");
+        if (volpath && !pool_ok(ctx))
+            return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering needs the slot-pool kernels (variant >= 2)");
         P.sensors = ctx->d_sensors;
         P.n_sensors = ctx->batch.n_sensors;
         P.film_w = ctx->batch.film_w;
@@ -561,9 +561,7 @@ static int nerf_params(uivr_ctx* ctx, const uivr_nerf_props* np, Params& P, cons
     if (np->queries_per_ray < 2) return fail(ctx, UIVR_ERR_INVALID, "queries_per_ray must be >= 2");
     if (np->activation != UIVR_NERF_IDENTITY && np->activation != UIVR_NERF_RELU)
         return fail(ctx, UIVR_ERR_INVALID, "Unsupported activation (nerf.py:44)");
-    ctx->nerf_call = true;
-    const int rc = fill_params(ctx, P, shard, seed, spp);
-    ctx->nerf_call = false;
+    const int rc = fill_params(ctx, P, shard, seed, spp, false);
     if (rc) return rc;
     P.nerf_queries = np->queries_per_ray;
     P.nerf_jitter = np->jittering_enabled ? 1 : 0;
