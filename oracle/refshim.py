@@ -519,6 +519,11 @@ class Color3f(Vec):
     __slots__ = ()
 
 
+class Vector4f(Vec):
+    N = 4
+    __slots__ = ()
+
+
 class Vec2(Vec):
     N = 2
     __slots__ = ()
@@ -750,6 +755,8 @@ class _Ptr:
 def width(x) -> int:
     if isinstance(x, SensorPtr):
         return len(x.index)
+    if isinstance(x, Tensor):
+        return int(x.v.size)
     leaves: List = []
     _flatten(x, leaves)
     return max([len(l.v) for l in leaves], default=1)
@@ -802,6 +809,8 @@ sqr = _lift(lambda a: _F(a) * _F(a))
 
 def _minmax(fn):
     def g(a, b):
+        if isinstance(a, Tensor) or isinstance(b, Tensor):
+            return Tensor(fn(a.v if isinstance(a, Tensor) else F32(a), b.v if isinstance(b, Tensor) else F32(b)))
         if isinstance(a, Vec) or isinstance(b, Vec):
             proto = a if isinstance(a, Vec) else b
             ac = a.c if isinstance(a, Vec) else [a] * proto.N
@@ -829,6 +838,36 @@ maximum = _minmax(np.maximum)
 
 def exp(a):
     return _un(a, np.exp, lambda v: np.exp(v))
+
+
+def clip(v, lo, hi):
+    return Tensor(np.minimum(np.maximum(v.v, F32(lo)), F32(hi))) if isinstance(v, Tensor) else minimum(maximum(v, lo), hi)
+
+
+def shape(x):
+    return x.shape
+
+
+def prod(x):
+    return int(np.prod(x)) if len(x) else 1
+
+
+def hmin(x):
+    return min(x) if isinstance(x, (tuple, list)) else _raw(np.minimum(np.minimum(x.c[0].v, x.c[1].v), x.c[2].v))
+
+
+def ravel(x):
+    if isinstance(x, Vec):
+        return _raw(np.ascontiguousarray(x.numpy()).reshape(-1))
+    return x.array if isinstance(x, Tensor) else x
+
+
+def hsum(x):
+    return Tensor(np.asarray(x.v, dtype=F64).sum().astype(F32).reshape(1)) if isinstance(x, Tensor) else x
+
+
+def habs(x):
+    return Tensor(np.abs(x.v)) if isinstance(x, Tensor) else _un(x, np.abs, lambda v: np.sign(v))
 
 
 def hmax(a):
@@ -896,6 +935,8 @@ def detach(x, preserve_type=True):
         for f in r.FIELDS:
             object.__setattr__(r, f, detach(getattr(r, f)))
         return r
+    if isinstance(x, Tensor):
+        return Tensor(x)
     return x
 
 
@@ -921,6 +962,10 @@ def gather(T, src, idx, active=True):
         return SensorPtr(src.frames, src.index[i])
     if isinstance(src, VecU):
         return VecU(UInt32(src.c[0].v[i]), UInt32(src.c[1].v[i]))
+    if isinstance(src, Float) and isinstance(T, type) and issubclass(T, Vec):
+        r = T.__new__(T)
+        r.c = [Float(src.v[i * T.N + c]) for c in range(T.N)]  # N consecutive entries per index
+        return r
     if isinstance(src, Vec):
         r = type(src).__new__(type(src))
         r.c = [Float(t.v[i]) for t in src.c]
@@ -1084,7 +1129,7 @@ def _make_drjit():
     m = types.ModuleType("drjit")
     m.__dict__.update(dict(
         ADMode=ADMode, width=width, select=select, rcp=rcp, sqr=sqr, minimum=minimum, maximum=maximum,
-        max=hmax, mean=mean, exp=exp, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
+        max=hmax, mean=mean, exp=exp, clip=clip, shape=shape, prod=prod, min=hmin, ravel=ravel, sum=hsum, abs=habs, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
         zeros=zeros, empty=empty, full=full, arange=arange, gather=gather, resume_grad=resume_grad,
         suspend_grad=suspend_grad, backward_from=backward_from, enable_grad=enable_grad, grad=grad,
         set_grad=set_grad, enqueue=enqueue, traverse=traverse, CustomOp=CustomOp, custom=custom,
@@ -1272,8 +1317,16 @@ class _SigmaLeaf:
 class Medium:
     """heterogeneous medium: sigma_t = scale * grid, albedo grid, majorant supergrid"""
 
+    _majorant_resolution_factor = 0
+
     def phase_function(self):
         return PhaseFunctionPtr(True)
+
+    def majorant_resolution_factor(self):
+        return Medium._majorant_resolution_factor
+
+    def set_majorant_resolution_factor(self, f):
+        Medium._majorant_resolution_factor = int(f)
 
     @staticmethod
     def _points(p: Vec, mask):
@@ -1496,11 +1549,30 @@ def _camera_rays(frames, idx, u, v):
 # ---- film (box filter, weight channel), only what batched.py drives -------------------
 
 class Tensor:
-    def __init__(self, v):
-        self.v = v
+    """mi.TensorXf: an n-d float32 array (host numpy here)"""
+
+    def __init__(self, v, shape=None):
+        if isinstance(v, Tensor):
+            v = v.v
+        elif isinstance(v, Float):
+            v = v.v
+        self.v = np.array(v, dtype=F32)
+        if shape is not None:
+            self.v = self.v.reshape(tuple(int(x) for x in shape))
+
+    shape = property(lambda s: tuple(int(x) for x in s.v.shape))
+    array = property(lambda s: _raw(np.ascontiguousarray(s.v).reshape(-1)))
 
     def numpy(self):
         return self.v
+
+    def _bin(self, o, f):
+        return Tensor(f(self.v, o.v if isinstance(o, Tensor) else o))
+
+    def __sub__(self, o): return self._bin(o, np.subtract)
+    def __add__(self, o): return self._bin(o, np.add)
+    def __mul__(self, o): return self._bin(o, np.multiply)
+    def __truediv__(self, o): return self._bin(o, np.divide)
 
 
 class ImageBlock:
@@ -1642,7 +1714,7 @@ def _make_mitsuba():
     ns = types.SimpleNamespace
     m.__dict__.update(dict(
         Float=Float, Int32=Int32, UInt32=UInt32, Mask=Mask, Bool=Mask, Spectrum=Color3f, Color3f=Color3f,
-        Vector3f=Vector3f, Point3f=Point3f, Point2f=Point2f, Vector2f=Vector2f, Point2u=VecU,
+        Vector3f=Vector3f, Vector4f=Vector4f, Point3f=Point3f, Point2f=Point2f, Vector2f=Vector2f, Point2u=VecU,
         ScalarVector2u=ScalarVector2, ScalarVector2f=ScalarVector2,
         Ray3f=Ray3f, RayDifferential3f=Ray3f, Interaction3f=Interaction3f,
         SurfaceInteraction3f=SurfaceInteraction3f, MediumInteraction3f=MediumInteraction3f,
@@ -1677,7 +1749,7 @@ def load_reference(ref_root: str = REF_ROOT):
         return _ref
     if not available(ref_root):
         raise FileNotFoundError(f"reference sources not found under {ref_root}")
-    names = ("drjit", "mitsuba", "util", "losses", "opt_config", "batched")
+    names = ("drjit", "mitsuba", "util", "losses", "opt_config", "batched", "optimize")
     saved = {k: sys.modules.pop(k, None) for k in names}
     sys.modules["drjit"] = _make_drjit()
     sys.modules["mitsuba"] = _make_mitsuba()
@@ -1688,7 +1760,8 @@ def load_reference(ref_root: str = REF_ROOT):
     try:
         mods = {}
         for name, rel in (("volpathsimple", "integrators/volpathsimple.py"), ("nerf", "integrators/nerf.py"),
-                          ("batched", "batched.py"), ("opt_config", "opt_config.py")):
+                          ("batched", "batched.py"), ("opt_config", "opt_config.py"), ("optimize", "optimize.py"),
+                          ("losses", "losses.py")):
             spec = importlib.util.spec_from_file_location("refshim_ref_" + name, os.path.join(pydir, rel))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)

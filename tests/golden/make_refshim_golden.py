@@ -80,6 +80,51 @@ def run_envmap():
     return out
 
 
+def run_host():
+    """Host-side functions of python/optimize.py, python/opt_config.py and python/losses.py, run unmodified."""
+    import types
+    ref = R.load_reference()
+    oc, opt_mod = ref.opt_config, ref.optimize
+    keys = ["m.sigma_t.data", "m.albedo.data", "m.emission.data"]
+    sc = types.SimpleNamespace(param_lr_factors={"m.albedo.data": 2.0}, param_keys=keys, max_density=250.0,
+                               majorant_resolution_factor=8)
+    out = {}
+    for name, sched in (("last25", oc.Schedule.Last25), ("constant", oc.Schedule.Constant), ("none", None)):
+        cfg = oc.OptimizationConfig("x", spp=4, n_iter=101, lr=5e-3, lr_schedule=sched)
+        out[f"lr/{name}"] = np.array([[cfg.learning_rates(sc, it)[k] for k in keys] for it in range(101)])
+    for i, (ups, n_iter) in enumerate((([0.25, 0.5, 0.75], 101), ([0.0, 1.0, 0.333], 3000), (None, 10))):
+        cfg = oc.OptimizationConfig("x", spp=4, n_iter=n_iter, lr=1.0, upsample=ups)
+        out[f"upsample_at/{i}"] = np.array(sorted(cfg.upsample_at), dtype=np.int64)
+        out[f"should_upsample/{i}"] = np.array([cfg.should_upsample(it) for it in range(n_iter)])
+    rng = np.random.default_rng(0)
+    vals = {k: (rng.standard_normal(200) * (300.0 if "sigma" in k else 2.0)).astype(np.float32) for k in keys}
+    opt = {k: R.Tensor(v) for k, v in vals.items()}
+    opt_mod.enforce_valid_params(sc, opt)
+    for k in keys:
+        out[f"clip_in/{k}"], out[f"clip_out/{k}"] = vals[k], opt[k].v
+    table = []
+    for factor in (0, 1, 2, 3, 4, 8, 16):
+        for res in ((3, 3, 3), (8, 8, 8), (15, 16, 17), (16, 16, 16), (31, 40, 64), (64, 64, 64), (256, 256, 256), (8, 64, 64)):
+            sc.majorant_resolution_factor = factor
+            R.Medium._majorant_resolution_factor = -1
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                opt_mod.adjust_majorant_res_factor(sc, R.Scene(), (*res, 1))
+            table.append((factor, *res, R.Medium._majorant_resolution_factor))
+    out["majorant_factor_table"] = np.array(table, dtype=np.int64)
+    for i, shp in enumerate(((3, 3, 3, 1), (2, 5, 4, 3), (1, 4, 2, 1))):
+        g = rng.random(shp).astype(np.float32)
+        new = (*[2 * r for r in shp[:3]], shp[3])
+        out[f"upsample_in/{i}"], out[f"upsample_out/{i}"] = g, opt_mod.upsample_grid(R.Tensor(g), shp, new).v
+    refs = rng.random((4, 6, 7, 3)).astype(np.float32)
+    si, px, py = rng.integers(0, 4, 50), rng.integers(0, 7, 50), rng.integers(0, 6, 50)
+    got = opt_mod.gather_ref_values(R.Tensor(refs), R.UInt32(si), R.VecU(R.UInt32(px), R.UInt32(py)))
+    out.update({"gather/refs": refs, "gather/sensor_idx": si, "gather/pixels": np.stack([px, py], axis=1), "gather/out": got.v})
+    a, b = rng.random((5, 6, 3)).astype(np.float32), rng.random((5, 6, 3)).astype(np.float32)
+    out.update({"loss/a": a, "loss/b": b, "loss/l1": ref.losses.l1(R.Tensor(a), R.Tensor(b)).v})
+    return out
+
+
 def run_nerf():
     c = RC.NERF
     out = {}
@@ -106,6 +151,8 @@ def run_nerf():
 
 def main():
     O.build()
+    np.savez_compressed(os.path.join(HERE, "refshim_host.npz"), **run_host())
+    print("host written")
     np.savez_compressed(os.path.join(HERE, "refshim_envmap.npz"), **run_envmap())
     print("envmap written")
     np.savez_compressed(os.path.join(HERE, "refshim_nerf.npz"), **run_nerf())

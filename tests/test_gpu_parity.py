@@ -1123,3 +1123,16 @@ def test_04_volpathsimple_gradients_vs_fd(uivr, dev, config):
     for k in keys:
         num = np.linalg.norm(acc[k] - fd[k]) / np.linalg.norm(fd[k])
         assert num < (0.15 if "drt" in config else 0.4), (config, k, num)
+
+
+def test_upsample_kernel_matches_reference_function(uivr, dev):
+    """uivr_upsample2x vs the output of the reference's own upsample_grid (python/optimize.py:203-225,
+    run unmodified by refshim; tests/golden/refshim_host.npz)."""
+    import os
+    _, gdir = _refshim_cases()
+    g = np.load(os.path.join(gdir, "refshim_host.npz"))
+    ctx = uivr._native.Context(0)
+    for i in range(3):
+        a, want = g[f"upsample_in/{i}"], g[f"upsample_out/{i}"]
+        out = uivr.upsample_grid(ctx, _gpu(a, dev), want.shape)
+        assert np.max(np.abs(out.cpu().numpy() - want)) < 1e-6
