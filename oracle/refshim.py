@@ -763,6 +763,8 @@ def width(x) -> int:
 
 
 def select(m, a, b):
+    if isinstance(a, Tensor) or isinstance(b, Tensor):   # python/losses.py:18-21 (huber)
+        return Tensor(np.where(m, a.v if isinstance(a, Tensor) else F32(a), b.v if isinstance(b, Tensor) else F32(b)))
     if isinstance(m, MaskVec) or isinstance(a, Vec) or isinstance(b, Vec):
         proto = a if isinstance(a, Vec) else (b if isinstance(b, Vec) else Color3f())
         n = proto.N
@@ -804,7 +806,17 @@ def _lift(f):
 
 
 rcp = _lift(lambda a: a.rcp() if isinstance(a, ScalarVector2) else 1.0 / _F(a))
-sqr = _lift(lambda a: _F(a) * _F(a))
+sqr = _lift(lambda a: a * a if isinstance(a, Tensor) else _F(a) * _F(a))
+
+
+def sqrt_t(a):
+    """dr.sqrt as python/losses.py uses it: on a tensor, or on a python float"""
+    return Tensor(np.sqrt(a.v)) if isinstance(a, Tensor) else float(np.sqrt(a))
+
+
+def log_t(a):
+    """dr.log as python/losses.py:50-51 uses it: on a tensor, or on a python float"""
+    return Tensor(np.log(a.v)) if isinstance(a, Tensor) else float(np.log(a))
 
 
 def _minmax(fn):
@@ -1129,7 +1141,7 @@ def _make_drjit():
     m = types.ModuleType("drjit")
     m.__dict__.update(dict(
         ADMode=ADMode, width=width, select=select, rcp=rcp, sqr=sqr, minimum=minimum, maximum=maximum,
-        max=hmax, mean=mean, exp=exp, clip=clip, shape=shape, prod=prod, min=hmin, ravel=ravel, sum=hsum, abs=habs, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
+        max=hmax, mean=mean, exp=exp, clip=clip, shape=shape, prod=prod, min=hmin, ravel=ravel, sum=hsum, hsum_async=hsum, sqrt=sqrt_t, log=log_t, abs=habs, any=any_, all=all_, neq=neq, eq=eq, isfinite=isfinite, detach=detach,
         zeros=zeros, empty=empty, full=full, arange=arange, gather=gather, resume_grad=resume_grad,
         suspend_grad=suspend_grad, backward_from=backward_from, enable_grad=enable_grad, grad=grad,
         set_grad=set_grad, enqueue=enqueue, traverse=traverse, CustomOp=CustomOp, custom=custom,
@@ -1573,6 +1585,10 @@ class Tensor:
     def __add__(self, o): return self._bin(o, np.add)
     def __mul__(self, o): return self._bin(o, np.multiply)
     def __truediv__(self, o): return self._bin(o, np.divide)
+    def __radd__(self, o): return Tensor(np.add(F32(o), self.v))
+    def __rsub__(self, o): return Tensor(np.subtract(F32(o), self.v))
+    def __rmul__(self, o): return Tensor(np.multiply(F32(o), self.v))
+    def __lt__(self, o): return self.v < (o.v if isinstance(o, Tensor) else F32(o))   # a plain bool array: only dr.select reads it
 
 
 class ImageBlock:

@@ -125,6 +125,28 @@ def run_host():
     return out
 
 
+LOSS_NAMES = ("average", "l1", "l2", "root_mean_squared_error", "huber", "mean_relative_absolute_error",
+              "mean_relative_squared_error", "root_mean_relative_squared_error", "psnr")
+
+
+def run_losses():
+    """Every function of python/losses.py, run unmodified, on two image pairs (one with residuals beyond the
+    huber delta on both sides); written to refshim_losses.npz."""
+    ref = R.load_reference()
+    rng = np.random.default_rng(7)
+    out = {}
+    for tag, scale in (("unit", 1.0), ("wide", 4.0)):
+        a = (rng.random((5, 6, 3)) * scale).astype(np.float32)
+        b = (rng.random((5, 6, 3)) * scale).astype(np.float32)
+        out[f"{tag}/a"], out[f"{tag}/b"] = a, b
+        for name in LOSS_NAMES:
+            out[f"{tag}/{name}"] = np.asarray(getattr(ref.losses, name)(R.Tensor(a), R.Tensor(b)).v, dtype=np.float32).reshape(-1)
+        out[f"{tag}/huber_delta_half"] = ref.losses.huber(R.Tensor(a), R.Tensor(b), delta=0.5).v.reshape(-1)
+        out[f"{tag}/psnr_max4"] = ref.losses.psnr(R.Tensor(a), R.Tensor(b), max_value=4.0).v.reshape(-1)
+        out[f"{tag}/mrse_eps"] = ref.losses.mean_relative_squared_error(R.Tensor(a), R.Tensor(b), epsilon=0.1).v.reshape(-1)
+    return out
+
+
 def run_nerf():
     c = RC.NERF
     out = {}
@@ -153,6 +175,8 @@ def main():
     O.build()
     np.savez_compressed(os.path.join(HERE, "refshim_host.npz"), **run_host())
     print("host written")
+    np.savez_compressed(os.path.join(HERE, "refshim_losses.npz"), **run_losses())
+    print("losses written")
     np.savez_compressed(os.path.join(HERE, "refshim_envmap.npz"), **run_envmap())
     print("envmap written")
     np.savez_compressed(os.path.join(HERE, "refshim_nerf.npz"), **run_nerf())

@@ -1,6 +1,6 @@
 """B200-native differential volumetric path tracer behind the reference's IntegratorConfig /
 integrator-plugin surface (hot path of rgl-epfl/unbiased-inverse-volume-rendering)."""
-from . import _native
+from . import _native, losses
 from ._native import NativeError, tea32
 from .integrator import (INTEGRATORS, NeRFIntegrator, Scene, VolpathSimpleIntegrator, load_dict,
                          register_integrator, render)
@@ -14,7 +14,7 @@ from .scene import (Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_t
                     cube_test_scene, look_at, synthetic_grids)
 
 __all__ = [
-    "NativeError", "tea32", "INTEGRATORS", "NeRFIntegrator", "Scene", "VolpathSimpleIntegrator", "load_dict",
+    "NativeError", "tea32", "losses", "INTEGRATORS", "NeRFIntegrator", "Scene", "VolpathSimpleIntegrator", "load_dict",
     "register_integrator", "render", "IntegratorConfig", "add_int_config", "get_int_config",
     "Sensor", "VolumeScene", "benchmark_scene", "circle_sensors", "cube_test_grids",
     "cube_test_scene", "look_at", "synthetic_grids",
