@@ -226,3 +226,258 @@ def test_vol_roundtrip_and_header(uivr, tmp_path):
     (tmp_path / "bad.vol").write_bytes(b"nope")
     with pytest.raises(ValueError):
         uivr.read_vol(str(tmp_path / "bad.vol"))
+
+
+# ---- the run around the step: OptimizationConfig / SceneConfig / run_optimization helpers ----------
+
+def _scene_config(uivr, **kw):
+    sensors = uivr.circle_sensors(4, 16, 12)
+    base = dict(volume=uivr.benchmark_scene(16, 16, 12), scene_sensors=sensors,
+                param_keys=["medium1.sigma_t.data", "medium1.albedo.data"], sensors=[0, 2, 3],
+                start_from_value={"medium1.sigma_t.data": 0.04, "medium1.albedo.data": 0.6})
+    base.update(kw)
+    return uivr.SceneConfig("t", **base)
+
+
+def test_optimization_config_matches_reference(uivr):
+    """OptimizationConfig (opt_config.py:11-75): defaults, upsample_at, should_upsample, the learning
+    rates against the reference's own OptimizationConfig run by refshim (refshim_host.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "refshim_host.npz"))
+    keys = ["m.sigma_t.data", "m.albedo.data", "m.emission.data"]
+    import types
+    sc = types.SimpleNamespace(param_lr_factors={"m.albedo.data": 2.0}, param_keys=keys)
+    for name, sched in (("last25", uivr.Schedule.Last25), ("constant", uivr.Schedule.Constant), ("none", None)):
+        cfg = uivr.OptimizationConfig("x", spp=4, n_iter=101, lr=5e-3, lr_schedule=sched)
+        got = np.array([[cfg.learning_rates(sc, it)[k] for k in keys] for it in range(101)])
+        assert np.array_equal(got, g[f"lr/{name}"])
+    with pytest.raises(ValueError, match="Unsupported schedule"):
+        uivr.OptimizationConfig("x", spp=4, n_iter=10, lr=1.0, lr_schedule=7).learning_rates(sc, 0)
+    for i, (ups, n_iter) in enumerate((([0.25, 0.5, 0.75], 101), ([0.0, 1.0, 0.333], 3000), (None, 10))):
+        cfg = uivr.OptimizationConfig("x", spp=4, n_iter=n_iter, lr=1.0, upsample=ups)
+        assert sorted(cfg.upsample_at) == list(g[f"upsample_at/{i}"])
+        assert np.array_equal(np.array([cfg.should_upsample(it) for it in range(n_iter)]), g[f"should_upsample/{i}"])
+    d = uivr.OptimizationConfig("x", spp=4, n_iter=10, lr=1.0)
+    assert (d.primal_spp_factor, d.batch_size, d.base_seed, d.preview_stride, d.checkpoint_stride, d.opt_type) == \
+        (64, None, 988378, 100, 1000, "adam")
+    assert d.loss is uivr.losses.l1 and d.render_initial and d.render_final and d.checkpoint_initial and d.checkpoint_final
+    with pytest.raises(AssertionError):
+        uivr.OptimizationConfig("x", spp=4, n_iter=10, lr=1.0, upsample=[1.5])
+    with pytest.raises(KeyError):
+        uivr.OptimizationConfig("x", spp=4, n_iter=10, lr=1.0, opt_type="lbfgs").optimizer({})
+
+
+def test_sgd_optimizer_and_projection(uivr):
+    import torch
+    p = {"m.sigma_t.data": torch.tensor([0.5, 249.0, 0.01]), "m.albedo.data": torch.tensor([0.5, 0.99, 0.0])}
+    opt = uivr.OptimizationConfig("x", spp=1, n_iter=2, lr=1.0, opt_type="sgd").optimizer(p)
+    assert isinstance(opt, uivr.SGD)
+    opt.set_learning_rate({"m.sigma_t.data": 2.0})
+    opt.step(None, {"m.sigma_t.data": torch.tensor([0.1, -1.0, 1.0]), "m.albedo.data": torch.tensor([0.25, -0.5, 0.5])})
+    assert torch.allclose(p["m.sigma_t.data"], torch.tensor([0.3, 250.0, 0.0]))   # clipped to [0, max_density]
+    assert torch.allclose(p["m.albedo.data"], torch.tensor([0.25, 1.0, 0.0]))      # clipped to [0, 1]
+    m = uivr.SGD(lr=1.0, params={"m.albedo.data": torch.tensor([0.5])}, momentum=0.5)
+    for want in (0.4, 0.25):                                                       # v = 0.1, then 0.5*0.1 + 0.1
+        m.step(None, {"m.albedo.data": torch.tensor([0.1])})
+        assert abs(float(m.params["m.albedo.data"]) - want) < 1e-6
+    m.step(None, {})                                                               # no gradient: parameter untouched
+    assert abs(float(m.params["m.albedo.data"]) - 0.25) < 1e-6
+
+
+def test_scene_config_rules(uivr, tmp_path):
+    sc = _scene_config(uivr)
+    assert sc.preview_sensors == [0] and sc.param_lr_factors == {"medium1.albedo.data": 2.0}
+    assert (sc.max_depth, sc.ref_spp, sc.ref_integrator, sc.max_density, sc.majorant_resolution_factor) == \
+        (64, 8192, "volpathsimple", 250, 8)
+    assert sc.references.endswith(os.path.join("references", "t")) and sc.ref_volume == sc.volume
+    with pytest.raises(ValueError, match="was not given an initial value"):
+        _scene_config(uivr, start_from_value={"medium1.sigma_t.data": 0.04})
+    with pytest.raises(ValueError, match="not part of the scene"):
+        _scene_config(uivr, sensors=[0, 9])
+    assert _scene_config(uivr, references=str(tmp_path)).references == str(tmp_path)   # an existing directory is kept
+    assert _scene_config(uivr, references="shared").references.endswith(os.path.join("references", "shared"))
+    M = __import__("importlib").import_module(uivr.__name__ + ".scene_config")
+    name = "cfg-test-base"
+    if name not in M._SCENE_CONFIGS:
+        kw = {f.name: getattr(sc, f.name) for f in __import__("dataclasses").fields(sc) if f.name in
+              ("volume", "scene_sensors", "param_keys", "sensors", "start_from_value")}
+        uivr.add_scene_config(name, **kw)
+        uivr.add_scene_config_variant(name + "-deep", name, max_depth=128, sensors=[1])
+    with pytest.raises(AssertionError, match="Duplicate"):
+        uivr.add_scene_config(name, **M._SCENE_CONFIG_KWARGS[name])
+    v = uivr.get_scene_config(name + "-deep")
+    assert (v.max_depth, v.sensors, v.preview_sensors) == (128, [1], [1]) and uivr.get_scene_config(name).max_depth == 64
+    v.sensors.append(2)                                                                 # private copy
+    assert uivr.get_scene_config(name + "-deep").sensors == [1]
+
+
+def test_run_helpers(uivr):
+    # PCG32 known answers (pcg32-demo): seed (42, 54)
+    r = uivr.PCG32(42, 54)
+    assert [r.next_uint32() for _ in range(6)] == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    r = uivr.PCG32()
+    assert [r.next_uint32() for _ in range(3)] == [0x1bbeb4f2, 0xe82e89e9, 0x681cfdeb]
+    r, f = uivr.PCG32(initstate=93483), uivr.PCG32(initstate=93483)                    # optimize.py:291
+    for _ in range(100):
+        u32, x = r.next_uint32(), f.next_float32()
+        assert 0.0 <= x < 1.0 and x == float(np.float32((u32 >> 9) * 2.0 ** -23))
+    # optimize.py:36-41
+    assert uivr.reference_pass_plan((720, 720), 8192, 720 * 720 * 2048) == (4, 2048)
+    assert uivr.reference_pass_plan((720, 620), 8192, 720 * 720 * 2048) == (4, 2048)
+    assert uivr.reference_pass_plan((64, 64), 8192, 720 * 720 * 2048) == (1, 8192)
+    assert uivr.reference_pass_plan((1000, 1000), 100, 30_000_000) == (4, 25)
+    assert uivr.reference_pass_plan((1000, 1000), 100, 33_000_000) == (4, 25)
+    assert uivr.reference_pass_plan((1000, 1000), 10, 3_400_000) == (3, 4)              # 3 x 4 >= 10
+    # optimize.py:146-156
+    assert uivr.initial_resolution((64, 64, 64, 3), None) == (64, 64, 64, 3)
+    assert uivr.initial_resolution((64, 48, 32, 1), [0.2, 0.5]) == (16, 12, 8, 1)
+    with pytest.raises(ValueError, match="Initial resolution not supported"):
+        uivr.initial_resolution((64, 64, 7, 1), [0.1, 0.2])
+    # optimize.py:255-268, :110-123
+    cfg = uivr.OptimizationConfig("x", spp=1, n_iter=10, lr=1.0, checkpoint_stride=4, checkpoint_final=False, render_initial=False)
+    assert [uivr.checkpoint_prefix(cfg, i) for i in (0, 3, 4, 8)] == [None, None, "00000004", "00000008"]
+    assert uivr.checkpoint_prefix(cfg, "initial") == "initial" and uivr.checkpoint_prefix(cfg, "final") is None
+    cfg.checkpoint_stride = 0
+    assert uivr.checkpoint_prefix(cfg, 8) is None
+    with pytest.raises(ValueError, match="Unsupported"):
+        uivr.checkpoint_prefix(cfg, "halfway")
+    assert [uivr.preview_suffix(cfg, i) for i in ("initial", "final", 300, "_x")] == [None, "_final", "_00000300", "_x"]
+
+
+def test_exr_against_opencv(uivr, tmp_path):
+    """write_exr / read_exr against OpenCV's OpenEXR codec (independent implementation)."""
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    f = str(tmp_path / "a.exr")
+    try:
+        ok = cv2.imwrite(f, np.zeros((2, 2, 3), np.float32)) and cv2.imread(f, cv2.IMREAD_UNCHANGED) is not None
+    except cv2.error:
+        ok = False
+    for shape in ((5, 7, 3), (33, 20, 3), (16, 16, 4), (1, 1, 3)):
+        a = (rng.random(shape) * 10 - 2).astype(np.float32)
+        bgr = [2, 1, 0] + ([3] if shape[2] == 4 else [])
+        for comp in ("NONE", "ZIPS", "ZIP"):
+            uivr.write_exr(f, a, comp)
+            assert np.array_equal(uivr.read_exr(f), a)
+            if ok:
+                assert np.array_equal(cv2.imread(f, cv2.IMREAD_UNCHANGED)[..., bgr], a), (shape, comp)
+        if ok:
+            cv2.imwrite(f, a[..., bgr])
+            assert np.array_equal(uivr.read_exr(f), a)
+            cv2.imwrite(f, a[..., bgr], [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF])
+            assert np.array_equal(uivr.read_exr(f), a.astype(np.float16).astype(np.float32))
+            cv2.imwrite(f, a[..., bgr], [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+            with pytest.raises(NotImplementedError, match="PIZ"):
+                uivr.read_exr(f)
+    with pytest.raises(NotImplementedError):
+        uivr.write_exr(f, a, "PIZ")
+    with pytest.raises(ValueError):
+        uivr.write_exr(f, np.zeros((4, 4)))
+    open(f, "wb").write(b"not an exr file at all")
+    with pytest.raises(ValueError, match="not an OpenEXR"):
+        uivr.read_exr(f)
+
+
+def test_run_optimization_control_flow_with_a_stand_in_renderer(uivr, tmp_path, monkeypatch):
+    """The host sequence of run_optimization (optimize.py:275-365) -- which files are written when, seeds,
+    sensor choice, upsampling, optimiser calls -- with the device path replaced by a differentiable
+    stand-in (no CUDA here; tests/test_zz_run_optimization.py runs the real thing on the GPU)."""
+    import importlib
+    import torch
+    import torch.nn.functional as F
+    O = importlib.import_module(uivr.__name__ + ".optimize")
+    B = importlib.import_module(uivr.__name__ + ".batched")
+    M = importlib.import_module(uivr.__name__ + ".multires")
+    I = importlib.import_module(uivr.__name__ + ".integrator")
+    calls = []
+
+    class FakeCtx:
+        def check_watchdog(self):
+            calls.append(("watchdog",))
+
+    class FakeScene:
+        def __init__(self, volume, device=None):
+            self.volume, self.ctx = volume, FakeCtx()
+
+        def update_medium(self, sigma_t, force=False):
+            calls.append(("update_medium", tuple(sigma_t.shape)))
+
+        def update_medium_after_reshape(self, sigma_t):
+            calls.append(("reshape", tuple(sigma_t.shape)))
+
+    def shade(params, h, w):
+        return (params[KEYS[0]].mean() * params[KEYS[1]].mean(dim=(0, 1, 2))).expand(h, w, 3)
+
+    KEYS = ["medium1.sigma_t.data", "medium1.albedo.data"]
+
+    def fake_integrator_render(self, scene, params, sensor=None, seed=0, spp=0, **kw):
+        calls.append(("integrator.render", seed, spp, sensor.width))
+        return shade(params, sensor.height, sensor.width).clone()
+
+    def fake_render(scene, params, integrator, sensor=None, spp=0, spp_grad=0, seed=0, seed_grad=0, **kw):
+        calls.append(("render", seed, seed_grad, spp, spp_grad, sensor))
+        return shade(params, sensor.height, sensor.width)
+
+    def fake_render_batch(batch_size, scene, sensors, params, integrator, seed=0, seed_grad=0, spp=0, spp_grad=0):
+        calls.append(("render_batch", batch_size, len(sensors), seed, seed_grad, spp, spp_grad))
+        si, px = B.sample_batch_pixels(batch_size, len(sensors), (sensors[0].width, sensors[0].height), seed)
+        return shade(params, batch_size, 1).reshape(batch_size, 3), si, px
+
+    monkeypatch.setattr(O, "_cuda_device", lambda device: torch.device("cpu"))
+    monkeypatch.setattr(O, "Scene", FakeScene)
+    monkeypatch.setattr(O, "render", fake_render)
+    monkeypatch.setattr(B, "render_batch", fake_render_batch)
+    monkeypatch.setattr(I.VolpathSimpleIntegrator, "render", fake_integrator_render)
+    monkeypatch.setattr(M, "upsample_grid", lambda ctx, v, new_res: F.interpolate(
+        v.permute(3, 0, 1, 2)[None], size=tuple(new_res[:3]), mode="nearest")[0].permute(1, 2, 3, 0).contiguous())
+
+    sig = np.full((8, 8, 8, 1), 0.7, np.float32)
+    alb = np.full((8, 8, 8, 3), 0.9, np.float32)
+    sc = _scene_config(uivr, volume=uivr.benchmark_scene(16, 16, 12), references=str(tmp_path / "refs"), ref_spp=100,
+                       ref_params={KEYS[0]: sig, KEYS[1]: alb}, max_depth=5, sensors=[0, 2, 3], preview_sensors=[2])
+    os.makedirs(sc.references, exist_ok=True)
+
+    # --- sensor mode, SGD, no upsampling
+    oc = uivr.OptimizationConfig("s", spp=3, n_iter=5, lr=0.05, primal_spp_factor=4, opt_type="sgd", checkpoint_stride=2,
+                                 preview_stride=3, base_seed=77)
+    losses = []
+    out = str(tmp_path / "sensor")
+    scene, params, opt = uivr.run_optimization(out, oc, sc, "volpathsimple-basic", callback=lambda it, l: losses.append(l))
+    assert sorted(os.listdir(sc.references)) == ["ref_000000.exr", "ref_000002.exr", "ref_000003.exr"]
+    assert np.allclose(uivr.read_exr(os.path.join(sc.references, "ref_000002.exr")), 0.7 * 0.9)
+    ref_calls = [c for c in calls if c[0] == "integrator.render" and c[2] == 100]
+    assert [c[1] for c in ref_calls] == [1234, 1234, 1234]                       # one pass per sensor at seed 1234
+    picks = uivr.PCG32(initstate=93483)
+    renders = [c for c in calls if c[0] == "render"]
+    assert len(renders) == 5
+    for it, c in enumerate(renders):
+        want = sc.scene_sensors[sc.sensors[int(picks.next_float32() * 3)]]
+        assert c[1:5] == (uivr.tea32(2 * it, 77), uivr.tea32(2 * it + 1, 77), 12, 3) and c[5] is want
+    assert losses[-1] < losses[0] and len(losses) == 5                            # sigma_t * albedo moves towards 0.63
+    assert sorted(os.listdir(os.path.join(out, "params"))) == sorted(
+        f"{p}-medium1_{g}.vol" for p in ("initial", "00000002", "00000004", "final") for g in ("sigma_t", "albedo"))
+    assert sorted(f for f in os.listdir(out) if f.endswith(".exr")) == [
+        "opt_00000003_0002.exr", "opt_final_0002.exr", "opt_init_0002.exr", "ref_0002.exr"]
+    assert [c for c in calls if c[0] == "update_medium"] == [("update_medium", (16, 16, 16, 1))] * 5
+    assert calls[-2][0] == "watchdog" and calls[-1][:3] == ("integrator.render", 1234, 3)   # ... then the final preview
+    assert tuple(params[KEYS[0]].shape) == (16, 16, 16, 1) and opt.params is params
+
+    # --- ray batches, two upsamplings: 16 -> 4 -> 8 -> 16; the cached references are not rendered again
+    calls.clear()
+    oc = uivr.OptimizationConfig("b", spp=2, n_iter=8, lr=0.05, batch_size=64, opt_type="sgd", upsample=[0.25, 0.5],
+                                 render_initial=False, render_final=False, checkpoint_initial=False, checkpoint_stride=0)
+    out = str(tmp_path / "batch")
+    scene, params, opt = uivr.run_optimization(out, oc, sc, uivr.get_int_config("volpathsimple-drt"))
+    assert not [c for c in calls if c[0] == "integrator.render"]
+    rb = [c for c in calls if c[0] == "render_batch"]
+    assert [c[1:3] for c in rb] == [(64, 3)] * 8 and all(c[5:] == (128, 2) for c in rb)
+    assert [c[3] for c in rb] == [uivr.tea32(2 * it, 988378) for it in range(8)]
+    shapes = [c[1][0] for c in calls if c[0] == "update_medium"]
+    assert shapes == [4, 4, 8, 8, 16, 16, 16, 16]
+    assert [c[1] for c in calls if c[0] == "reshape"] == [(8, 8, 8, 1), (16, 16, 16, 1)]
+    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 4
+    assert sorted(os.listdir(os.path.join(out, "params"))) == ["final-medium1_albedo.vol", "final-medium1_sigma_t.vol"]
+    assert sorted(f for f in os.listdir(out) if f.endswith(".exr")) == ["ref_0002.exr"]
+    with pytest.raises(ValueError, match="Initial resolution not supported"):
+        uivr.run_optimization(out, uivr.OptimizationConfig("b", spp=2, n_iter=8, lr=0.05, upsample=[0.1, 0.2, 0.3, 0.4]),
+                              sc, "volpathsimple-drt")

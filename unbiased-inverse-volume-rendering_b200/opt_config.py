@@ -10,9 +10,71 @@ from __future__ import annotations
 
 import copy
 import dataclasses
-from typing import Any, Dict, Optional, Union
+import enum
+from typing import Any, Callable, Dict, List, Optional, Union
 
+from . import losses
 from .integrator import load_dict
+
+
+class Schedule(enum.IntEnum):
+    """opt_config.py:78-80."""
+    Constant = 0
+    Last25 = 1
+
+
+@dataclasses.dataclass
+class OptimizationConfig:
+    """opt_config.py:11-75: the options of one optimisation run, same field names and defaults.
+    `optimizer(params)` hands out the native-backed optimiser (optimize.Adam: fused update +
+    projection kernel) where the reference constructs `mi.ad.Adam` / `mi.ad.SGD`."""
+    name: str
+    spp: int
+    n_iter: int
+    lr: float
+
+    primal_spp_factor: int = 64
+    batch_size: Optional[int] = None
+    lr_schedule: Optional[Schedule] = None
+    upsample: Optional[List[float]] = None
+
+    base_seed: int = 988378
+
+    render_initial: bool = True
+    render_final: bool = True
+    preview_stride: int = 100
+
+    checkpoint_initial: bool = True
+    checkpoint_final: bool = True
+    checkpoint_stride: int = 1000
+
+    preview_spp: Optional[int] = None
+    opt_type: str = "adam"
+    opt_args: Optional[Dict[str, Any]] = None
+    loss: Callable = losses.l1
+
+    def __post_init__(self):
+        from .multires import upsample_iterations
+        self.upsample_at = upsample_iterations(self.upsample, self.n_iter)          # opt_config.py:39-44
+
+    def optimizer(self, params):
+        """opt_config.py:46-48; an unknown opt_type is a KeyError there as well."""
+        from . import optimize
+        make = {"sgd": optimize.SGD, "adam": optimize.Adam}[self.opt_type]
+        return make(lr=self.lr, params=params, **(self.opt_args or {}))
+
+    def learning_rates(self, scene_config, it_i: int) -> Dict[str, float]:
+        """opt_config.py:50-69, through optimize.learning_rates (which holds the Last25 rule)."""
+        from .optimize import learning_rates
+        if self.lr_schedule is not None and self.lr_schedule not in tuple(Schedule):
+            raise ValueError(f"Unsupported schedule: {self.lr_schedule}")
+        name = None if self.lr_schedule is None else Schedule(self.lr_schedule).name.lower()
+        return learning_rates(self.lr, scene_config.param_keys, it_i, self.n_iter, name, scene_config.param_lr_factors)
+
+    def should_upsample(self, it_i: int) -> bool:
+        """opt_config.py:72-75."""
+        return it_i in self.upsample_at
+
 
 # rr_depth = max_depth + this: Russian roulette never fires (opt_config.py:103-106)
 _RR_OFFSET = 1000

@@ -17,12 +17,16 @@ BASELINE.json's config 4.  PyTorch only holds the tensors; the update runs in li
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence, Tuple
+import math
+import os
+from typing import Callable, Dict, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _native
-from .integrator import ALBEDO_SUFFIX, SIGMA_T_SUFFIX, Scene, VolpathSimpleIntegrator, _stream
+from .exr import read_exr, write_exr
+from .integrator import ALBEDO_SUFFIX, SIGMA_T_SUFFIX, Scene, VolpathSimpleIntegrator, _stream, load_dict, render
 from .scene import Sensor
 
 LAST25_STEPS = (0.75, 0.85, 0.95)  # opt_config.py:54-55
@@ -97,14 +101,48 @@ class Adam:
     def step(self, ctx: _native.Context, grads: Dict[str, torch.Tensor], max_density: float = 250.0):
         """opt.step() + enforce_valid_params in one pass per tensor."""
         for k, p in self.params.items():
+            g = grads.get(k)
+            if g is None:        # mi.ad.Adam.step skips a parameter whose gradient is empty (not touched by the render)
+                continue
             self.t[k] += 1
-            g = grads[k]
             if g.shape != p.shape or g.dtype != torch.float32 or not g.is_contiguous():
                 raise ValueError(f"gradient of {k} must match its parameter")
             lo, hi = param_bounds(k, max_density)
             ctx.adam_step(p.data_ptr(), g.data_ptr(), self.m[k].data_ptr(), self.v[k].data_ptr(), p.numel(),
                           self.lr[k], self.beta_1, self.beta_2, self.epsilon, self.t[k], lo,
                           hi if hi != float("inf") else 3.4028234663852886e38, _stream())
+
+
+class SGD:
+    """mi.ad.SGD as `OptimizationConfig.optimizer` can construct it (opt_config.py:46-48; the reference's
+    runs all use Adam): value -= lr * (momentum-filtered) gradient, then the projection of
+    enforce_valid_params.  Plain torch element-wise updates -- SGD is not part of any measured
+    configuration and has no kernel of its own."""
+
+    def __init__(self, lr: float, params: Dict[str, torch.Tensor], momentum: float = 0.0):
+        self.params = params
+        self.momentum = float(momentum)
+        self.lr = {k: float(lr) for k in params}
+        self.state = {}
+
+    set_learning_rate = Adam.set_learning_rate
+    items = Adam.items
+
+    def replace(self, key: str, value: torch.Tensor):
+        if key not in self.params:
+            raise KeyError(key)
+        self.params[key] = value.detach().to(torch.float32).contiguous()
+        self.state.pop(key, None)
+
+    def step(self, ctx, grads: Dict[str, torch.Tensor], max_density: float = 250.0):
+        for k, p in self.params.items():
+            g = grads.get(k)
+            if g is None:
+                continue
+            if self.momentum != 0.0:
+                g = self.state[k] = g.clone() if k not in self.state else self.state[k].mul_(self.momentum).add_(g)
+            lo, hi = param_bounds(k, max_density)
+            p.detach().add_(g, alpha=-self.lr[k]).clamp_(lo, hi)
 
 
 def l1_loss_grad(image: torch.Tensor, ref: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -141,3 +179,246 @@ def optimization_step(scene: Scene, integrator: VolpathSimpleIntegrator, opt: Ad
     opt.step(scene.ctx, grads, max_density)                 # optimize.py:352-353
     scene.update_medium(params[k_sig], force=True)          # params.update(), optimize.py:354
     return float(loss_sum.item()) / max(1, len(sensors))
+
+
+# ======================================================================================
+# The run around the step: python/optimize.py:14-88, :110-166, :255-365
+# ======================================================================================
+
+class PCG32:
+    """mi.scalar_rgb.PCG32 as optimize.py:291, :343 uses it to pick the sensor of an iteration."""
+    _MULT, _M64 = 0x5851F42D4C957F2D, (1 << 64) - 1
+
+    def __init__(self, initstate: int = 0x853C49E6748FEA9B, initseq: int = 0xDA3E39CB94B95BDB):
+        self.inc = ((initseq << 1) | 1) & self._M64
+        self.state = 0
+        self.next_uint32()
+        self.state = (self.state + initstate) & self._M64
+        self.next_uint32()
+
+    def next_uint32(self) -> int:
+        old = self.state
+        self.state = (old * self._MULT + self.inc) & self._M64
+        xs = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        return ((xs >> rot) | (xs << ((-rot) & 31))) & 0xFFFFFFFF
+
+    def next_float32(self) -> float:
+        return float(np.array((self.next_uint32() >> 9) | 0x3F800000, dtype=np.uint32).view(np.float32) - np.float32(1.0))
+
+
+def _cuda_device(device: Optional[int]) -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+
+def _grid_shape(volume, key: str) -> Tuple[int, int, int, int]:
+    x, y, z = volume.res
+    return (z, y, x, 1 if key.endswith(SIGMA_T_SUFFIX) else 3)
+
+
+def _bound_scene(volume, sigma_t_shape, device) -> Scene:
+    z, y, x = sigma_t_shape[:3]
+    return Scene(volume.with_resolution((x, y, z), volume.majorant_resolution_factor), device)
+
+
+def reference_pass_plan(film_size: Tuple[int, int], ref_spp: int, max_rays_per_pass: int) -> Tuple[int, int]:
+    """optimize.py:36-41: (pass_count, spp_per_pass) so that one pass traces at most max_rays_per_pass rays."""
+    total_rays = int(film_size[0]) * int(film_size[1]) * int(ref_spp)
+    pass_count = int(math.ceil(total_rays / max_rays_per_pass))
+    spp_per_pass = int(math.ceil(ref_spp / pass_count))
+    assert spp_per_pass * pass_count >= ref_spp
+    return pass_count, spp_per_pass
+
+
+def render_reference_image(scene_config, to_render: Dict[int, str], seed: int = 1234,
+                           max_rays_per_pass: int = 720 * 720 * 2048, device: Optional[int] = None) -> None:
+    """optimize.py:24-53: the reference medium rendered at ref_spp with `ref_integrator`, split into
+    passes with consecutive seeds and averaged, one EXR per sensor."""
+    if not scene_config.ref_params:
+        raise ValueError(f"scene config '{scene_config.name}' has no ref_params to render references from")
+    dev = _cuda_device(device)
+    params = {k: torch.as_tensor(v).to(device=dev, dtype=torch.float32).contiguous() for k, v in scene_config.ref_params.items()}
+    k_sig = next(k for k in params if k.endswith(SIGMA_T_SUFFIX))
+    scene = _bound_scene(scene_config.ref_volume, params[k_sig].shape, dev.index)
+    integrator = load_dict({"type": scene_config.ref_integrator, "max_depth": scene_config.max_depth})
+    for s, fname in to_render.items():
+        sensor = scene_config.scene_sensors[s]
+        pass_count, spp_per_pass = reference_pass_plan((sensor.width, sensor.height), scene_config.ref_spp, max_rays_per_pass)
+        result = None
+        for pass_i in range(pass_count):
+            image = integrator.render(scene, params, sensor=sensor, spp=spp_per_pass, seed=seed + pass_i)
+            result = image / pass_count if result is None else result + image / pass_count
+        write_exr(fname, result)
+
+
+def get_reference_image_paths(scene_config, overwrite: bool = False, device: Optional[int] = None) -> Dict[int, str]:
+    """optimize.py:56-72: `<references>/ref_%06d.exr` per optimisation sensor, rendered when missing."""
+    ref_dir = scene_config.references
+    os.makedirs(ref_dir, exist_ok=True)
+    paths = {s: os.path.join(ref_dir, "ref_{:06d}.exr".format(s)) for s in scene_config.sensors}
+    missing = dict(paths) if overwrite else {s: f for s, f in paths.items() if not os.path.isfile(f)}
+    if missing:
+        render_reference_image(scene_config, missing, device=device)
+    return paths
+
+
+def load_reference_images(paths: Dict[int, str], batchify: bool = False, device=None):
+    """optimize.py:75-88: one [n, H, W, C] tensor in the order of `paths` (ray batches) or {sensor: [H, W, C]}."""
+    if batchify:
+        return torch.from_numpy(np.stack([read_exr(f) for f in paths.values()])).to(device)
+    return {s: torch.from_numpy(read_exr(f)).to(device) for s, f in paths.items()}
+
+
+def initial_resolution(shape: Sequence[int], upsample) -> Tuple[int, ...]:
+    """optimize.py:146-156: the resolution that reaches `shape` after len(upsample) doublings."""
+    if not upsample:
+        return tuple(int(v) for v in shape)
+    assert len(shape) == 4
+    f = 2 ** len(upsample)
+    init_res = (*[max(1, int(v) // f) for v in shape[:3]], int(shape[-1]))
+    if 1 in init_res[:3]:
+        raise ValueError(f"Initial resolution not supported: {init_res}. Maybe reduce upsample_steps?")
+    return init_res
+
+
+def initialize_scene(opt_config, scene_config, device: Optional[int] = None):
+    """optimize.py:134-166 -> (scene bound to the device at the initial resolution, params)."""
+    from .multires import adjust_majorant_res_factor
+    dev = _cuda_device(device)
+    params, factor = {}, scene_config.majorant_resolution_factor
+    for k, v in scene_config.start_from_value.items():
+        assert k in scene_config.param_keys
+        if v is None:                                            # keep what the scene file holds
+            assert not opt_config.upsample
+            params[k] = torch.as_tensor(scene_config.initial_params[k]).to(device=dev, dtype=torch.float32).contiguous().clone()
+            continue
+        init_res = initial_resolution(_grid_shape(scene_config.volume, k), opt_config.upsample)
+        if opt_config.upsample and ".sigma_t." in k:
+            factor = adjust_majorant_res_factor(scene_config.majorant_resolution_factor, init_res)
+        params[k] = torch.full(init_res, float(v), dtype=torch.float32, device=dev)
+    k_sig = next(k for k in params if k.endswith(SIGMA_T_SUFFIX))
+    z, y, x = params[k_sig].shape[:3]
+    scene = Scene(scene_config.volume.with_resolution((x, y, z), factor), dev.index)
+    return scene, params
+
+
+def checkpoint_prefix(opt_config, name_or_it) -> Optional[str]:
+    """optimize.py:255-268: the file prefix of a checkpoint, or None when this one is not written."""
+    if name_or_it == "initial":
+        return "initial" if opt_config.checkpoint_initial else None
+    if name_or_it == "final":
+        return "final" if opt_config.checkpoint_final else None
+    if isinstance(name_or_it, int) and not isinstance(name_or_it, bool):
+        stride = opt_config.checkpoint_stride
+        if name_or_it == 0 or not stride or name_or_it % stride != 0:
+            return None
+        return f"{name_or_it:08d}"
+    raise ValueError("Unsupported: " + str(name_or_it))
+
+
+def create_checkpoint(output_dir: str, opt_config, scene_config, params, name_or_it):
+    """optimize.py:255-272: `.vol` grids of every optimised key under <output_dir>/params."""
+    from .multires import save_params
+    prefix = checkpoint_prefix(opt_config, name_or_it)
+    if prefix is None:
+        return None
+    return save_params(os.path.join(output_dir, "params"), params, prefix, scene_config.param_keys)
+
+
+def preview_suffix(opt_config, it_i) -> Optional[str]:
+    """optimize.py:110-123."""
+    if it_i == "initial":
+        return "_init" if opt_config.render_initial else None
+    if it_i == "final":
+        return "_final" if opt_config.render_final else None
+    if isinstance(it_i, int):
+        return f"_{it_i:08d}"
+    assert isinstance(it_i, str)
+    return it_i
+
+
+def render_previews(output_dir: str, opt_config, scene_config, scene: Scene, params, integrator, it_i):
+    """optimize.py:110-131: `opt<suffix>_%04d.exr` of every preview sensor at seed 1234."""
+    suffix = preview_suffix(opt_config, it_i)
+    if suffix is None:
+        return []
+    preview_spp = opt_config.preview_spp or opt_config.spp
+    written = []
+    for s in scene_config.preview_sensors:
+        fname = os.path.join(output_dir, f"opt{suffix}_{s:04d}.exr")
+        image = integrator.render(scene, params, sensor=scene_config.scene_sensors[s], seed=1234, spp=preview_spp)
+        write_exr(fname, image)
+        written.append(fname)
+    return written
+
+
+def run_optimization(output_dir: str, opt_config, scene_config, int_config, device: Optional[int] = None,
+                     callback: Optional[Callable[[int, float], None]] = None):
+    """python/optimize.py:275-365.  Same sequence: reference images (rendered once, cached as EXR) ->
+    integrator from the registry -> constant initial grids (coarse when upsampling) -> per iteration
+    {seeds from the base seed, learning rates, upsampling, one ray batch or one random sensor, loss,
+    backward, optimiser step + projection, medium rebuild, checkpoint, preview} -> final checkpoint.
+    Returns (scene, params, opt) like the reference.  `callback(it, loss)` is an addition: the
+    reference never reports its loss."""
+    from .batched import gather_ref_values, render_batch
+    from .multires import upsample_params
+    from .opt_config import get_int_config
+    os.makedirs(output_dir, exist_ok=True)
+    batch_size = opt_config.batch_size
+    ref_paths = get_reference_image_paths(scene_config, device=device)
+    dev = _cuda_device(device)
+    ref_images = load_reference_images(ref_paths, batchify=(batch_size is not None), device=dev)
+    integrator = get_int_config(int_config).create(max_depth=scene_config.max_depth)
+    sampler = PCG32(initstate=93483)
+
+    n_sensors = len(scene_config.sensors)
+    spp_grad = opt_config.spp
+    spp_primal = spp_grad * opt_config.primal_spp_factor
+    if batch_size is not None:
+        batch_sensors = [scene_config.scene_sensors[s] for s in scene_config.sensors]
+
+    scene, params = initialize_scene(opt_config, scene_config, dev.index)
+    opt = opt_config.optimizer(params)
+
+    create_checkpoint(output_dir, opt_config, scene_config, opt.params, "initial")
+    render_previews(output_dir, opt_config, scene_config, scene, opt.params, integrator, "initial")
+    for s in scene_config.preview_sensors:                       # the matching reference views, for comparison
+        ref = ref_images[scene_config.sensors.index(s)] if batch_size is not None else ref_images[s]
+        write_exr(os.path.join(output_dir, f"ref_{s:04d}.exr"), ref)
+
+    for it_i in range(opt_config.n_iter):
+        seed = _native.tea32(2 * it_i + 0, opt_config.base_seed)
+        seed_grad = _native.tea32(2 * it_i + 1, opt_config.base_seed)
+        opt.set_learning_rate(opt_config.learning_rates(scene_config, it_i))
+        if opt_config.should_upsample(it_i):
+            upsample_params(scene, opt, scene_config.majorant_resolution_factor)
+
+        p = {k: v.requires_grad_(True) for k, v in opt.params.items()}
+        if batch_size is not None:
+            image, sensor_idx, pixel_idx = render_batch(batch_size, scene, batch_sensors, p, integrator, seed=seed,
+                                                        seed_grad=seed_grad, spp=spp_primal, spp_grad=spp_grad)
+            ref_values = gather_ref_values(ref_images, sensor_idx, pixel_idx)
+        else:
+            sensor_i = scene_config.sensors[int(sampler.next_float32() * n_sensors)]
+            image = render(scene, p, integrator, sensor=scene_config.scene_sensors[sensor_i], spp=spp_primal,
+                           spp_grad=spp_grad, seed=seed, seed_grad=seed_grad)
+            ref_values = ref_images[sensor_i]
+        loss_value = opt_config.loss(image, ref_values)
+        loss_value.backward()
+        grads = {k: v.grad for k, v in p.items()}
+        for v in p.values():
+            v.requires_grad_(False)
+            v.grad = None
+
+        opt.step(scene.ctx, grads, max_density=scene_config.max_density)       # opt.step() + enforce_valid_params
+        scene.update_medium(opt.params[next(k for k in opt.params if k.endswith(SIGMA_T_SUFFIX))], force=True)
+        create_checkpoint(output_dir, opt_config, scene_config, opt.params, it_i)
+        if callback is not None:
+            callback(it_i, float(loss_value.detach()))
+        if it_i > 0 and it_i % opt_config.preview_stride == 0:
+            render_previews(output_dir, opt_config, scene_config, scene, opt.params, integrator, it_i)
+
+    scene.ctx.check_watchdog()
+    create_checkpoint(output_dir, opt_config, scene_config, opt.params, "final")
+    render_previews(output_dir, opt_config, scene_config, scene, opt.params, integrator, "final")
+    return scene, opt.params, opt
