@@ -59,7 +59,7 @@ def test_run_optimization_first_iteration_equals_the_manual_sequence(uivr, tmp_p
                         seed=uivr.tea32(0, 4321), seed_grad=uivr.tea32(1, 4321))
     loss = uivr.losses.l1(image, ref)
     loss.backward()
-    assert abs(float(loss) - losses[0]) < 1e-6
+    assert abs(float(loss.detach()) - losses[0]) < 1e-6
     grads = {k: v.grad for k, v in q.items()}
     for v in q.values():
         v.requires_grad_(False)
