@@ -28,30 +28,29 @@ class OptimizationConfig:
     """opt_config.py:11-75: the options of one optimisation run, same field names and defaults.
     `optimizer(params)` hands out the native-backed optimiser (optimize.Adam: fused update +
     projection kernel) where the reference constructs `mi.ad.Adam` / `mi.ad.SGD`."""
+    # required, in the reference's positional order (opt_config.py:14-17)
     name: str
-    spp: int
+    spp: int                                       # samples per pixel of the adjoint pass
     n_iter: int
     lr: float
-
-    primal_spp_factor: int = 64
-    batch_size: Optional[int] = None
-    lr_schedule: Optional[Schedule] = None
-    upsample: Optional[List[float]] = None
-
+    # sampling
+    primal_spp_factor: int = 64                    # primal spp = spp x this
+    batch_size: Optional[int] = None               # None: one random sensor per iteration; else rays per batch
     base_seed: int = 988378
-
+    # schedule
+    lr_schedule: Optional[Schedule] = None
+    upsample: Optional[List[float]] = None         # fractions of the run at which the grids double
+    opt_type: str = "adam"                         # "adam" | "sgd"
+    opt_args: Optional[Dict[str, Any]] = None
+    loss: Callable = losses.l1
+    # outputs
+    checkpoint_initial: bool = True
+    checkpoint_final: bool = True
+    checkpoint_stride: Optional[int] = 1000        # None / 0: no intermediate checkpoints
     render_initial: bool = True
     render_final: bool = True
     preview_stride: int = 100
-
-    checkpoint_initial: bool = True
-    checkpoint_final: bool = True
-    checkpoint_stride: int = 1000
-
-    preview_spp: Optional[int] = None
-    opt_type: str = "adam"
-    opt_args: Optional[Dict[str, Any]] = None
-    loss: Callable = losses.l1
+    preview_spp: Optional[int] = None              # None: spp
 
     def __post_init__(self):
         from .multires import upsample_iterations
