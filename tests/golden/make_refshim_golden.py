@@ -147,6 +147,29 @@ def run_losses():
     return out
 
 
+RANDOM_CASES = 16  # the seeds of tests/test_gpu_parity.py::test_randomized_parity_sweep
+
+
+def run_random():
+    """The randomized sweep of helpers.random_case (anisotropic grids / boxes, random cameras and films,
+    supergrid factors, every flag, constant and envmap emitters) through the reference's files."""
+    from helpers import random_case
+    import uivr_b200 as u
+    out = {}
+    for case in range(RANDOM_CASES):
+        c = random_case(u, case)
+        props = dict(c["props"])
+        integ = R.make_integrator("volpathsimple-drt", max_depth=props.pop("max_depth"), **props)
+        desc = c["vol"].as_dict()
+        img, samples = R.render_forward(desc, integ, c["sig"], c["alb"], c["seed"], c["spp"])
+        gimg = loss_grad(img)
+        ds, da, samples_g = R.render_backward(desc, integ, c["sig"], c["alb"], gimg, c["seed_grad"], c["spp"])
+        out.update({f"{case}/image": img, f"{case}/samples": samples, f"{case}/grad_image": gimg,
+                    f"{case}/samples_grad_pass": samples_g, f"{case}/dsigma": ds.astype(np.float32),
+                    f"{case}/dalbedo": da.astype(np.float32)})
+    return out
+
+
 def run_nerf():
     c = RC.NERF
     out = {}
@@ -177,6 +200,8 @@ def main():
     print("host written")
     np.savez_compressed(os.path.join(HERE, "refshim_losses.npz"), **run_losses())
     print("losses written")
+    np.savez_compressed(os.path.join(HERE, "refshim_random.npz"), **run_random())
+    print("random sweep written")
     np.savez_compressed(os.path.join(HERE, "refshim_envmap.npz"), **run_envmap())
     print("envmap written")
     np.savez_compressed(os.path.join(HERE, "refshim_nerf.npz"), **run_nerf())

@@ -4,6 +4,8 @@ Bars: per-sample radiance and event counters BIT-EXACT (every branch decision of
 identical); image L-inf < 1e-5; gradient relative L-inf < 1e-3 (north_star tolerance; only the
 atomic summation order differs, observed ~1e-6).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -1029,6 +1031,13 @@ def test_randomized_parity_sweep(uivr, oracle, dev, case):
         assert rel_linf(ds_g, ds_o) < GRAD_TOL
     if np.abs(da_o).max() > 0:
         assert rel_linf(da_g, da_o) < GRAD_TOL
+    # the same case through the reference's own files (tests/golden/refshim_random.npz)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refshim_random.npz"))
+    assert np.max(np.abs(smp_g - g[f"{case}/samples"])) < REFSHIM_SAMPLE_TOL
+    assert np.max(np.abs(smp_bg - g[f"{case}/samples_grad_pass"])) < REFSHIM_SAMPLE_TOL
+    for got, want in ((ds_g, g[f"{case}/dsigma"]), (da_g, g[f"{case}/dalbedo"])):
+        if np.abs(want).max() > 0:
+            assert rel_linf(got, want) < GRAD_TOL
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
