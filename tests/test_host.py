@@ -481,3 +481,28 @@ def test_run_optimization_control_flow_with_a_stand_in_renderer(uivr, tmp_path, 
     with pytest.raises(ValueError, match="Initial resolution not supported"):
         uivr.run_optimization(out, uivr.OptimizationConfig("b", spp=2, n_iter=8, lr=0.05, upsample=[0.1, 0.2, 0.3, 0.4]),
                               sc, "volpathsimple-drt")
+
+
+def test_exr_roundtrip_properties(uivr, tmp_path):
+    """Round trips on arbitrary float bit patterns (NaN payloads, infinities, denormals, -0) and image
+    shapes around the 16-scanline ZIP block size; the ZIP byte transform is its own inverse."""
+    from hypothesis import given, settings, strategies as st
+    E = __import__("importlib").import_module(uivr.__name__ + ".exr")
+    f = str(tmp_path / "p.exr")
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 9), st.sampled_from([3, 4]), st.sampled_from(["NONE", "ZIPS", "ZIP"]),
+           st.integers(0, 2 ** 32 - 1))
+    def images(h, w, c, comp, seed):
+        bits = np.random.default_rng(seed).integers(0, 2 ** 32, size=(h, w, c), dtype=np.uint64).astype(np.uint32)
+        a = bits.view(np.float32)
+        uivr.write_exr(f, a, comp)
+        assert np.array_equal(uivr.read_exr(f).view(np.uint32), bits)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.binary(min_size=1, max_size=300))
+    def codec(raw):
+        assert E._zip_decode(E._zip_encode(raw), len(raw)) == raw
+
+    images()
+    codec()
