@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import uivr_b200 as u
 
-def main(n=256, w=512, h=512, spp=64, variant=1, factor=8, reps=3):
+def main(n=256, w=512, h=512, spp=64, variant=1, factor=8, reps=3, counters=1):
     dev = torch.device("cuda:0")
     sig, alb = u.synthetic_grids(n)
     sig, alb = sig.to(dev), alb.to(dev)
@@ -27,6 +27,8 @@ def main(n=256, w=512, h=512, spp=64, variant=1, factor=8, reps=3):
         print(f"n={n} {w}x{h}x{spp} variant={variant} factor={factor}: fwd {tf:.1f} ms  bwd {tb:.1f} ms  "
               f"-> {S / (tf + tb) / 1e3:.1f} Msamples/s  img mean {img.mean().item():.4f} "
               f"|ds| {ds.abs().sum().item():.4e} |da| {da.abs().sum().item():.4e}", flush=True)
+    if not counters:
+        return
     scene.ctx.set_counting(True); scene.ctx.reset_counters()
     img = integ.render(scene, params, seed=1234, spp=spp)
     cf = scene.ctx.get_counters()
