@@ -146,6 +146,51 @@ def oracle_step(O, desc, props, sig, alb, it, spp, nthreads):
     O.render_backward(desc, props, sig, alb, g, seed_grad, spp, nthreads=nthreads)
 
 
+def parity_check(u, scene, integ, params, vol, sig_h, alb_h, spp: int = 2):
+    """BASELINE.json's metric is quoted with "grad L-inf vs ref": the CUDA path against the oracle (the
+    checker, never the thing measured) on the bench's own grids / camera / flags at a spp the oracle
+    finishes in a second -- per-sample radiance bit for bit, image and gradient L-inf.  Runs after all
+    timing; never lets a failure take the bench line down."""
+    try:
+        import numpy as np
+        import torch
+        from oracle import oracle as O
+        O.build()
+        seed, seed_grad = step_seeds(0)
+        desc, props = vol.as_dict(), integ.props()
+        sig, alb = sig_h.numpy(), alb_h.numpy()
+        n = FILM_W * FILM_H * spp
+        nthreads = os.cpu_count() or 1
+        img_o, smp_o, _ = O.render_forward(desc, props, sig, alb, seed, spp, want_samples=True, nthreads=nthreads)
+        gimg = (2.0 * (img_o.astype(np.float64) - 0.5) / img_o.size).astype(np.float32)
+        ds_o, da_o, smp_bo, _ = O.render_backward(desc, props, sig, alb, gimg, seed_grad, spp, want_samples=True,
+                                                  nthreads=nthreads)
+        dev = params["medium.sigma_t.data"].device
+        smp = torch.zeros((n, 3), device=dev)
+        img = integ.render(scene, params, seed=seed, spp=spp, sample_out=smp)
+        smp_b = torch.zeros((n, 3), device=dev)
+        ds, da = integ.render_backward(scene, params, torch.from_numpy(gimg).to(dev), seed=seed_grad, spp=spp,
+                                       sample_out=smp_b)
+        torch.cuda.synchronize()
+
+        def rel(a, b):
+            return float(np.max(np.abs(a.astype(np.float64) - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+        return {
+            "checked_against": "oracle (CPU restatement of the reference algorithm, pinned by refshim vectors)",
+            "sample": f"config3 grids/camera/flags at {FILM_W}x{FILM_H}x{spp}spp ({n} samples), matched seeds",
+            "per_sample_radiance_bit_exact": bool(
+                np.array_equal(smp.cpu().numpy().view(np.uint32), smp_o.view(np.uint32))
+                and np.array_equal(smp_b.cpu().numpy().view(np.uint32), smp_bo.view(np.uint32))),
+            "image_linf": float(np.max(np.abs(img.cpu().numpy() - img_o))),
+            "grad_sigma_t_linf_rel": rel(ds.cpu().numpy(), ds_o),
+            "grad_albedo_linf_rel": rel(da.cpu().numpy(), da_o),
+            "tolerance": 1e-3,
+        }
+    except Exception as e:  # noqa: BLE001 -- the measurement above must be reported whatever happens here
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline(target_s: float = 12.0):
     """The CPU oracle (kind 'port': C restatement of the reference algorithm, pthreads over all
     host cores) on a bounded sample of config 3: same grids / camera / flags, reduced spp."""
@@ -413,6 +458,7 @@ def run_native(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+            line["parity"] = parity_check(u, scene, integ, params, vol, sig_h, alb_h)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -169,6 +169,18 @@ def test_bench_reference_arm_contract():
     assert bench.algorithmic_bytes({"sigma_taps": 1, "albedo_taps": 1, "majorant_reads": 1, "sigma_scatters": 1,
                                     "albedo_scatters": 1}, 2, True) == 32 + 96 + 4 + 64 + 192 + 24
     json.dumps(bench.workload_config(2, 128))
+    # the parity leg never takes the bench line down: without a device it reports the error instead
+    import uivr_b200 as u
+    sig, alb = u.synthetic_grids(8)
+    old = bench.FILM_W, bench.FILM_H
+    bench.FILM_W = bench.FILM_H = 8
+    try:
+        r = bench.parity_check(u, None, u.get_int_config("volpathsimple-drt").create(max_depth=4),
+                               {"medium.sigma_t.data": sig, "medium.albedo.data": alb},
+                               u.benchmark_scene(8, 8, 8, majorant_resolution_factor=2), sig, alb)
+    finally:
+        bench.FILM_W, bench.FILM_H = old
+    assert set(r) == {"error"} and "AttributeError" in r["error"]
 
 
 def test_batch_index_sampler_matches_oracle(uivr, oracle):
