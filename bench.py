@@ -191,6 +191,39 @@ def parity_check(u, scene, integ, params, vol, sig_h, alb_h, spp: int = 2):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def parity_only() -> int:
+    """`bench.py --parity-only`: the parity leg in a process of its own (prints one JSON object)."""
+    import torch
+    import uivr_b200 as u
+    try:
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        sig_h, alb_h = u.synthetic_grids(GRID_N)
+        vol = u.benchmark_scene(GRID_N, FILM_W, FILM_H, scale=8.0, majorant_resolution_factor=8)
+        scene = u.Scene(vol, device=dev.index)
+        integ = u.get_int_config("volpathsimple-drt").create(max_depth=64)
+        params = {"medium.sigma_t.data": sig_h.to(dev), "medium.albedo.data": alb_h.to(dev)}
+        out = parity_check(u, scene, integ, params, vol, sig_h, alb_h)
+    except Exception as e:  # noqa: BLE001
+        out = {"error": f"{type(e).__name__}: {e}"}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def parity_in_child(timeout_s: int = 180) -> dict:
+    """Runs the parity leg in a child process, so that nothing it does (a crash included) can reach the
+    process that holds the measurement."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--parity-only"], capture_output=True,
+                           text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"parity process exited with {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline(target_s: float = 12.0):
     """The CPU oracle (kind 'port': C restatement of the reference algorithm, pthreads over all
     host cores) on a bounded sample of config 3: same grids / camera / flags, reduced spp."""
@@ -458,7 +491,7 @@ def run_native(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-            line["parity"] = parity_check(u, scene, integ, params, vol, sig_h, alb_h)
+            line["parity"] = parity_in_child()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -472,10 +505,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--parity-only", action="store_true", help="internal: run the parity leg and print its JSON object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         print(f"note: warmup {args.warmup} < 3 breaks the timing rules; use only for profiling runs", file=sys.stderr)
+    if args.parity_only:
+        return parity_only()
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "RANK" not in os.environ:
