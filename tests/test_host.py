@@ -332,6 +332,14 @@ def test_run_helpers(uivr):
     for _ in range(100):
         u32, x = r.next_uint32(), f.next_float32()
         assert 0.0 <= x < 1.0 and x == float(np.float32((u32 >> 9) * 2.0 ** -23))
+    # the scalar generator and the vectorised one of batched.py (seeded through TEA like the `independent`
+    # sampler) are the same PCG32
+    Bm = __import__("importlib").import_module(uivr.__name__ + ".batched")
+    vec = Bm._Pcg32(seed=99, n=5)
+    v0, v1 = Bm._tea(np.full(5, 99, dtype=np.uint32), np.arange(5, dtype=np.uint32))
+    scal = [uivr.PCG32(initstate=int(a), initseq=int(b)) for a, b in zip(v0, v1)]
+    for _ in range(20):
+        assert list(vec.next_1d()) == [np.float32(g.next_float32()) for g in scal]
     # optimize.py:36-41
     assert uivr.reference_pass_plan((720, 720), 8192, 720 * 720 * 2048) == (4, 2048)
     assert uivr.reference_pass_plan((720, 620), 8192, 720 * 720 * 2048) == (4, 2048)
@@ -388,6 +396,12 @@ def test_exr_against_opencv(uivr, tmp_path):
     open(f, "wb").write(b"not an exr file at all")
     with pytest.raises(ValueError, match="not an OpenEXR"):
         uivr.read_exr(f)
+    # reference images with an alpha channel load as RGB (optimize.py:75-88 reads whatever the file holds)
+    rgba = rng.random((6, 5, 4)).astype(np.float32)
+    uivr.write_exr(f, rgba)
+    refs = uivr.load_reference_images({3: f, 7: f}, batchify=True)
+    assert tuple(refs.shape) == (2, 6, 5, 3) and np.array_equal(refs[1].numpy(), rgba[..., :3])
+    assert set(uivr.load_reference_images({3: f})) == {3}
 
 
 def test_run_optimization_control_flow_with_a_stand_in_renderer(uivr, tmp_path, monkeypatch):

@@ -264,9 +264,11 @@ def get_reference_image_paths(scene_config, overwrite: bool = False, device: Opt
 
 def load_reference_images(paths: Dict[int, str], batchify: bool = False, device=None):
     """optimize.py:75-88: one [n, H, W, C] tensor in the order of `paths` (ray batches) or {sensor: [H, W, C]}."""
+    def rgb(f):  # the path renders RGB; an alpha channel in a foreign reference file is not compared
+        return np.ascontiguousarray(read_exr(f)[..., :3])
     if batchify:
-        return torch.from_numpy(np.stack([read_exr(f) for f in paths.values()])).to(device)
-    return {s: torch.from_numpy(read_exr(f)).to(device) for s, f in paths.items()}
+        return torch.from_numpy(np.stack([rgb(f) for f in paths.values()])).to(device)
+    return {s: torch.from_numpy(rgb(f)).to(device) for s, f in paths.items()}
 
 
 def initial_resolution(shape: Sequence[int], upsample) -> Tuple[int, ...]:
