@@ -532,3 +532,44 @@ def test_exr_roundtrip_properties(uivr, tmp_path):
 
     images()
     codec()
+
+
+def test_radiance_hdr_against_opencv_and_envmap_from_file(uivr, tmp_path):
+    """read_hdr / write_hdr (the reference's envmap format, scene_config.py `envmap_filename: *.hdr`) against
+    OpenCV's codec -- run-length encoded and flat scanlines, widths outside the RLE range -- and
+    EnvMap.from_file for .hdr / .exr."""
+    cv2 = pytest.importorskip("cv2")
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    rng = np.random.default_rng(11)
+    f = str(tmp_path / "a.hdr")
+    for shape in ((5, 7, 3), (33, 20, 3), (16, 64, 3), (3, 300, 3), (2, 8, 3)):
+        a = (rng.random(shape) ** 4 * 50).astype(np.float32)
+        a[0, 0] = 0
+        a[1, 1] = (1e-6, 2e-6, 0)
+        a[:, :shape[1] // 2] = a[:, :1]                       # constant stretches: runs in the RLE stream
+        tol = a.max(axis=2, keepdims=True) / 128 + 1e-30      # shared exponent: 8 bits relative to the largest channel
+        cv2.imwrite(f, a[..., ::-1])                          # OpenCV writes run-length encoded scanlines
+        got = uivr.read_hdr(f)
+        assert np.array_equal(got, cv2.imread(f, cv2.IMREAD_UNCHANGED)[..., ::-1]) and np.all(np.abs(got - a) <= tol)
+        uivr.write_hdr(f, a)                                  # flat scanlines
+        back = uivr.read_hdr(f)
+        assert np.array_equal(back, cv2.imread(f, cv2.IMREAD_UNCHANGED)[..., ::-1]) and np.array_equal(back, got)
+    env = uivr.EnvMap.from_file(f, scale=1.5)
+    assert np.array_equal(env.image, back) and env.scale == 1.5 and env.tables()["env_w"] == 8
+    g = str(tmp_path / "a.exr")
+    lat = (rng.random((6, 12, 3)) + 0.1).astype(np.float32)
+    lat[0, 0] = (-1.0, np.nan, np.inf)                        # bad texels of captured maps are zeroed
+    uivr.write_exr(g, lat)
+    env = uivr.EnvMap.from_file(g, to_world=((0, 0, 1), (0, 1, 0), (-1, 0, 0)))
+    assert np.array_equal(env.image[1:], lat[1:]) and np.all(env.image[0, 0] == 0) and env.tables()["env_h"] == 6
+    with pytest.raises(ValueError, match="unsupported environment map format"):
+        uivr.EnvMap.from_file(str(tmp_path / "a.png"))
+    open(f, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_xyze\n\n-Y 1 +X 1\n\0\0\0\0")
+    with pytest.raises(NotImplementedError, match="xyze"):
+        uivr.read_hdr(f)
+    open(f, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n+Y 1 +X 1\n\0\0\0\0")
+    with pytest.raises(NotImplementedError, match="orientation"):
+        uivr.read_hdr(f)
+    open(f, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 2\n\0\0\0\0")
+    with pytest.raises(ValueError, match="truncated"):
+        uivr.read_hdr(f)

@@ -84,6 +84,21 @@ class EnvMap:
     scale: float = 1.0
     to_world: Tuple[Tuple[float, float, float], ...] = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
 
+    @classmethod
+    def from_file(cls, path: str, scale: float = 1.0, to_world=None) -> "EnvMap":
+        """Mitsuba's `envmap` `filename` (`envmap_filename` of python/scene_config.py:102-340): a Radiance
+        `.hdr` or an OpenEXR lat-long image; negative / non-finite texels (seen in captured maps) become 0."""
+        if path.lower().endswith((".hdr", ".rgbe", ".pic")):
+            from .rgbe import read_hdr
+            img = read_hdr(path)
+        elif path.lower().endswith(".exr"):
+            from .exr import read_exr
+            img = read_exr(path)[..., :3]
+        else:
+            raise ValueError(f"unsupported environment map format: {path}")
+        img = np.where(np.isfinite(img) & (img > 0), img, 0.0).astype(np.float32)
+        return cls(img, scale) if to_world is None else cls(img, scale, to_world)
+
     def tables(self) -> Dict[str, object]:
         """Built once per EnvMap object (the image is treated as immutable)."""
         cached = getattr(self, "_tables", None)
