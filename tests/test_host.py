@@ -373,7 +373,7 @@ def test_exr_against_opencv(uivr, tmp_path):
         ok = cv2.imwrite(f, np.zeros((2, 2, 3), np.float32)) and cv2.imread(f, cv2.IMREAD_UNCHANGED) is not None
     except cv2.error:
         ok = False
-    for shape in ((5, 7, 3), (33, 20, 3), (16, 16, 4), (1, 1, 3)):
+    for shape in ((5, 7, 3), (33, 20, 3), (16, 16, 4), (1, 1, 3), (70, 129, 3)):
         a = (rng.random(shape) * 10 - 2).astype(np.float32)
         bgr = [2, 1, 0] + ([3] if shape[2] == 4 else [])
         for comp in ("NONE", "ZIPS", "ZIP"):
@@ -386,8 +386,17 @@ def test_exr_against_opencv(uivr, tmp_path):
             assert np.array_equal(uivr.read_exr(f), a)
             cv2.imwrite(f, a[..., bgr], [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF])
             assert np.array_equal(uivr.read_exr(f), a.astype(np.float16).astype(np.float32))
-            cv2.imwrite(f, a[..., bgr], [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
-            with pytest.raises(NotImplementedError, match="PIZ"):
+            # PIZ (wavelet + Huffman; what mi.Bitmap.write and HDRI libraries produce) is read, not written:
+            # noise exercises the 16-bit wavelet path, a smooth image the 14-bit path and the run-length symbol
+            yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+            smooth = np.stack([np.sin(xx / 7.0 + k) * np.cos(yy / 5.0) + 1.5 for k in range(shape[2])], -1).astype(np.float32)
+            for img in (a, smooth, np.full(shape, 0.25, np.float32)):
+                for extra, want in (([], img), ([cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF],
+                                                img.astype(np.float16).astype(np.float32))):
+                    cv2.imwrite(f, img[..., bgr], [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ] + extra)
+                    assert np.array_equal(uivr.read_exr(f), want), shape
+            cv2.imwrite(f, a[..., bgr], [cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_RLE])
+            with pytest.raises(NotImplementedError, match="RLE"):
                 uivr.read_exr(f)
     with pytest.raises(NotImplementedError):
         uivr.write_exr(f, a, "PIZ")
@@ -532,6 +541,30 @@ def test_exr_roundtrip_properties(uivr, tmp_path):
 
     images()
     codec()
+
+    # damaged files end in ValueError (or decode to something), never in a hang or another exception type
+    cv2 = pytest.importorskip("cv2")
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:40, 0:33]
+    img = np.stack([np.sin(xx / 5.0 + k) + 1.2 + 0.05 * rng.random((40, 33)) for k in range(3)], -1).astype(np.float32)
+    for code in (cv2.IMWRITE_EXR_COMPRESSION_PIZ, cv2.IMWRITE_EXR_COMPRESSION_ZIP):
+        try:
+            if not cv2.imwrite(f, img, [cv2.IMWRITE_EXR_COMPRESSION, code]):
+                continue
+        except cv2.error:
+            continue
+        good = open(f, "rb").read()
+        assert uivr.read_exr(f).shape == (40, 33, 3)
+        for trial in range(60):
+            bad = bytearray(good)
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(300, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+            open(f, "wb").write(bytes(bad[:len(bad) - int(rng.integers(0, 50)) * (trial % 3 == 0)]))
+            try:
+                uivr.read_exr(f)
+            except (ValueError, NotImplementedError):
+                pass
 
 
 def test_radiance_hdr_against_opencv_and_envmap_from_file(uivr, tmp_path):
