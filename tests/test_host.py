@@ -517,6 +517,24 @@ def test_run_optimization_control_flow_with_a_stand_in_renderer(uivr, tmp_path, 
         uivr.run_optimization(out, uivr.OptimizationConfig("b", spp=2, n_iter=8, lr=0.05, upsample=[0.1, 0.2, 0.3, 0.4]),
                               sc, "volpathsimple-drt")
 
+    # --- warm start: start_from_value None keeps "what the scene file holds" (optimize.py:141-144), given here as the
+    # path of a .vol checkpoint (how the reference chains its nerf results into the next run, scene_config.py)
+    warm = np.random.default_rng(2).random((16, 16, 16, 1)).astype(np.float32)
+    vol_path = str(tmp_path / "warm-medium1_sigma_t.vol")
+    uivr.write_vol(vol_path, warm)
+    sc2 = _scene_config(uivr, volume=uivr.benchmark_scene(16, 16, 12), references=sc.references, ref_spp=100,
+                        ref_params={KEYS[0]: vol_path, KEYS[1]: alb}, sensors=[0, 2, 3],
+                        start_from_value={KEYS[0]: None, KEYS[1]: 0.5}, initial_params={KEYS[0]: vol_path})
+    oc = uivr.OptimizationConfig("w", spp=1, n_iter=1, lr=0.0, opt_type="sgd", render_initial=False, render_final=False,
+                                 checkpoint_final=False)
+    scene, params, opt = uivr.run_optimization(str(tmp_path / "warm"), oc, sc2, "volpathsimple-drt")
+    assert np.array_equal(params[KEYS[0]].numpy(), warm) and float(params[KEYS[1]].mean()) == 0.5
+    got, _, _ = uivr.read_vol(str(tmp_path / "warm" / "params" / "initial-medium1_sigma_t.vol"))
+    assert np.array_equal(got, warm)
+    with pytest.raises(AssertionError):                      # a kept grid cannot be combined with upsampling (optimize.py:142)
+        uivr.run_optimization(out, uivr.OptimizationConfig("w", spp=1, n_iter=4, lr=0.0, opt_type="sgd", upsample=[0.5]),
+                              sc2, "volpathsimple-drt")
+
 
 def test_exr_roundtrip_properties(uivr, tmp_path):
     """Round trips on arbitrary float bit patterns (NaN payloads, infinities, denormals, -0) and image

@@ -211,6 +211,18 @@ def _cuda_device(device: Optional[int]) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device() if device is None else device)
 
 
+def _as_grid(value, dev) -> torch.Tensor:
+    """A parameter grid given as data or as the path of a `.vol` file (the reference names its volumes by
+    file: `medium_filename`, `albedo_filename`, scene_config.py:102-340) -> float32 (Z, Y, X, C) on `dev`."""
+    if isinstance(value, (str, os.PathLike)):
+        from .multires import read_vol
+        value = read_vol(os.fspath(value))[0]
+    t = torch.as_tensor(value).to(device=dev, dtype=torch.float32)
+    if t.dim() == 3:
+        t = t.unsqueeze(-1)
+    return t.contiguous().clone()
+
+
 def _grid_shape(volume, key: str) -> Tuple[int, int, int, int]:
     x, y, z = volume.res
     return (z, y, x, 1 if key.endswith(SIGMA_T_SUFFIX) else 3)
@@ -237,7 +249,7 @@ def render_reference_image(scene_config, to_render: Dict[int, str], seed: int = 
     if not scene_config.ref_params:
         raise ValueError(f"scene config '{scene_config.name}' has no ref_params to render references from")
     dev = _cuda_device(device)
-    params = {k: torch.as_tensor(v).to(device=dev, dtype=torch.float32).contiguous() for k, v in scene_config.ref_params.items()}
+    params = {k: _as_grid(v, dev) for k, v in scene_config.ref_params.items()}
     k_sig = next(k for k in params if k.endswith(SIGMA_T_SUFFIX))
     scene = _bound_scene(scene_config.ref_volume, params[k_sig].shape, dev.index)
     integrator = load_dict({"type": scene_config.ref_integrator, "max_depth": scene_config.max_depth})
@@ -292,7 +304,7 @@ def initialize_scene(opt_config, scene_config, device: Optional[int] = None):
         assert k in scene_config.param_keys
         if v is None:                                            # keep what the scene file holds
             assert not opt_config.upsample
-            params[k] = torch.as_tensor(scene_config.initial_params[k]).to(device=dev, dtype=torch.float32).contiguous().clone()
+            params[k] = _as_grid(scene_config.initial_params[k], dev)
             continue
         init_res = initial_resolution(_grid_shape(scene_config.volume, k), opt_config.upsample)
         if opt_config.upsample and ".sigma_t." in k:
