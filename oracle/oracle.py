@@ -246,6 +246,20 @@ def build_majorant(sigma_t, scale: float, factor: int) -> np.ndarray:
     return out
 
 
+def build_exit_mask(majorant) -> np.ndarray:
+    """(MZ,MY,MX) uint8: bit o of a cell = only empty supergrid cells ahead in octant o (uivr_oracle.c)."""
+    majorant = _f32(majorant)
+    mz, my, mx = majorant.shape
+    out = np.zeros((mz, my, mx), dtype=np.uint8)
+    lib().uivr_oracle_build_exit_mask(_ptr(majorant, C.c_float), (C.c_int32 * 3)(mx, my, mz), _ptr(out, C.c_uint8))
+    return out
+
+
+def set_exit_mask(enable: bool) -> None:
+    """Test hook: walks stop early in empty space (default) or always run to the medium boundary."""
+    lib().uivr_oracle_set_exit_mask(1 if enable else 0)
+
+
 def adam_step(param, grad, m, v, lr, beta1, beta2, eps, t, lo, hi):
     """In place on float32 arrays: mi.ad.Adam step + clip (optimize.py:169-179, :352-353)."""
     n = param.size

@@ -208,6 +208,7 @@ typedef struct {
     int32_t mres[3];
     float mcs[3];          /* supergrid cell size 1/M */
     float* majorant;
+    uint8_t* exit_mask;    /* per supergrid cell: bit o = nothing but empty cells ahead in octant o (see below) */
     float half_le[3];      /* 0.5 * radiance: NEE weight phase*mis*Le/pdf folded */
     /* adjoint accumulation (shared between threads, CAS-atomic doubles) */
     double* dsigma;
@@ -357,6 +358,32 @@ void uivr_oracle_build_majorant(const float* sigma_t, const int32_t res[3], floa
                         }
                 out[((size_t) cz * mres[1] + cy) * mres[0] + cx] = scale * m;
             }
+}
+
+/* Exit mask of the supergrid [part of OUR definition of Medium::sample_interaction, App. B.5]: bit o of
+ * cell c is set iff the majorant is 0 in every cell of the box spanned by c and the grid corner that
+ * octant o points to (octant bit a = the ray direction is negative along axis a).  A walk that enters
+ * such a cell can only meet empty cells from there on, so it ends without a collision right away;
+ * results are those of walking on to the boundary, only the number of supergrid reads changes. */
+void uivr_oracle_build_exit_mask(const float* majorant, const int32_t mres[3], uint8_t* out) {
+    const int mx = mres[0], my = mres[1], mz = mres[2];
+    for (int o = 0; o < 8; ++o) {
+        const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+        /* visit the cells so that the three neighbours ahead (c + s_a e_a) are done first */
+        for (int kz = 0; kz < mz; ++kz)
+            for (int ky = 0; ky < my; ++ky)
+                for (int kx = 0; kx < mx; ++kx) {
+                    const int x = sx > 0 ? mx - 1 - kx : kx, y = sy > 0 ? my - 1 - ky : ky, z = sz > 0 ? mz - 1 - kz : kz;
+                    const size_t c = ((size_t) z * my + y) * mx + x;
+                    int e = !(majorant[c] > 0.0f);
+                    if (o == 0) out[c] = 0;
+                    const int nx = x + sx, ny = y + sy, nz = z + sz;
+                    if (e && nx >= 0 && nx < mx) e = (out[((size_t) z * my + y) * mx + nx] >> o) & 1;
+                    if (e && ny >= 0 && ny < my) e = (out[((size_t) z * my + ny) * mx + x] >> o) & 1;
+                    if (e && nz >= 0 && nz < mz) e = (out[((size_t) nz * my + y) * mx + x] >> o) & 1;
+                    if (e) out[c] |= (uint8_t) (1u << o);
+                }
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -528,6 +555,12 @@ static inline float mis_power(float a, float b) {
     return a > 0.0f ? a2 / FMA(b, b, a2) : 0.0f;
 }
 
+/* analysis hooks (scripts/dda_stats.c counts supergrid steps by kind); no-ops in the oracle build */
+#ifndef UIVR_ORACLE_WALK_HOOK
+#define UIVR_ORACLE_WALK_HOOK(C, s, w)
+#define UIVR_ORACLE_STEP_HOOK(C, w)
+#endif
+
 /* Medium::sample_interaction with supergrid DDA [UPSTREAM App. B.5, a14]; the DDA state is
  * carried along the segment instead of being restarted per call (same distribution). */
 typedef struct {
@@ -535,6 +568,7 @@ typedef struct {
     int cell[3], step[3];
     float tn[3], dt[3];
     float sig_bar;
+    int octant;            /* bit a: d[a] < 0 */
 } walk_t;
 
 static inline float majorant_at(const ctx_t* C, counters_t* K, const int cell[3]) {
@@ -542,9 +576,22 @@ static inline float majorant_at(const ctx_t* C, counters_t* K, const int cell[3]
     return C->majorant[((size_t) cell[2] * C->mres[1] + cell[1]) * C->mres[0] + cell[0]];
 }
 
+/* test hook: with the exit mask switched off every walk runs on to the boundary; radiance and gradients
+ * must not change by a single bit (tests/test_oracle.py), only the number of supergrid reads does */
+static int g_use_exit_mask = 1;
+void uivr_oracle_set_exit_mask(int enable) { g_use_exit_mask = enable; }
+
+/* the walk has entered a cell behind which (along the ray's octant) every cell is empty */
+static inline int walk_sees_exit(const ctx_t* C, const walk_t* w) {
+    if (!g_use_exit_mask) return 0;
+    const size_t c = ((size_t) w->cell[2] * C->mres[1] + w->cell[1]) * C->mres[0] + w->cell[0];
+    return !(w->sig_bar > 0.0f) && ((C->exit_mask[c] >> w->octant) & 1);
+}
+
 static void walk_init(const ctx_t* C, counters_t* K, const seg_t* s, walk_t* w) {
     w->t = 0.0f;
     w->tmax = s->tmax;
+    w->octant = (s->d[0] < 0.0f ? 1 : 0) | (s->d[1] < 0.0f ? 2 : 0) | (s->d[2] < 0.0f ? 4 : 0);
     for (int a = 0; a < 3; ++a) {
         int c = (int) floorf(s->o[a] * (float) C->mres[a]);
         c = clampi(c, 0, C->mres[a] - 1);
@@ -564,6 +611,7 @@ static void walk_init(const ctx_t* C, counters_t* K, const seg_t* s, walk_t* w) 
         }
     }
     w->sig_bar = majorant_at(C, K, w->cell);
+    UIVR_ORACLE_WALK_HOOK(C, s, w);
 }
 
 /* next tentative collision for uniform u; returns 0 when the segment end is reached */
@@ -571,6 +619,8 @@ static int walk_next(const ctx_t* C, counters_t* K, walk_t* w, float u, float* t
                      float* sig_bar_out) {
     float tau = neg_log1m(u);
     for (;;) {
+        UIVR_ORACLE_STEP_HOOK(C, w);
+        if (walk_sees_exit(C, w)) return 0;
         int ax = 0;
         if (w->tn[1] < w->tn[ax]) ax = 1;
         if (w->tn[2] < w->tn[ax]) ax = 2;
@@ -1188,6 +1238,9 @@ static int setup_ctx(ctx_t* C, const uivr_oracle_scene* sc, const float* sigma_t
     C->majorant = (float*) malloc(sizeof(float) * (size_t) m[0] * m[1] * m[2]);
     if (!C->majorant) return -1;
     uivr_oracle_build_majorant(sigma_t, sc->res, sc->scale, sc->majorant_factor, C->mres, C->majorant);
+    C->exit_mask = (uint8_t*) malloc((size_t) m[0] * m[1] * m[2]);
+    if (!C->exit_mask) { free(C->majorant); return -1; }
+    uivr_oracle_build_exit_mask(C->majorant, C->mres, C->exit_mask);
     for (int a = 0; a < 3; ++a) {
         C->mcs[a] = 1.0f / (float) C->mres[a];
         C->half_le[a] = 0.5f * sc->radiance[a];
@@ -1245,6 +1298,7 @@ int uivr_oracle_render_forward(const uivr_oracle_scene* scene, const float* sigm
     }
     free(acc);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1267,6 +1321,7 @@ int uivr_oracle_render_backward(const uivr_oracle_scene* scene, const float* sig
         memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * scene->height * (size_t) spp_grad);
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, shard, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1291,6 +1346,7 @@ int uivr_oracle_render_batch_forward(const uivr_oracle_scene* scene, const uivr_
     }
     free(acc);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1313,6 +1369,7 @@ int uivr_oracle_render_batch_backward(const uivr_oracle_scene* scene, const uivr
     if (sample_L_out) memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * (size_t) spp_grad);
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, NULL, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1338,6 +1395,7 @@ int uivr_oracle_nerf_forward(const uivr_oracle_scene* scene, const uivr_oracle_n
     }
     free(acc);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1364,6 +1422,7 @@ int uivr_oracle_nerf_backward(const uivr_oracle_scene* scene, const uivr_oracle_
         memset(sample_L_out, 0, sizeof(float) * 3 * (size_t) scene->width * scene->height * (size_t) spp_grad);
     int rc = run(&C, 1, seed_grad, (uint32_t) spp_grad, shard, nthreads, grad_image, NULL, sample_L_out, counters);
     free(C.majorant);
+    free(C.exit_mask);
     return rc;
 }
 
@@ -1387,6 +1446,7 @@ uivr_oracle_shim* uivr_oracle_shim_create(const uivr_oracle_scene* scene, const 
 void uivr_oracle_shim_destroy(uivr_oracle_shim* h) {
     if (!h) return;
     free(h->C.majorant);
+    free(h->C.exit_mask);
     free(h);
 }
 

@@ -124,6 +124,11 @@ void  uivr_oracle_trilinear(const float* grid, const int32_t res[3], int channel
 void  uivr_oracle_build_majorant(const float* sigma_t, const int32_t res[3], float scale,
                                  int32_t factor, int32_t mres[3], float* out);
 
+/* exit mask of the supergrid (one byte per cell, bit o: only empty cells ahead in octant o; octant bit a =
+ * ray direction negative along axis a): lets a walk stop as soon as nothing but empty space is ahead */
+void  uivr_oracle_build_exit_mask(const float* majorant, const int32_t mres[3], uint8_t* out);
+void  uivr_oracle_set_exit_mask(int enable);  /* test hook (default on) */
+
 /* ---- the path ---- */
 /* image_out: H*W*3 (overwritten; pixels outside the shard are zero).
  * sample_L_out: optional (NULL) S*3 per-sample radiance, S = W*H*spp.

@@ -150,6 +150,53 @@ def test_majorant_bounds_the_density(oracle, n, factor):
     assert maj.min() < maj.max()
 
 
+def test_exit_mask_against_brute_force(oracle):
+    """bit o of a cell <=> every cell of the box between the cell and the grid corner of octant o is empty."""
+    rng = np.random.default_rng(5)
+    for shape in ((5, 4, 6), (8, 8, 8), (1, 3, 2)):
+        maj = (rng.random(shape) * (rng.random(shape) < 0.25)).astype(np.float32)
+        mask = oracle.build_exit_mask(maj)
+        mz, my, mx = shape
+        empty = ~(maj > 0)
+        for o in range(8):
+            for z in range(mz):
+                for y in range(my):
+                    for x in range(mx):
+                        xs = slice(None, x + 1) if o & 1 else slice(x, None)
+                        ys = slice(None, y + 1) if o & 2 else slice(y, None)
+                        zs = slice(None, z + 1) if o & 4 else slice(z, None)
+                        assert bool((mask[z, y, x] >> o) & 1) == bool(empty[zs, ys, xs].all()), (shape, o, z, y, x)
+
+
+def test_exit_mask_changes_nothing_but_the_supergrid_reads(oracle, uivr):
+    """Stopping a walk once only empty cells are ahead is an optimisation of the supergrid traversal, not
+    a change of the estimator: per-sample radiance and gradients are bit-identical with it switched off."""
+    n = 16
+    sig, alb = hetero_grids(n, seed=3)
+    vol = uivr.cube_test_scene(24, 20, density_scale=5.0, res=(n, n, n))
+    vol.majorant_resolution_factor = 2
+    desc = vol.as_dict()
+    props = dict(max_depth=12, use_nee=True, **FLAG_COMBOS["volpathsimple-drt"])
+    out = []
+    try:
+        for on in (True, False):
+            oracle.set_exit_mask(on)
+            img, smp, cf = oracle.render_forward(desc, props, sig, alb, 11, 4, want_samples=True)
+            ds, da, smp_g, cb = oracle.render_backward(desc, props, sig, alb, loss_grad(img), 12, 4, want_samples=True,
+                                                       nthreads=1)
+            out.append((smp, smp_g, ds, da, cf, cb))
+    finally:
+        oracle.set_exit_mask(True)
+    a, b = out
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])   # one thread: same summation order
+    for k in ("sigma_taps", "albedo_taps", "rng_draws", "real_collisions", "sigma_scatters"):
+        assert a[4][k] == b[4][k] and a[5][k] == b[5][k]
+    # not vacuous: the mask saves supergrid reads on this scene
+    assert a[4]["majorant_reads"] < b[4]["majorant_reads"] and a[5]["majorant_reads"] < b[5]["majorant_reads"]
+
+
 # ---------------------------------------------------------------------------------------
 # KA1 / KA3: analytic known answers on homogeneous media
 # ---------------------------------------------------------------------------------------
