@@ -114,7 +114,7 @@ int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props);   /*
 
 /* Enter (batch != NULL) or leave (NULL) ray-batch mode.  In batch mode uivr_render_forward /
  * uivr_render_backward render the batch: d_image / d_grad_image are [B, 3]; the sensor and film of
- * uivr_set_scene are ignored; shards split the batch elements.  Needs kernel variant >= 2. */
+ * uivr_set_scene are ignored; shards split the batch elements.  Needs the slot-pool kernels (variant 3). */
 int uivr_set_batch(uivr_ctx* ctx, const uivr_batch_desc* batch);
 
 /* The scene's emitter is an `envmap` (lat-long environment map; every scene of
@@ -226,10 +226,11 @@ int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms);
 int uivr_check_watchdog(uivr_ctx* ctx, uint32_t out[64], void* stream);
 /* number of kernel launches issued by this context so far */
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
-/* kernel variant: 0 = persistent lane-refill megakernel, 1 = one-sample-per-lane,
- * 2 = persistent slot-pool megakernel (CTA-wide compaction through shared-memory queues),
- * 3 = slot-pool kernels with the backward split into primal replay -> adjoint replay -> DRT
- *     launches that hand per-sample state through context-owned HBM scratch (default) */
+/* kernel variant: 3 (default) = persistent slot-pool kernels (CTA-wide compaction of live rays through
+ * shared-memory queues; walker warps run the supergrid DDA, handler warps everything else in full batches;
+ * the backward runs as primal replay -> adjoint replay -> DRT launches that hand per-sample state through
+ * context-owned HBM scratch); 1 = one sample per lane, run to completion (in-GPU cross-check, and the
+ * O(n^2) `use_drt_subsampling = False` mode).  Other values: UIVR_ERR_INVALID. */
 int uivr_set_variant(uivr_ctx* ctx, int variant);
 
 /* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */
@@ -244,6 +245,10 @@ int uivr_test_sampler(uivr_ctx* ctx, uint32_t seed, uint32_t idx0, int nstreams,
 int uivr_test_sigma_lookup(uivr_ctx* ctx, const float* d_p, int n, float* d_out, void* stream);
 /* copy the current majorant supergrid to d_out (mres[0]*mres[1]*mres[2] floats) */
 int uivr_get_majorant(uivr_ctx* ctx, int32_t mres[3], float* d_out, void* stream);
+/* copy the walk table to d_out: (mres[2]+2)*(mres[1]+2)*(mres[0]+2) words, the supergrid with a one-cell
+ * border.  Non-empty cell: bits of its majorant; empty cell: 0x80000000 | exit mask (bit o: only empty
+ * cells ahead in octant o, octant bit a = direction negative along axis a); border: 0x800001FF. */
+int uivr_get_walk_table(uivr_ctx* ctx, int32_t mres[3], uint32_t* d_out, void* stream);
 uint32_t uivr_tea32(uint32_t v0, uint32_t v1);          /* mi.sample_tea_32(v0, v1)[0] */
 uint32_t uivr_alt_seed(uint32_t seed_grad);             /* volpathsimple.py:99-107 under mi.render */
 uint32_t uivr_alt_seed_batch(uint32_t seed_grad);       /* same under render_batch (no jitter draws, batched.py:390) */

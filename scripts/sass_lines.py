@@ -36,7 +36,7 @@ def main():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            start = name if pat in name else None
+            start = name if (pat in name and (opts.get("exclude") is None or opts["exclude"] not in name)) else None
             if start:
                 print("kernel:", name)
             continue

@@ -75,4 +75,4 @@ def random_case(uivr, seed):
         props["max_depth"] = min(props["max_depth"], 5)
     return dict(vol=vol, sig=sig[..., None].copy(), alb=alb, props=props, spp=int(rng.integers(1, 10)),
                 seed=int(rng.integers(0, 2 ** 32)), seed_grad=int(rng.integers(0, 2 ** 32)),
-                variant=int(rng.integers(0, 4)))
+                variant=int(rng.choice([1, 3])))

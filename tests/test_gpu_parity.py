@@ -60,7 +60,7 @@ def _run_backward(uivr, vol, props, sig, alb, gimg, seed, spp, dev, variant, sha
     return ds.cpu().numpy(), da.cpu().numpy(), samples.cpu().numpy(), cnt
 
 
-VARIANTS = [0, 1, 2, 3]
+VARIANTS = [1, 3]   # 3: slot-pool kernels (default); 1: one sample per lane (cross-check)
 
 
 # ---------------------------------------------------------------------------------------
@@ -114,6 +114,15 @@ def test_lookup_and_majorant_bit_exact(uivr, oracle, dev, n, factor):
     scene.ctx.get_majorant(dm.data_ptr())
     assert tuple(mref.shape[::-1]) == mres
     assert np.array_equal(dm.cpu().numpy().view(np.uint32), mref.reshape(-1).view(np.uint32))
+    # walk table: padded supergrid, majorant bits in dense cells, exit masks in empty ones
+    mz, my, mx = mref.shape
+    dw = torch.empty((mz + 2) * (my + 2) * (mx + 2), device=dev, dtype=torch.int32)
+    scene.ctx.get_walk_table(dw.data_ptr())
+    wt = dw.cpu().numpy().view(np.uint32).reshape(mz + 2, my + 2, mx + 2)
+    want = np.full_like(wt, 0x800001FF)
+    mask = oracle.build_exit_mask(mref)
+    want[1:-1, 1:-1, 1:-1] = np.where(mref > 0, mref.view(np.uint32), np.uint32(0x80000000) | mask.astype(np.uint32))
+    assert np.array_equal(wt, want)
 
 
 # ---------------------------------------------------------------------------------------
@@ -387,7 +396,7 @@ def test_error_behaviour(uivr, dev):
 # (the small cases above finish before a slot is reused)
 # ---------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("variant", [3])
 def test_steady_state_recycling_matches_oracle(uivr, oracle, dev, variant):
     """~0.9 M samples: each of the 148 CTAs recycles its slots ~8 times.  Per-sample radiance of
     the forward and of the primal replay bit-exact, event counters equal, gradients < 1e-3."""
@@ -540,7 +549,7 @@ def test_ragged_shapes(uivr, oracle, dev, variant):
 # ray-batch rendering (python/batched.py)
 # ---------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [3])
 def test_render_batch_matches_oracle(uivr, oracle, dev, variant):
     """render_batch: B (sensor, pixel) pairs x spp through the C-ABI in batch mode vs the oracle's
     restatement of batched.py: per-sample radiance bit-exact (primal at `seed`, primal replay at
@@ -615,9 +624,16 @@ def test_render_batch_autograd_and_rules(uivr, oracle, dev):
     assert rel_linf(params["m.albedo.data"].grad.cpu().numpy(), da_o) < GRAD_TOL
     with pytest.raises(Exception):
         uivr.render_batch(B, scene, sensors, params, integ, seed=5, seed_grad=5, spp=spp)
-    scene.ctx.set_variant(0)
+    # the O(n^2) mode runs on the one-sample-per-lane kernels, which generate sensor rays only: refused
+    quad = uivr.get_int_config("volpathsimple-drt-quadratic").create(max_depth=16)
+    with pytest.raises(uivr.NativeError):
+        img_q, _, _ = uivr.render_batch(B, scene, sensors, params, quad, seed=5, spp=spp)
+        img_q.sum().backward()
+    scene.ctx.set_variant(1)
     with pytest.raises(uivr.NativeError):
         uivr.render_batch(B, scene, sensors, params, integ, seed=5, spp=spp)
+    with pytest.raises(uivr.NativeError):
+        scene.ctx.set_variant(0)
 
 
 # ---------------------------------------------------------------------------------------

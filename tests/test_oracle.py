@@ -279,6 +279,176 @@ def test_ka3_white_furnace(uivr, oracle):
 
 
 # ---------------------------------------------------------------------------------------
+# KA2 + an independent primal estimator: checks of the NEE / MIS / ratio-tracking / supergrid arithmetic
+# against something that shares no code with the oracle (the role Mitsuba's stock `volpath` plays in the
+# reference's test_03, tests/test_integrators.py:222-257)
+# ---------------------------------------------------------------------------------------
+
+def _camera_rays(desc, u, v):
+    """World-space perspective rays through film positions (u, v) in [0,1]^2 (float64, written from the
+    sensor's definition: fov along x, look-at frame), independent of the oracle's camera code."""
+    cx = float(desc["tan_x"]) * (1.0 - 2.0 * u)
+    cy = float(desc["tan_y"]) * (1.0 - 2.0 * v)
+    d = (cx[:, None] * desc["cam_left"].astype(np.float64) + cy[:, None] * desc["cam_up"].astype(np.float64)
+         + desc["cam_dir"].astype(np.float64))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = np.broadcast_to(desc["cam_origin"].astype(np.float64), d.shape)
+    return o, d
+
+
+def _box_span(o, d, lo, hi):
+    """[t_near, t_far] of rays against an axis-aligned box; t_far <= max(t_near, 0) means a miss."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0, t1 = (lo - o) / d, (hi - o) / d
+    tn = np.max(np.minimum(t0, t1), axis=1)
+    tf = np.min(np.maximum(t0, t1), axis=1)
+    return np.maximum(tn, 0.0), tf
+
+
+def test_ka2_single_scatter_closed_form(uivr, oracle):
+    """Homogeneous medium, constant emitter, max_depth = 2: exactly one scattering order carries light.
+    E[R] = Le [ exp(-s l) + albedo * s * int_0^l exp(-s t) A(p(t)) dt ],  A(p) = (1/4pi) int exp(-s d(p, w)) dw
+    (d = distance from p to the box boundary along w): the NEE half (ratio-tracked transmittance, MIS 1/2) and
+    the phase-sampled half (escape after the vertex, MIS 1/2) must add up to the single-scatter integral, which
+    is evaluated here by plain quadrature in float64."""
+    n, w, spp = 4, 6, 8192
+    grid_val, scale, albedo = 0.8, 1.25, 0.7
+    s_t = grid_val * scale
+    sig = np.full((n, n, n, 1), grid_val, np.float32)
+    alb = np.full((n, n, n, 3), albedo, np.float32)
+    vol = uivr.cube_test_scene(w, w, density_scale=scale, res=(n, n, n))
+    desc = vol.as_dict()
+    props = dict(max_depth=2, use_nee=True, **FLAG_COMBOS["volpathsimple-basic"])
+    img, _, _ = oracle.render_forward(desc, props, sig, alb, 21, spp)
+    lo, hi = np.array(vol.bbox_min, dtype=np.float64), np.array(vol.bbox_min) + np.array(vol.bbox_extent)
+    # sphere quadrature: Gauss-Legendre in cos(theta) x uniform in phi
+    mu, wmu = np.polynomial.legendre.leggauss(24)
+    phi = (np.arange(48) + 0.5) * (2 * np.pi / 48)
+    sin_t = np.sqrt(1 - mu ** 2)
+    dirs = np.stack([np.outer(sin_t, np.cos(phi)).ravel(), np.outer(sin_t, np.sin(phi)).ravel(),
+                     np.repeat(mu, 48)], axis=1)
+    wdir = np.repeat(wmu, 48) * (2 * np.pi / 48) / (4 * np.pi)          # sums to 1
+
+    def sphere_mean_transmittance(p):
+        _, tf = _box_span(np.broadcast_to(p, dirs.shape), dirs, lo, hi)
+        return float(np.sum(wdir * np.exp(-s_t * tf)))
+
+    le = np.array(vol.radiance, dtype=np.float64)
+    tq, wq = np.polynomial.legendre.leggauss(32)
+    sub = (np.arange(3) + 0.5) / 3                                       # 3 x 3 positions per pixel (box filter)
+    worst = 0.0
+    for (px, py) in [(2, 3), (3, 2), (1, 1), (4, 4)]:
+        acc = 0.0
+        for jy in sub:
+            for jx in sub:
+                o, d = _camera_rays(desc, np.array([(px + jx) / w]), np.array([(py + jy) / w]))
+                tn, tf = _box_span(o, d, lo, hi)
+                ell = max(float(tf[0] - tn[0]), 0.0) if tf[0] > tn[0] else 0.0
+                val = math.exp(-s_t * ell)
+                if ell > 0:
+                    ts = 0.5 * ell * (tq + 1.0)
+                    inner = sum(wk * math.exp(-s_t * tk) * sphere_mean_transmittance(o[0] + (tn[0] + tk) * d[0])
+                                for tk, wk in zip(ts, wq)) * 0.5 * ell
+                    val += albedo * s_t * inner
+                acc += val / 9.0
+        expect = le * acc
+        worst = max(worst, float(np.max(np.abs(img[py, px] - expect) / le)))
+    # per-pixel Monte-Carlo error at 8192 spp: ~0.5 / sqrt(8192) = 0.006 (+ the 3x3 pixel quadrature)
+    assert worst < 0.025, worst
+    # not vacuous: the single-scatter term is a large part of these pixels
+    assert albedo * s_t > 0.5 and float(img.mean()) > 0.3
+
+
+def _naive_trilinear(grid, p):
+    """Trilinear lookup of a (Z,Y,X) grid at local points p in [0,1]^3 (voxel centres at (i + 0.5) / res, border
+    clamp) written directly from GridVolume's definition, float64."""
+    z, y, x = grid.shape
+    q = p * np.array([x, y, z]) - 0.5
+    i0 = np.floor(q).astype(int)
+    f = q - i0
+    out = np.zeros(p.shape[0])
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                ix = np.clip(i0[:, 0] + dx, 0, x - 1)
+                iy = np.clip(i0[:, 1] + dy, 0, y - 1)
+                iz = np.clip(i0[:, 2] + dz, 0, z - 1)
+                wgt = (f[:, 0] if dx else 1 - f[:, 0]) * (f[:, 1] if dy else 1 - f[:, 1]) * (f[:, 2] if dz else 1 - f[:, 2])
+                out += wgt * grid[iz, iy, ix]
+    return out
+
+
+def test_primal_against_an_independent_naive_estimator(uivr, oracle):
+    """The oracle's primal image (supergrid DDA + exit mask, NEE with ratio tracking, MIS) against a naive
+    estimator that shares none of that: numpy, float64, pure delta tracking against ONE global majorant, no
+    next-event estimation (light is only picked up when a path escapes), its own trilinear lookup, camera and
+    box intersection, numpy's random generator.  Same heterogeneous medium with empty space; both are unbiased
+    for the same max_depth-truncated transport, so the images agree to Monte-Carlo error."""
+    n, w, h, max_depth = 12, 10, 8, 12
+    scale = 6.0
+    sig, alb = hetero_grids(n, seed=4)
+    vol = uivr.cube_test_scene(w, h, density_scale=scale, res=(n, n, n))
+    vol.majorant_resolution_factor = 3
+    desc = vol.as_dict()
+    assert desc["majorant_factor"] == 3
+    props = dict(max_depth=max_depth, use_nee=True, **FLAG_COMBOS["volpathsimple-drt"])
+    img_o, _, _ = oracle.render_forward(desc, props, sig, alb, 77, 2048)
+
+    spp = 3000
+    rng = np.random.default_rng(123)
+    lo = np.array(vol.bbox_min, dtype=np.float64)
+    ext = np.array(vol.bbox_extent, dtype=np.float64)
+    grid = sig[..., 0].astype(np.float64) * scale
+    sig_bar = grid.max()
+    le = np.array(vol.radiance, dtype=np.float64)
+    pix = np.repeat(np.arange(w * h), spp)
+    N = pix.size
+    o, d = _camera_rays(desc, ((pix % w) + rng.random(N)) / w, ((pix // w) + rng.random(N)) / h)
+    tn, tf = _box_span(o, d, lo, lo + ext)
+    hit = tf > tn
+    beta = np.ones((N, 3))
+    R = np.zeros((N, 3))
+    R[~hit] = le
+    pos = o + (tn + 1e-9)[:, None] * d
+    alive = hit.copy()
+    depth = np.zeros(N, dtype=int)
+    for _ in range(100000):
+        idx = np.nonzero(alive)[0]
+        if idx.size == 0:
+            break
+        t = -np.log1p(-rng.random(idx.size)) / sig_bar
+        p_new = pos[idx] + t[:, None] * d[idx]
+        local = (p_new - lo) / ext
+        inside = np.all((local >= 0) & (local <= 1), axis=1)
+        esc = idx[~inside]
+        R[esc] += beta[esc] * le                       # the emitter is seen through the boundary
+        alive[esc] = False
+        idx, p_new, local = idx[inside], p_new[inside], local[inside]
+        pos[idx] = p_new
+        real = rng.random(idx.size) < _naive_trilinear(grid, local) / sig_bar
+        ridx, rloc = idx[real], local[real]
+        a = np.stack([_naive_trilinear(alb[..., c].astype(np.float64), rloc) for c in range(3)], axis=1)
+        beta[ridx] *= a
+        depth[ridx] += 1
+        dead = depth[ridx] >= max_depth                # volpathsimple.py:199-200: the path ends, nothing is added
+        alive[ridx[dead]] = False
+        zc = 1 - 2 * rng.random(ridx.size)
+        ph = 2 * np.pi * rng.random(ridx.size)
+        rr = np.sqrt(np.maximum(0, 1 - zc * zc))
+        d[ridx] = np.stack([rr * np.cos(ph), rr * np.sin(ph), zc], axis=1)
+    img_n = R.reshape(h, w, spp, 3).mean(axis=2)
+    var_n = R.reshape(h, w, spp, 3).var(axis=2) / spp
+    # per pixel: within 5 sigma of the combined Monte-Carlo error (the oracle's NEE estimator has the smaller one)
+    err = np.abs(img_n - img_o)
+    sigma = np.sqrt(var_n + var_n * spp / 2048.0) + 1e-3
+    assert np.all(err < 5 * sigma), float(np.max(err / sigma))
+    # whole image: relative difference of the means well below a percent
+    assert abs(img_n.mean() - img_o.mean()) / img_o.mean() < 6e-3
+    # not vacuous: the medium matters (image far from the bare emitter) and is heterogeneous
+    assert float(np.abs(img_o - le).max()) > 0.2 and float((sig == 0).mean()) > 0.2
+
+
+# ---------------------------------------------------------------------------------------
 # KA4: finite differences vs adjoint on the reference's 3^3 fixture
 # ---------------------------------------------------------------------------------------
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
     "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
-    "uivr_get_majorant", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
+    "uivr_get_majorant", "uivr_get_walk_table", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
     "uivr_nerf_forward", "uivr_nerf_backward", "uivr_test_exp", "uivr_set_envmap", "uivr_test_atan2_turns",
 ]
 
@@ -120,6 +120,7 @@ def lib():
         "uivr_test_sampler": ([vp, u32, u32, C.c_int, C.c_int, fp, vp], C.c_int),
         "uivr_test_sigma_lookup": ([vp, fp, C.c_int, fp, vp], C.c_int),
         "uivr_get_majorant": ([vp, C.POINTER(C.c_int32), fp, vp], C.c_int),
+        "uivr_get_walk_table": ([vp, C.POINTER(C.c_int32), fp, vp], C.c_int),
         "uivr_tea32": ([u32, u32], u32),
         "uivr_alt_seed": ([u32], u32),
         "uivr_alt_seed_batch": ([u32], u32),
@@ -339,4 +340,10 @@ class Context:
     def get_majorant(self, out_ptr: Optional[int] = None, stream=0):
         mres = (C.c_int32 * 3)()
         self._check(self._L.uivr_get_majorant(self._h, mres, out_ptr, stream), "uivr_get_majorant")
+        return tuple(int(v) for v in mres)
+
+    def get_walk_table(self, out_ptr: Optional[int] = None, stream=0):
+        """Padded supergrid + exit masks ((mres + 2)^3 uint32 words, include/uivr.h)."""
+        mres = (C.c_int32 * 3)()
+        self._check(self._L.uivr_get_walk_table(self._h, mres, out_ptr, stream), "uivr_get_walk_table")
         return tuple(int(v) for v in mres)

@@ -9,7 +9,6 @@
 #include <string>
 
 #include "uivr_kernels.cuh"
-#include "uivr_mega.cuh"
 #include "uivr_pool.cuh"
 #include "uivr_nerf.cuh"
 
@@ -27,6 +26,8 @@ struct uivr_ctx {
     size_t oct_cells = 0;
     float* maj = nullptr;
     size_t maj_cells = 0;
+    uint32_t* wtab = nullptr;       // walk table: padded supergrid + exit masks (Params::wtab)
+    uint8_t* emask[2] = {nullptr, nullptr};  // ping-pong buffers of the exit-mask sweeps
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
     unsigned int* debug = nullptr;  // [64] watchdog record of the slot-pool kernel
@@ -86,9 +87,9 @@ int check_ready(uivr_ctx* ctx) {
     return UIVR_OK;
 }
 
-// the slot-pool kernel packs depth into 16 bits and the supergrid step counters into 9 bits
+// the slot-pool kernels pack depth into 16 bits and the padded supergrid cell index into 28 bits
 bool pool_ok(const uivr_ctx* ctx) {
-    return ctx->variant >= 2 && ctx->props.max_depth < 65536 && ctx->mres[0] <= 512 && ctx->mres[1] <= 512 &&
+    return ctx->variant == 3 && ctx->props.max_depth < 65536 && ctx->mres[0] <= 512 && ctx->mres[1] <= 512 &&
            ctx->mres[2] <= 512;
 }
 
@@ -117,6 +118,8 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     memcpy(P.to_local, s.to_local, sizeof(P.to_local));
     P.oct = ctx->oct;
     P.maj = ctx->maj;
+    P.wtab = ctx->wtab;
+    for (int a = 0; a < 3; ++a) P.pm[a] = ctx->mres[a] + 2;
     P.scale = s.scale;
     P.tan_x = s.tan_x;
     P.tan_y = s.tan_y;
@@ -127,7 +130,7 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.inv_h = 1.0f / (float) P.height;
     if (ctx->batch_on) {
         if (volpath && !pool_ok(ctx))
-            return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering needs the slot-pool kernels (variant >= 2)");
+            return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering needs the slot-pool kernels (variant 3)");
         P.sensors = ctx->d_sensors;
         P.n_sensors = ctx->batch.n_sensors;
         P.film_w = ctx->batch.film_w;
@@ -245,7 +248,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -340,7 +343,7 @@ int uivr_set_counting(uivr_ctx* ctx, int enable) {
 }
 
 int uivr_set_variant(uivr_ctx* ctx, int variant) {
-    if (!ctx || variant < 0 || variant > 3) return UIVR_ERR_INVALID;
+    if (!ctx || (variant != 1 && variant != 3)) return UIVR_ERR_INVALID;
     ctx->variant = variant;
     return UIVR_OK;
 }
@@ -413,18 +416,28 @@ int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream) {
         if (ctx->mres[a] < 1) ctx->mres[a] = 1;
     }
     const size_t mcells = (size_t) ctx->mres[0] * ctx->mres[1] * ctx->mres[2];
+    const int mx = ctx->mres[0], my = ctx->mres[1], mz = ctx->mres[2];
+    const size_t pcells = (size_t) (mx + 2) * (my + 2) * (mz + 2);
     if (mcells != ctx->maj_cells) {
-        cudaFree(ctx->maj);
-        ctx->maj = nullptr;
+        cudaFree(ctx->maj); cudaFree(ctx->wtab); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]);
+        ctx->maj = nullptr; ctx->wtab = nullptr; ctx->emask[0] = ctx->emask[1] = nullptr;
         ctx->maj_cells = 0;
         UIVR_CUDA(ctx, cudaMalloc(&ctx->maj, mcells * sizeof(float)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->wtab, pcells * sizeof(uint32_t)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[0], mcells));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[1], mcells));
         ctx->maj_cells = mcells;
     }
     const int grid = ctx->num_sms * 8;
     k_build_octets<<<grid, kBlock, 0, st>>>(d_sigma_t, ctx->oct, s.res[0], s.res[1], s.res[2]);
-    k_build_majorant<<<grid, kBlock, 0, st>>>(d_sigma_t, ctx->maj, s.res[0], s.res[1], s.res[2], ctx->mres[0],
-                                               ctx->mres[1], ctx->mres[2], s.scale);
-    ctx->launches += 2;
+    k_build_majorant<<<grid, kBlock, 0, st>>>(d_sigma_t, ctx->maj, s.res[0], s.res[1], s.res[2], mx, my, mz, s.scale);
+    // exit mask: separable AND sweeps along x, y, z (one thread per grid line), then the padded walk table
+    const size_t sxy = (size_t) mx * my;
+    k_exit_sweep<<<(my * mz + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, nullptr, ctx->emask[0], mx, 1, my, (size_t) mx, mz, sxy, 1);
+    k_exit_sweep<<<(mx * mz + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, ctx->emask[0], ctx->emask[1], my, (size_t) mx, mx, 1, mz, sxy, 2);
+    k_exit_sweep<<<(mx * my + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, ctx->emask[1], ctx->emask[0], mz, sxy, mx, 1, my, (size_t) mx, 4);
+    k_build_walk_table<<<grid, kBlock, 0, st>>>(ctx->maj, ctx->emask[0], ctx->wtab, mx, my, mz);
+    ctx->launches += 6;
     UIVR_CUDA(ctx, cudaGetLastError());
     ctx->have_medium = true;
     return UIVR_OK;
@@ -449,7 +462,7 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], st));
-    if (ctx->variant == 1 || (ctx->env_on && !pool_ok(ctx))) {  // (the lane-refill megakernel has no envmap path)
+    if (!pool_ok(ctx)) {  // variant 1, or a scene outside the slot-pool kernels' packing limits
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_forward_v1<true>, kBlock, &grid))) return rc;
             k_forward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -457,10 +470,8 @@ int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int
             if ((rc = persistent_grid(ctx, k_forward_v1<false>, kBlock, &grid))) return rc;
             k_forward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
-    } else if (pool_ok(ctx)) {
-        if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     } else {
-        if ((rc = launch_mega(ctx->num_sms, false, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
+        if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
     }
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], st));
     ctx->ev_valid[0] = true;
@@ -494,8 +505,11 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     int grid = 0;
     // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
     const bool quadratic = ctx->props.use_drt && !ctx->props.use_drt_subsampling;
+    if (ctx->batch_on && quadratic)
+        return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering is not available for use_drt_subsampling = False "
+                                           "(the O(n^2) mode runs on the one-sample-per-lane kernels, which generate sensor rays only)");
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    if (ctx->variant == 1 || quadratic || (ctx->env_on && !pool_ok(ctx))) {
+    if (quadratic || !pool_ok(ctx)) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -503,44 +517,41 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             if ((rc = persistent_grid(ctx, k_backward_v1<false>, kBlock, &grid))) return rc;
             k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
-    } else if (pool_ok(ctx)) {
-        const bool split = ctx->variant == 3 && ctx->props.use_drt && ctx->props.use_drt_subsampling;
-        if (!split) {
-            if ((rc = launch_pool(ctx->num_sms, KIND_BWD, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
-        } else {
-            // split pipeline: primal replay (forward kernel, radiance per sample to HBM) -> adjoint replay
-            // (reservoir records to HBM) -> DRT pass.  Work counters: [0] primal, [1] adjoint, [2] DRT, [3] records.
-            const size_t n_global = (size_t) P.npix * P.spp, n_local = (size_t) P.n_slots * P.spp;
-            if (!P.sample_L) {
-                if (ctx->scratch_L_samples < n_global) {
-                    cudaFree(ctx->scratch_L);
-                    ctx->scratch_L = nullptr;
-                    ctx->scratch_L_samples = 0;
-                    UIVR_CUDA(ctx, cudaMalloc(&ctx->scratch_L, n_global * 3 * sizeof(float)));
-                    ctx->scratch_L_samples = n_global;
-                }
-                P.sample_L = ctx->scratch_L;
+    } else {
+        // pipeline: primal replay (forward kernel, radiance per sample to HBM) -> adjoint replay (reservoir
+        // records to HBM) -> DRT pass.  Work counters: [0] primal, [1] adjoint, [2] DRT, [3] records.
+        const bool drt_pass = ctx->props.use_drt != 0;
+        const size_t n_global = (size_t) P.npix * P.spp, n_local = (size_t) P.n_slots * P.spp;
+        if (!P.sample_L) {
+            if (ctx->scratch_L_samples < n_global) {
+                cudaFree(ctx->scratch_L);
+                ctx->scratch_L = nullptr;
+                ctx->scratch_L_samples = 0;
+                UIVR_CUDA(ctx, cudaMalloc(&ctx->scratch_L, n_global * 3 * sizeof(float)));
+                ctx->scratch_L_samples = n_global;
             }
-            if (ctx->records_cap < n_local) {
-                cudaFree(ctx->records);
-                ctx->records = nullptr;
-                ctx->records_cap = 0;
-                UIVR_CUDA(ctx, cudaMalloc(&ctx->records, n_local * kRecWords * sizeof(uint32_t)));
-                ctx->records_cap = n_local;
-            }
-            P.records = ctx->records;
-            P.rec_count = ctx->work_counter + 3;
-            Params PA = P;
-            PA.image = nullptr;
-            if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, PA, st))) return fail(ctx, rc, "pool kernel launch failed");
-            P.work_counter = ctx->work_counter + 1;
-            if ((rc = launch_pool(ctx->num_sms, KIND_ADJ, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+            P.sample_L = ctx->scratch_L;
+        }
+        if (drt_pass && ctx->records_cap < n_local) {
+            cudaFree(ctx->records);
+            ctx->records = nullptr;
+            ctx->records_cap = 0;
+            UIVR_CUDA(ctx, cudaMalloc(&ctx->records, n_local * kRecWords * sizeof(uint32_t)));
+            ctx->records_cap = n_local;
+        }
+        P.records = ctx->records;
+        P.rec_count = ctx->work_counter + 3;
+        Params PA = P;
+        PA.image = nullptr;
+        if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, PA, st))) return fail(ctx, rc, "pool kernel launch failed");
+        P.work_counter = ctx->work_counter + 1;
+        if ((rc = launch_pool(ctx->num_sms, KIND_ADJ, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
+        ctx->launches += 1;
+        if (drt_pass) {
             P.work_counter = ctx->work_counter + 2;
             if ((rc = launch_pool(ctx->num_sms, KIND_DRT, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
-            ctx->launches += 2;
+            ctx->launches += 1;
         }
-    } else {
-        if ((rc = launch_mega(ctx->num_sms, true, ctx->counting != 0, P, st))) return fail(ctx, rc, "mega kernel launch failed");
     }
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
     ctx->ev_valid[1] = true;
@@ -803,6 +814,17 @@ int uivr_get_majorant(uivr_ctx* ctx, int32_t mres[3], float* d_out, void* stream
     for (int a = 0; a < 3; ++a) mres[a] = ctx->mres[a];
     if (d_out)
         UIVR_CUDA(ctx, cudaMemcpyAsync(d_out, ctx->maj, ctx->maj_cells * sizeof(float), cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t) stream));
+    return UIVR_OK;
+}
+
+int uivr_get_walk_table(uivr_ctx* ctx, int32_t mres[3], uint32_t* d_out, void* stream) {
+    if (!ctx || !mres) return UIVR_ERR_INVALID;
+    if (!ctx->have_medium) return fail(ctx, UIVR_ERR_STATE, "uivr_update_medium has not been called");
+    for (int a = 0; a < 3; ++a) mres[a] = ctx->mres[a];
+    const size_t pcells = (size_t) (ctx->mres[0] + 2) * (ctx->mres[1] + 2) * (ctx->mres[2] + 2);
+    if (d_out)
+        UIVR_CUDA(ctx, cudaMemcpyAsync(d_out, ctx->wtab, pcells * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
                                        (cudaStream_t) stream));
     return UIVR_OK;
 }

@@ -26,6 +26,11 @@ struct Params {
     const float4* __restrict__ oct;     // corner octets: 2 x float4 per cell, ((z*OY+y)*OX+x)
     const float*  __restrict__ albedo;  // (Z,Y,X,3)
     const float*  __restrict__ maj;     // supergrid (MZ,MY,MX)
+    // walk table: the supergrid with a one-cell border, (MZ+2,MY+2,MX+2), one word per cell.  Non-empty cell:
+    // the bits of its majorant (> 0).  Empty cell: kWalkEmpty | exit mask (bit o: only empty cells ahead in
+    // octant o; octant bit a = direction negative along axis a).  Border: kWalkBorder (ends every walk).
+    const uint32_t* __restrict__ wtab;
+    int   pm[3];             // padded dims = mres + 2
     int   mres[3];
     float fmres[3];          // (float) mres
     float mcs[3];            // 1 / mres
@@ -211,6 +216,31 @@ UIVR_DEV float draw(Rng& r, Counters<COUNT>& K) {
 // --------------------------------------------------------------------------------------
 // grid lookups
 // --------------------------------------------------------------------------------------
+// Taps are gathers with little reuse (one 32-byte sector per sigma_t tap out of 537 MB, 8 x 12 bytes per albedo
+// tap): they read through the non-coherent path WITHOUT allocating in L1, so that what is left of the L1 /
+// shared-memory carve-out next to the slot pool keeps the walk table (157 KB at 256^3 / 8), which every DDA
+// step reads.  UIVR_TAP_NOALLOC=0 restores plain __ldg for A/B runs.
+#ifndef UIVR_TAP_NOALLOC
+#define UIVR_TAP_NOALLOC 1
+#endif
+UIVR_DEV float4 ldg_tap4(const float4* p) {
+#if UIVR_TAP_NOALLOC
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+UIVR_DEV float ldg_tap(const float* p) {
+#if UIVR_TAP_NOALLOC
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 UIVR_DEV bool inside_unit(float x, float y, float z) {
     return x >= 0.0f && x <= 1.0f && y >= 0.0f && y <= 1.0f && z >= 0.0f && z <= 1.0f;
 }
@@ -224,8 +254,8 @@ UIVR_DEV float sigma_tap(const Params& P, float px, float py, float pz) {
     float wx = qx - fx, wy = qy - fy, wz = qz - fz;
     int ix = (int) fx + 1, iy = (int) fy + 1, iz = (int) fz + 1;
     size_t cell = ((size_t) iz * P.ores[1] + iy) * P.ores[0] + ix;
-    const float4 a = __ldg(P.oct + 2 * cell);
-    const float4 b = __ldg(P.oct + 2 * cell + 1);
+    const float4 a = ldg_tap4(P.oct + 2 * cell);
+    const float4 b = ldg_tap4(P.oct + 2 * cell + 1);
     float c00 = lerpf(a.x, a.y, wx), c10 = lerpf(a.z, a.w, wx);
     float c01 = lerpf(b.x, b.y, wx), c11 = lerpf(b.z, b.w, wx);
     float c0 = lerpf(c00, c10, wy), c1 = lerpf(c01, c11, wy);
@@ -263,10 +293,10 @@ UIVR_DEV void albedo_tap(const Params& P, float px, float py, float pz, float a[
     const float* b111 = P.albedo + 3 * (g.z1 * sz + g.y1 * sy + g.x1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float c00 = lerpf(__ldg(b000 + c), __ldg(b100 + c), g.wx);
-        float c10 = lerpf(__ldg(b010 + c), __ldg(b110 + c), g.wx);
-        float c01 = lerpf(__ldg(b001 + c), __ldg(b101 + c), g.wx);
-        float c11 = lerpf(__ldg(b011 + c), __ldg(b111 + c), g.wx);
+        float c00 = lerpf(ldg_tap(b000 + c), ldg_tap(b100 + c), g.wx);
+        float c10 = lerpf(ldg_tap(b010 + c), ldg_tap(b110 + c), g.wx);
+        float c01 = lerpf(ldg_tap(b001 + c), ldg_tap(b101 + c), g.wx);
+        float c11 = lerpf(ldg_tap(b011 + c), ldg_tap(b111 + c), g.wx);
         a[c] = lerpf(lerpf(c00, c10, g.wy), lerpf(c01, c11, g.wy), g.wz);
     }
 }
@@ -347,13 +377,21 @@ UIVR_DEV bool make_segment(const Params& P, float px, float py, float pz, float 
 // F = sensor frame: origin[3] left[3] up[3] dir[3] tan_x tan_y near_clip; (u, v) = film position in [0,1]^2
 UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, float v, Seg& s);
 
-UIVR_DEV int camera_segment(const Params& P, uint32_t pix, float jx, float jy, Seg& s) {
+// the scene's own sensor: frame F and film position (u, v) of pixel `pix` with sub-pixel offset (jx, jy)
+UIVR_DEV void sensor_film_position(const Params& P, uint32_t pix, float jx, float jy, float F[15], float& u, float& v) {
     uint32_t px = pix % (uint32_t) P.width, py = pix / (uint32_t) P.width;
-    float u = ((float) px + jx) * P.inv_w;
-    float v = ((float) py + jy) * P.inv_h;
-    const float F[15] = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2], P.cam_left[0], P.cam_left[1], P.cam_left[2],
-                         P.cam_up[0], P.cam_up[1], P.cam_up[2], P.cam_dir[0], P.cam_dir[1], P.cam_dir[2],
-                         P.tan_x, P.tan_y, P.near_clip};
+    u = ((float) px + jx) * P.inv_w;
+    v = ((float) py + jy) * P.inv_h;
+    F[0] = P.cam_origin[0]; F[1] = P.cam_origin[1]; F[2] = P.cam_origin[2];
+    F[3] = P.cam_left[0]; F[4] = P.cam_left[1]; F[5] = P.cam_left[2];
+    F[6] = P.cam_up[0]; F[7] = P.cam_up[1]; F[8] = P.cam_up[2];
+    F[9] = P.cam_dir[0]; F[10] = P.cam_dir[1]; F[11] = P.cam_dir[2];
+    F[12] = P.tan_x; F[13] = P.tan_y; F[14] = P.near_clip;
+}
+
+UIVR_DEV int camera_segment(const Params& P, uint32_t pix, float jx, float jy, Seg& s) {
+    float F[15], u, v;
+    sensor_film_position(P, pix, jx, jy, F, u, v);
     return camera_segment_frame(P, F, u, v, s);
 }
 
@@ -402,9 +440,10 @@ UIVR_DEV int camera_segment_frame(const Params& P, const float F[15], float u, f
 }
 
 // sample_batch_pixels + sample_batch_rays (batched.py:397-467): ray of wavefront entry idx = b * spp + j
-UIVR_DEV int batch_segment(const Params& P, uint32_t b, uint32_t idx, Seg& s) {
+template <typename SeedFn>
+UIVR_DEV void batch_film_position_t(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v, SeedFn seed) {
     Rng q;
-    q.seed_sampler(P.seed_pixels, b);
+    seed(q, P.seed_pixels, b);
     const float u0 = q.f(), u1 = q.f(), u2 = q.f();
     uint32_t si = (uint32_t) ((float) P.n_sensors * u0);
     uint32_t px = (uint32_t) ((float) P.film_w * u1), py = (uint32_t) ((float) P.film_h * u2);
@@ -412,32 +451,44 @@ UIVR_DEV int batch_segment(const Params& P, uint32_t b, uint32_t idx, Seg& s) {
     px = min(px, (uint32_t) P.film_w - 1u);
     py = min(py, (uint32_t) P.film_h - 1u);
     Rng o;
-    o.seed_sampler(P.seed_offsets, idx);
+    seed(o, P.seed_offsets, idx);
     const float jx = o.f(), jy = o.f();
-    const float u = ((float) px + jx) * (1.0f / (float) P.film_w);
-    const float v = ((float) py + jy) * (1.0f / (float) P.film_h);
-    float F[15];
+    u = ((float) px + jx) * (1.0f / (float) P.film_w);
+    v = ((float) py + jy) * (1.0f / (float) P.film_h);
     const float4* f4 = reinterpret_cast<const float4*>(P.sensors + 16 * (size_t) si);
     const float4 a = __ldg(f4), bb = __ldg(f4 + 1), c = __ldg(f4 + 2), d = __ldg(f4 + 3);
     F[0] = a.x; F[1] = a.y; F[2] = a.z; F[3] = a.w; F[4] = bb.x; F[5] = bb.y; F[6] = bb.z; F[7] = bb.w;
     F[8] = c.x; F[9] = c.y; F[10] = c.z; F[11] = c.w; F[12] = d.x; F[13] = d.y; F[14] = d.z;
+}
+
+UIVR_DEV int batch_segment(const Params& P, uint32_t b, uint32_t idx, Seg& s) {
+    float F[15], u, v;
+    batch_film_position_t(P, b, idx, F, u, v, [](Rng& r, uint32_t sd, uint32_t i) { r.seed_sampler(sd, i); });
     return camera_segment_frame(P, F, u, v, s);
 }
 
 // --------------------------------------------------------------------------------------
 // free-flight walk over the majorant supergrid (Medium::sample_interaction, App. B.5)
 // --------------------------------------------------------------------------------------
+constexpr uint32_t kWalkEmpty = 0x80000000u;
+constexpr uint32_t kWalkBorder = 0x800001FFu;  // bit 8 tells the border from an empty in-grid cell (event counting)
+
 struct Walk {
     float t, tmax;
     float tnx, tny, tnz;
     int cx, cy, cz;
     float sb;
+    bool exit;      // the current cell is empty and so is everything ahead of it in the ray's octant
+    unsigned obit;  // 1 << octant
 };
 
+// majorant of cell (cx, cy, cz) + "nothing but empty space ahead" flag, from the walk table
 template <bool COUNT>
-UIVR_DEV float majorant_at(const Params& P, int cx, int cy, int cz, Counters<COUNT>& K) {
+UIVR_DEV float majorant_at(const Params& P, int cx, int cy, int cz, unsigned obit, bool& exit, Counters<COUNT>& K) {
     K.add(C_MAJ, 1);
-    return __ldg(P.maj + ((size_t) cz * P.mres[1] + cy) * P.mres[0] + cx);
+    const uint32_t e = __ldg(P.wtab + ((size_t) (cz + 1) * P.pm[1] + (cy + 1)) * P.pm[0] + (cx + 1));
+    exit = (int) e < 0 && (e & obit) != 0u;
+    return (int) e > 0 ? __uint_as_float(e) : 0.0f;
 }
 
 UIVR_DEV void walk_axis_init(float o, float d, float inv, float fm, float cs, int m, int& c, float& tn) {
@@ -454,7 +505,8 @@ UIVR_DEV void walk_init(const Params& P, const Seg& s, Walk& w, Counters<COUNT>&
     walk_axis_init(s.ox, s.dx, s.ix, P.fmres[0], P.mcs[0], P.mres[0], w.cx, w.tnx);
     walk_axis_init(s.oy, s.dy, s.iy, P.fmres[1], P.mcs[1], P.mres[1], w.cy, w.tny);
     walk_axis_init(s.oz, s.dz, s.iz, P.fmres[2], P.mcs[2], P.mres[2], w.cz, w.tnz);
-    w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, K);
+    w.obit = 1u << ((s.dx < 0.0f ? 1 : 0) | (s.dy < 0.0f ? 2 : 0) | (s.dz < 0.0f ? 4 : 0));
+    w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, w.obit, w.exit, K);
 }
 
 // advance to the next tentative collision; false when the segment end is reached
@@ -462,6 +514,7 @@ template <bool COUNT>
 UIVR_DEV bool walk_next(const Params& P, const Seg& s, Walk& w, float u, Counters<COUNT>& K) {
     float tau = neg_log1m(u);
     for (;;) {
+        if (w.exit) return false;
         int ax = 0;
         float tn = w.tnx;
         if (w.tny < tn) { ax = 1; tn = w.tny; }
@@ -494,7 +547,7 @@ UIVR_DEV bool walk_next(const Params& P, const Seg& s, Walk& w, float u, Counter
             if (w.cz < 0 || w.cz >= P.mres[2]) return false;
             w.tnz += fabsf(P.mcs[2] * s.iz);
         }
-        w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, K);
+        w.sb = majorant_at<COUNT>(P, w.cx, w.cy, w.cz, w.obit, w.exit, K);
     }
 }
 

@@ -74,6 +74,51 @@ __global__ void __launch_bounds__(kBlock) k_build_majorant(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K4c: walk table = supergrid + exit mask (uivr_device.cuh, Params::wtab).  Bit o of an empty cell's exit
+// mask says that every cell of the box between the cell and the grid corner octant o points to is empty:
+// an AND over that box, computed as three separable prefix / suffix sweeps (x, then y, then z), one thread
+// per grid line.  After the sweep along axis a, bit index gains bit a (0: suffix = direction positive,
+// 1: prefix = direction negative), so the final byte is indexed by the octant.
+// ---------------------------------------------------------------------------------------
+// sweep along the axis with stride `sa` and length `na`; `nb` bits in, 2 * nb bits out
+__global__ void __launch_bounds__(kBlock) k_exit_sweep(const float* __restrict__ maj, const uint8_t* __restrict__ in,
+                                                       uint8_t* __restrict__ out, int na, size_t sa, int n1, size_t s1,
+                                                       int n2, size_t s2, int nb) {
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n1 * n2) return;
+    const size_t base = (size_t) (line % n1) * s1 + (size_t) (line / n1) * s2;
+    const unsigned full = (1u << nb) - 1u;
+    unsigned run = full;
+    for (int i = na - 1; i >= 0; --i) {  // suffix: cells i' >= i
+        const size_t c = base + (size_t) i * sa;
+        run &= in ? (unsigned) in[c] : (maj[c] > 0.0f ? 0u : 1u);
+        out[c] = (uint8_t) run;
+    }
+    run = full;
+    for (int i = 0; i < na; ++i) {       // prefix: cells i' <= i
+        const size_t c = base + (size_t) i * sa;
+        run &= in ? (unsigned) in[c] : (maj[c] > 0.0f ? 0u : 1u);
+        out[c] = (uint8_t) (out[c] | (run << nb));
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_build_walk_table(const float* __restrict__ maj, const uint8_t* __restrict__ mask,
+                                                             uint32_t* __restrict__ wtab, int mx, int my, int mz) {
+    const int px = mx + 2, py = my + 2, pz = mz + 2;
+    const int n = px * py * pz;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int x = i % px - 1, y = (i / px) % py - 1, z = i / (px * py) - 1;
+        uint32_t w = kWalkBorder;
+        if (x >= 0 && x < mx && y >= 0 && y < my && z >= 0 && z < mz) {
+            const size_t c = ((size_t) z * my + y) * mx + x;
+            const float m = maj[c];
+            w = m > 0.0f ? __float_as_uint(m) : (kWalkEmpty | (uint32_t) mask[c]);
+        }
+        wtab[i] = w;
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_scale(float* __restrict__ x, size_t n, float s) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
         x[i] = x[i] * s;

@@ -1,25 +1,28 @@
-// uivr_pool.cuh -- persistent SLOT-POOL megakernels (sm_100a): variants 2 and 3 (default).
+// uivr_pool.cuh -- persistent SLOT-POOL megakernels (sm_100a): the default pipeline.
 //
-// Why: in the lane-refill megakernel (uivr_mega.cuh) every lane keeps its sample in registers,
-// so a warp can only batch the <= 32 samples it owns; ncu showed the transition handlers
-// (vertex / NEE end / path end / fetch) running with ~4 of 32 lanes active and 37 % of the
-// stall samples waiting for instruction fetch (profiles/r01_history.md).  Here ONE CTA per SM
-// owns a pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA,
+// ONE CTA per SM owns a pool of NSLOT in-flight samples whose path state lives in SHARED MEMORY (SoA,
 // field-major), and every state of the per-sample state machine has a CTA-wide queue of slot ids:
 //
-//      Q_FREE -> [fetch] -> Q_WALK -> [walk] -> Q_VERTEX(_ADJ) -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK ...
-//                                            -> Q_NEE_END / Q_PATH_END -> ... -> Q_FREE
+//   Q_FREE -> [fetch] -> Q_WALK -> (walk) -> Q_TAP -> [tap] -> Q_WALK ...            (null collision)
+//                                                           -> Q_VERTEX(_ADJ) -> [vertex] -> Q_SPAWN -> [spawn] -> Q_WALK
+//                                         -> Q_VERTEX / Q_NEE_END / Q_SPAWN (segment end) ... -> Q_PATH_END -> Q_FREE
 //
-// Warps are specialised.  HANDLER warps serve the transition queues: a handler warp pops a FULL
-// batch of 32 slot ids from the fullest queue, loads only the fields that handler needs from the
-// pool, and routes the slots on to their next queue -- compaction of live rays across the whole
-// CTA instead of within one warp.  WALKER warps only run the free-flight walk (the hot loop: a
-// branch-free supergrid DDA with batched sigma_t taps), whose state lives in registers; a walker
-// warp is refilled from Q_WALK whenever kWalkQuantum of its lanes have finished.  The two roles
-// run separate loops, so the walk loop is not charged for the handlers' registers or code.
+// Warps are specialised.  WALKER warps run ONLY the supergrid DDA of the free-flight walk (Medium::
+// sample_interaction and its ratio-tracking / DRT siblings): ~30 instructions per cell, no RNG, no taps, no
+// divisions.  The walk is a CONTINUATION stored in the pool (next-boundary times, their increments, cell
+// index, remaining optical depth tau, position t): a walker lane picks one up with a dozen shared-memory
+// loads, steps cells until the walk ends or tau is used up inside a cell, and hands the slot on -- on a
+// tentative collision it first saves the six words that changed.  Everything else runs in HANDLER warps,
+// which pop FULL batches of 32 slots of one queue, so that the expensive code (ray generation, the walk
+// set-up with its divisions, the sigma_t tap + accept/reject decision, vertices, emitter / phase sampling,
+// gradient scatter) always runs with all lanes: compaction of live rays across the whole CTA.
 //
-// KIND selects what is compiled in: the forward / primal kernel, the combined backward kernel
-// (variant 2), or the two halves of the split backward pipeline (variant 3, see KIND_* below).
+// Round 1 kept the tap and the walk set-up inside the walker warps, where they ran with 11-14 of 32 lanes
+// (profiles/r01_split_*_regions.txt: 65 % of the walkers' issue slots went to idle lanes); see
+// profiles/r02_history.md for the measurements that led here.
+//
+// KIND selects what is compiled in: the forward / primal kernel, or one of the two halves of the backward
+// pipeline (adjoint replay; DRT pass), see KIND_* below.
 //
 // Per-sample arithmetic, RNG draw order and handler logic are exactly those of uivr_path.cuh
 // (= volpathsimple.py), so results stay bit-identical per sample (tests/test_gpu_parity.py).
@@ -31,66 +34,59 @@
 namespace uivr {
 
 // tuning knobs (overridable at build time for sweeps: scripts/sweep_pool.sh)
-#ifndef UIVR_POOL_BLOCK_BWD
-#define UIVR_POOL_BLOCK_BWD 896
-#endif
-#ifndef UIVR_POOL_HANDLERS_BWD
-#define UIVR_POOL_HANDLERS_BWD 12
-#endif
 #ifndef UIVR_POOL_BLOCK_ADJ
-#define UIVR_POOL_BLOCK_ADJ 768
+#define UIVR_POOL_BLOCK_ADJ 1024
 #endif
 #ifndef UIVR_POOL_HANDLERS_ADJ
-#define UIVR_POOL_HANDLERS_ADJ 8
+#define UIVR_POOL_HANDLERS_ADJ 12
 #endif
 #ifndef UIVR_POOL_SLOTS_ADJ
-#define UIVR_POOL_SLOTS_ADJ 768
+#define UIVR_POOL_SLOTS_ADJ 512
 #endif
 #ifndef UIVR_POOL_BLOCK_DRT
-#define UIVR_POOL_BLOCK_DRT 768
+#define UIVR_POOL_BLOCK_DRT 1024
 #endif
 #ifndef UIVR_POOL_HANDLERS_DRT
-#define UIVR_POOL_HANDLERS_DRT 8
+#define UIVR_POOL_HANDLERS_DRT 12
 #endif
 #ifndef UIVR_POOL_SLOTS_DRT
-#define UIVR_POOL_SLOTS_DRT 768
+#define UIVR_POOL_SLOTS_DRT 512
 #endif
 #ifndef UIVR_POOL_BLOCK_FWD
 #define UIVR_POOL_BLOCK_FWD 1024
 #endif
 #ifndef UIVR_POOL_HANDLERS_FWD
-#define UIVR_POOL_HANDLERS_FWD 8
+#define UIVR_POOL_HANDLERS_FWD 12
+#endif
+#ifndef UIVR_POOL_SLOTS_FWD
+#define UIVR_POOL_SLOTS_FWD 1024
 #endif
 #ifndef UIVR_POOL_QUANTUM
 #define UIVR_POOL_QUANTUM 16
 #endif
-#ifndef UIVR_POOL_SUBSTEPS
-#define UIVR_POOL_SUBSTEPS 1
-#endif
-#ifndef UIVR_POOL_TAPBATCH
-#define UIVR_POOL_TAPBATCH 8
-#endif
-#ifndef UIVR_POOL_SLOTS_BWD
-#define UIVR_POOL_SLOTS_BWD 896
-#endif
-#ifndef UIVR_POOL_SLOTS_FWD
-#define UIVR_POOL_SLOTS_FWD 1280
-#endif
-constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // the walk loop returns once this many lanes have finished
-constexpr int kPoolTapBatch = UIVR_POOL_TAPBATCH; // tentative collisions are evaluated when this many lanes wait
-constexpr int kPoolSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
-// walker lane states
-enum : int { W_IDLE = 0, W_WALKING = 1, W_PENDING = 2 };
-// remaining-steps counters of the three axes, 10 bits each with a guard bit (bit 9): a counter
-// that steps below zero clears its guard without borrowing from its neighbour
-constexpr unsigned kGuard3 = (512u) | (512u << 10) | (512u << 20);
-constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
 #ifndef UIVR_POOL_MINBATCH
 #define UIVR_POOL_MINBATCH 12
 #endif
 #ifndef UIVR_POOL_STARVE
-#define UIVR_POOL_STARVE 16
+#define UIVR_POOL_STARVE 32
 #endif
+#ifndef UIVR_POOL_SETMAXNREG
+#define UIVR_POOL_SETMAXNREG 1
+#endif
+#ifndef UIVR_POOL_WALKER_REGS
+#define UIVR_POOL_WALKER_REGS 48
+#endif
+#ifndef UIVR_POOL_HANDLERS_LAST
+#define UIVR_POOL_HANDLERS_LAST 0   // 1: the handler warps are the LAST warps of the CTA (scheduler priority A/B)
+#endif
+#ifndef UIVR_POOL_SUBSTEPS
+#define UIVR_POOL_SUBSTEPS 1
+#endif
+constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // a walker warp hands its finished lanes on once this many have finished
+constexpr int kWalkSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
+// walker lane states
+enum : int { W_IDLE = 0, W_WALKING = 1, W_HIT = 2, W_END = 3 };
+constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
 constexpr int kPoolMinBatch = UIVR_POOL_MINBATCH;    // smallest handler batch while the walk queue runs dry
 constexpr int kPoolStarveBelow = UIVR_POOL_STARVE;   // "runs dry": fewer walk jobs than this are queued
 constexpr unsigned kPoolHandlerSleepMax = 512;   // ns; idle handler warps back off up to this
@@ -98,21 +94,21 @@ constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
 constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
 
-enum : int { Q_FREE = 0, Q_WALK, Q_VERTEX, Q_VERTEX_ADJ, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
+enum : int { Q_FREE = 0, Q_WALK, Q_TAP, Q_VERTEX, Q_VERTEX_ADJ, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
 enum : int { PM_DELTA = 0, PM_NEE, PM_NEE_ADJ, PM_DRT };
 enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
 
 // pool fields (one 32-bit word per slot each).  Shared memory spent on the pool is L1 taken from
 // the supergrid / sigma_t taps (the carve-out is shared), so fields with disjoint lifetimes alias:
-//   F_TS   sigma_t at the real collision (walk -> vertex) | transmittance T (spawn/walk -> NEE end)
+//   F_TS   sigma_t at the real collision (tap -> vertex) | transmittance T (spawn / tap -> NEE end; DRT walk)
 //          | sum of the NEE adjoint (NEE end -> replay walk)
 //   F_SEQ  PCG32 stream selector v1: inc = (v1 << 1) | 1   (the 64-bit increment is not stored)
 //   pixel = idx / spp is recomputed instead of stored
 //   DRT reservoir sums (live during the adjoint replay) | Li and albedo of the DRT vertex (after it)
-//   sampler clone of the NEE replay (adjoint replay)     | DRT distance-sampling result (after it)
+//   sampler clone of the NEE replay (adjoint replay)     | T of the replay walk | DRT distance-sampling result
 enum : int {
     F_IDX = 0, F_RNG_LO, F_RNG_HI, F_SEQ,
-    F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TMAX, F_WT,
+    F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ,
     F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_TS, F_FLAGS, F_DEPTH, F_VPX, F_VPY, F_VPZ,
     F_NUM_FWD,
     // adjoint-only state
@@ -125,7 +121,18 @@ enum : int {
     // aliases
     F_ST = F_TS, F_T = F_TS, F_ASUM = F_TS,
     F_LI0 = F_RSW0, F_LI1 = F_RSW1, F_LI2 = F_RSW2, F_AL0 = F_RSC0, F_AL1 = F_RSC1, F_AL2 = F_RSC2,
-    F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI
+    F_T2 = F_CLONE_LO, F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI
+};
+
+// The CONTINUATION of the free-flight walk is a 12-word record per slot (array of structures, 48 bytes): a
+// walker lane picks it up with three 128-bit loads (conflict-free for any 8 slots per phase: the stride of 12
+// words maps 8 consecutive quarter-warps onto distinct bank quads) and saves a tentative collision with one
+// 128-bit + one 64-bit store.
+enum : int {
+    C_TNX = 0, C_TNY, C_TNZ, C_TAU,    // next-boundary times of the three axes, remaining optical depth
+    C_ADX, C_ADY, C_ADZ, C_TMAX,       // their increments per cell, segment end t_exit
+    C_CI, C_WT, C_ENDQ, C_PAD,         // cell index | octant << 28, position t, queue at the end of the walk
+    C_WORDS
 };
 
 // F_FLAGS bits
@@ -133,8 +140,10 @@ enum : unsigned {
     FL_PASS_MASK = 3u, FL_MODE_SHIFT = 2, FL_MODE_MASK = 3u << 2,
     FL_DID_SCATTER = 1u << 4, FL_ESCAPED = 1u << 5, FL_HAS_SCATTERED = 1u << 6, FL_ACTIVE = 1u << 7,
     FL_NEE_VALID = 1u << 8, FL_RS_VALID = 1u << 9, FL_DRT_FOUND = 1u << 10, FL_SPAWN_PHASE = 1u << 11,
-    FL_RESTART = 1u << 12
+    FL_ENDQ_SHIFT = 12, FL_ENDQ_MASK = 7u << 12   // queue the slot goes to when its walk ends
 };
+// F_CI: padded linear supergrid cell index | octant << 28
+constexpr unsigned kCiMask = 0x0FFFFFFFu;
 
 struct PoolCtl {
     unsigned head[Q_NUM];
@@ -145,12 +154,36 @@ struct PoolCtl {
     int abort;       // watchdog tripped: every warp leaves
 };
 
-// kernel kinds: the forward / primal kernel, the combined backward kernel (primal replay + adjoint
-// + DRT in one launch), and the two halves of the SPLIT backward pipeline, which runs the primal
-// replay with the forward kernel (per-sample radiance to HBM), then the adjoint replay (reservoir
-// records to HBM), then the DRT pass.  Splitting trades ~1.3 GB of coalesced HBM traffic (the
-// path is at < 10 % of the HBM roofline) for three lean kernels with fewer live modes each.
-enum : int { KIND_FWD = 0, KIND_BWD = 1, KIND_ADJ = 2, KIND_DRT = 3 };
+// sampler.seed(seed, wavefront) for one lane, out of line: TEA + the PCG32 seeding sequence are ~150 instructions
+// and FETCH / ray-batch generation need them at several places (instruction-cache footprint of the handlers)
+__device__ __noinline__ void pool_seed_sampler(Rng& r, uint32_t seed, uint32_t idx) { r.seed_sampler(seed, idx); }
+
+UIVR_DEV void batch_film_position(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v) {
+    batch_film_position_t(P, b, idx, F, u, v, [](Rng& r, uint32_t sd, uint32_t i) { pool_seed_sampler(r, sd, i); });
+}
+
+// watchdog record (cold code, kept out of line): reason + queue state; every warp of the CTA leaves
+__device__ __noinline__ void pool_trip(PoolCtl* ctl, unsigned* debug, unsigned why) {
+    if (atomicExch(&ctl->abort, 1) == 0 && debug) {
+        if (atomicExch(&debug[0], why) == 0u) {
+            debug[1] = blockIdx.x;
+            debug[2] = threadIdx.x;
+            for (int q = 0; q < Q_NUM; ++q) {
+                debug[4 + 3 * q] = ctl->head[q];
+                debug[5 + 3 * q] = ctl->tail[q];
+                debug[6 + 3 * q] = (unsigned) ctl->count[q];
+            }
+            debug[4 + 3 * Q_NUM] = (unsigned) ctl->live;
+            debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
+        }
+    }
+}
+
+// kernel kinds: the forward / primal kernel and the two halves of the backward pipeline, which runs the
+// primal replay with the forward kernel (per-sample radiance to HBM), then the adjoint replay (reservoir
+// records to HBM), then the DRT pass.  Splitting trades ~1.3 GB of coalesced HBM traffic (the path is at
+// < 15 % of the HBM roofline) for three lean kernels with fewer live modes each.
+enum : int { KIND_FWD = 0, KIND_ADJ = 2, KIND_DRT = 3 };
 constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) alt seq(1) depth(1) pad(2)
 
 // ENV (envmap emitter, uivr_env.cuh): three more fields per slot hold the NEE weight
@@ -158,26 +191,28 @@ constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) a
 template <bool BWD, int NSLOT, bool ENV = false>
 constexpr size_t pool_smem_bytes() {
     return 128 + (size_t) Q_NUM * NSLOT * sizeof(unsigned) +
-           (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT * sizeof(uint32_t);
+           (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0) + C_WORDS) * NSLOT * sizeof(uint32_t);
 }
 
-// BLOCK threads per CTA (one CTA per SM), of which the first HANDLERS warps serve the transition
-// queues and the rest walk
+// BLOCK threads per CTA (one CTA per SM), of which HANDLERS warps serve the transition queues and the
+// rest walk
 template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS, bool ENV = false>
 __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
-    constexpr bool BWD = KIND != KIND_FWD;                            // any gradient work
-    constexpr int F_NW0 = BWD ? F_NUM_BWD : F_NUM_FWD;                // ENV only: NEE weight (3 words)
-    constexpr bool HAS_PRIMAL = KIND == KIND_FWD || KIND == KIND_BWD; // sample(Primal) from the camera
-    constexpr bool HAS_ADJ = KIND == KIND_BWD || KIND == KIND_ADJ;    // adjoint replay (reservoir, NEE adjoint)
-    constexpr bool HAS_DRT = KIND == KIND_BWD || KIND == KIND_DRT;    // DRT walk, DRT vertex, recursive path
+    constexpr bool BWD = KIND != KIND_FWD;               // any gradient work
+    constexpr int F_NW0 = BWD ? F_NUM_BWD : F_NUM_FWD;   // ENV only: NEE weight (3 words)
+    constexpr bool HAS_ADJ = KIND == KIND_ADJ;           // adjoint replay (reservoir, NEE adjoint)
+    constexpr bool HAS_DRT = KIND == KIND_DRT;           // DRT walk, DRT vertex, recursive path
     constexpr int kPoolBlock = BLOCK;
     constexpr int kPoolHandlerWarps = HANDLERS;
     static_assert(NSLOT > (Q_NUM - 1) * 31 && NSLOT % 32 == 0, "pool too small for the full-batch scheduling rule");
     static_assert(sizeof(PoolCtl) <= 128, "PoolCtl must fit its 128-byte header");
+    static_assert(Q_NUM <= 8, "the handler scheduler packs the queue id into 3 bits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PoolCtl* const ctl = reinterpret_cast<PoolCtl*>(smem_raw);
     unsigned* const ring = reinterpret_cast<unsigned*>(smem_raw + 128);  // one mailbox cell per ring position
     uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * NSLOT * sizeof(unsigned));
+    uint32_t* const cont = pool + (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT;  // [slot][C_WORDS]
+    static_assert(NSLOT % 4 == 0, "the continuation records must stay 16-byte aligned");
 
     Counters<COUNT> K;
     const unsigned lane = threadIdx.x & 31u;
@@ -189,6 +224,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 #define PU(f, s) pool[(f) * NSLOT + (s)]
 #define PF(f, s) __uint_as_float(pool[(f) * NSLOT + (s)])
 #define PSET(f, s, v) pool[(f) * NSLOT + (s)] = __float_as_uint(v)
+#define CU(k, s) cont[(s) * C_WORDS + (k)]
+#define CF(k, s) __uint_as_float(cont[(s) * C_WORDS + (k)])
+#define CSET(k, s, v) cont[(s) * C_WORDS + (k)] = __float_as_uint(v)
 
     // ---- pool / queue initialisation: every slot starts in Q_FREE ----
     for (int i = threadIdx.x; i < Q_NUM * NSLOT; i += kPoolBlock)
@@ -202,23 +240,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; }
     __syncthreads();
 
-    // ---- queue primitives (warp-collective; each is instantiated ONCE to keep the code small) ----
+    // ---- queue primitives (warp-collective; each is instantiated ONCE per role to keep the code small) ----
     // watchdog: a tripped limit records the reason + queue state and makes every warp leave
-    auto trip = [&](unsigned why) {
-        if (atomicExch(&ctl->abort, 1) == 0 && P.debug) {
-            if (atomicExch(&P.debug[0], why) == 0u) {
-                P.debug[1] = blockIdx.x;
-                P.debug[2] = threadIdx.x;
-                for (int q = 0; q < Q_NUM; ++q) {
-                    P.debug[4 + 3 * q] = ctl->head[q];
-                    P.debug[5 + 3 * q] = ctl->tail[q];
-                    P.debug[6 + 3 * q] = (unsigned) ctl->count[q];
-                }
-                P.debug[4 + 3 * Q_NUM] = (unsigned) ctl->live;
-                P.debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
-            }
-        }
-    };
+    auto trip = [&](unsigned why) { pool_trip(ctl, P.debug, why); };
     // pops up to `want` ids from queue q (all-or-nothing when `exact`); lane i < got receives one
     auto q_pop = [&](int q, int want, bool exact, unsigned& slot) -> int {
         int got = 0;
@@ -232,7 +256,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         got = __shfl_sync(FULL, got, 0);
         base = __shfl_sync(FULL, base, 0);
         if ((int) lane < got) {
-            unsigned* cell = &ring[q * NSLOT + (base + lane) % (unsigned) NSLOT];
+            unsigned pos = base % (unsigned) NSLOT + lane;  // (head runs free; the ring has NSLOT cells)
+            pos -= pos >= (unsigned) NSLOT ? (unsigned) NSLOT : 0u;
+            unsigned* cell = &ring[q * NSLOT + pos];
             unsigned v;
             int spins = 0;
             // the position is reserved by a producer; its store may still be in flight
@@ -244,23 +270,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         __threadfence_block();
         return got;
     };
-
-    // ---- walker state (registers; one walk job per lane) ----
-    int wslot = -1;            // pool slot this lane walks for, -1 = idle
-    int wstate = W_IDLE;       // W_WALKING: stepping cells; W_PENDING: a tentative collision at `wt` waits for its tap
-    unsigned wflags = 0;
-    int mode = PM_DELTA;
-    Rng rng;
-    rng.state = rng.inc = 0;
-    float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f, tmax = 0.0f;
-    float wt = 0.0f, tnx = 0.0f, tny = 0.0f, tnz = 0.0f, sb = 0.0f, tau = 0.0f;
-    float adx = 0.0f, ady = 0.0f, adz = 0.0f;
-    int ci = 0;                // linear supergrid cell index
-    int sxl = 0, syl = 0, szl = 0;  // its signed strides along the ray
-    unsigned nrem = 0;         // packed remaining-steps counters (kGuard3)
-    float T = 1.0f, asum = 0.0f, sigma_t = 0.0f;
-    float drt_D = 0.0f, drt_t = 0.0f, drt_st = 0.0f;
-    bool drt_found = false, did_scatter = false;
 
     // route: hand every finished slot to its next queue (lane-wise: slot `s` -> queue `next`, -1: none)
     auto route = [&](unsigned s, int next) {
@@ -274,7 +283,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             if ((int) lane == leader) base = atomicAdd(&ctl->tail[q], (unsigned) __popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (next == q) {
-                unsigned* cell = &ring[q * NSLOT + (base + __popc(m & lt_mask)) % (unsigned) NSLOT];
+                unsigned pos = base % (unsigned) NSLOT + __popc(m & lt_mask);
+                pos -= pos >= (unsigned) NSLOT ? (unsigned) NSLOT : 0u;
+                unsigned* cell = &ring[q * NSLOT + pos];
                 int spins = 0;
                 // the cell is free unless the consumer of the previous lap has not taken its id yet
                 while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
@@ -287,25 +298,43 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         }
     };
 
-    // Warp roles.  The first kPoolHandlerWarps warps serve the transition queues, all others are
-    // walkers.  The two loops share no registers, so the walker loop (the hot code: a few KB of
-    // SASS that stays in the instruction caches) is not charged for the handlers' working set.
-    const bool is_handler = (threadIdx.x >> 5) < kPoolHandlerWarps;
+    // Warp roles.  The two loops share no registers, so the walker loop (the hot code: ~100 instructions
+    // that stay in the L0 instruction cache) is not charged for the handlers' working set.
+    const int warp_id = threadIdx.x >> 5;
+    const bool is_handler = UIVR_POOL_HANDLERS_LAST ? warp_id >= kPoolBlock / 32 - kPoolHandlerWarps
+                                                    : warp_id < kPoolHandlerWarps;
     long long t_progress = clock64();
 
+    // Register re-allocation between the roles (sm_90a+ `setmaxnreg`, per warpgroup of 4 warps): a walker
+    // lane needs ~30 registers, a handler lane wants ~100; launched with 64 per thread (1024 threads), the
+    // walkers give registers up and the handlers take them.  HANDLERS must be a multiple of 4.
+#if UIVR_POOL_SETMAXNREG
+    static_assert(HANDLERS % 4 == 0 && BLOCK == 1024, "setmaxnreg works on aligned warpgroups");
+    constexpr int kRegWalker = UIVR_POOL_WALKER_REGS;
+    constexpr int kRegHandler = ((2048 - (32 - HANDLERS) * kRegWalker) / HANDLERS) / 8 * 8;
+#endif
     if (!is_handler) {
+#if UIVR_POOL_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegWalker));
+#endif
         // ==================================================================================
-        // WALKER WARPS
+        // WALKER WARPS: supergrid DDA of the free-flight walk (Medium::sample_interaction, App. B.5)
         // ==================================================================================
+        int wslot = -1;            // pool slot this lane walks for, -1 = idle
+        int wst = W_IDLE;
+        int wendq = 0;             // queue of the slot when the walk ends without a collision
+        float tnx = 0.0f, tny = 0.0f, tnz = 0.0f, adx = 0.0f, ady = 0.0f, adz = 0.0f;
+        float tau = 0.0f, wt = 0.0f, tmax = 0.0f;
+        int ci = 0, sxl = 0, syl = 0, szl = 0;
+        unsigned e = 0u, obit = 0u, oct = 0u;
+        unsigned widle_ns = 64;
         for (;;) {
             if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
-            const int cnt = (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0;
-            // ==============================================================================
-            // 1. refill idle walker lanes from Q_WALK
-            // ==============================================================================
-            {
-                const unsigned idle = __ballot_sync(FULL, wslot < 0);
-                if (idle && __shfl_sync(FULL, cnt, 0) > 0) {
+            // ---- 1. idle lanes pick up walk continuations from Q_WALK ----
+            const unsigned idle = __ballot_sync(FULL, wslot < 0);
+            if (idle) {
+                const int cnt = __shfl_sync(FULL, (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0, 0);
+                if (cnt > 0) {
                     unsigned got_slot = 0;
                     const int got = q_pop(Q_WALK, __popc(idle), false, got_slot);
                     if (got) {
@@ -313,189 +342,116 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         const unsigned s = __shfl_sync(FULL, got_slot, rank & 31);
                         if (wslot < 0 && rank < got) {
                             wslot = (int) s;
-                            wflags = PU(F_FLAGS, s);
-                            mode = (int) ((wflags & FL_MODE_MASK) >> FL_MODE_SHIFT);
-                            rng.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
-                            rng.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
-                            ox = PF(F_OX, s); oy = PF(F_OY, s); oz = PF(F_OZ, s);
-                            dx = PF(F_DX, s); dy = PF(F_DY, s); dz = PF(F_DZ, s);
-                            tmax = PF(F_TMAX, s);
-                            T = 1.0f;
-                            drt_D = 0.0f;
-                            drt_found = false;
-                            did_scatter = false;
-                            if (HAS_ADJ) asum = PF(F_ASUM, s);
-                            // walk_init (Medium::sample_interaction set-up, App. B.5)
-                            const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
-                            const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
-                            const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
-                            wt = 0.0f;
-                            int cx, cy, cz;
-                            walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
-                            walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
-                            walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
-                            adx = fabsf(P.mcs[0] * ix);
-                            ady = fabsf(P.mcs[1] * iy);
-                            adz = fabsf(P.mcs[2] * iz);
-                            // cell coordinates -> linear index + steps left before the walk leaves the grid
-                            const int mx = P.mres[0], mxy = P.mres[0] * P.mres[1];
-                            ci = cz * mxy + cy * mx + cx;
-                            sxl = dx > 0.0f ? 1 : -1;
-                            syl = dy > 0.0f ? mx : -mx;
-                            szl = dz > 0.0f ? mxy : -mxy;
-                            nrem = kGuard3 | (unsigned) (dx > 0.0f ? P.mres[0] - 1 - cx : cx) |
-                                   ((unsigned) (dy > 0.0f ? P.mres[1] - 1 - cy : cy) << 10) |
-                                   ((unsigned) (dz > 0.0f ? P.mres[2] - 1 - cz : cz) << 20);
-                            K.add(C_MAJ, 1);
-                            sb = __ldg(P.maj + ci);
-                            tau = neg_log1m(draw(rng, K));
-                            wstate = W_WALKING;
+                            const uint4* rec = reinterpret_cast<const uint4*>(cont + s * C_WORDS);
+                            const uint4 ra = rec[0], rb = rec[1], rc = rec[2];
+                            tnx = __uint_as_float(ra.x); tny = __uint_as_float(ra.y); tnz = __uint_as_float(ra.z);
+                            tau = __uint_as_float(ra.w);
+                            adx = __uint_as_float(rb.x); ady = __uint_as_float(rb.y); adz = __uint_as_float(rb.z);
+                            tmax = __uint_as_float(rb.w);
+                            ci = (int) (rc.x & kCiMask);
+                            oct = rc.x >> 28;
+                            wt = __uint_as_float(rc.y);
+                            wendq = (int) rc.z;
+                            e = __ldg(P.wtab + ci);
+                            obit = 1u << oct;
+                            const int px = P.pm[0], pxy = P.pm[0] * P.pm[1];
+                            sxl = (oct & 1u) ? -1 : 1;
+                            syl = (oct & 2u) ? -px : px;
+                            szl = (oct & 4u) ? -pxy : pxy;
+                            wst = W_WALKING;
                         }
                     }
                 }
             }
-
-            const unsigned m_walk = __ballot_sync(FULL, wstate != W_IDLE);
+            const unsigned m_walk = __ballot_sync(FULL, wst == W_WALKING);
             if (!m_walk) {
                 if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
                 if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
-                __nanosleep(64);
+                __nanosleep(widle_ns);
+                widle_ns = widle_ns < kPoolHandlerSleepMax ? widle_ns * 2 : widle_ns;  // back off: polling costs issue slots
                 continue;
             }
+            widle_ns = 64;
             t_progress = clock64();
-            unsigned s = 0;
-            int next = -1;
-            // ==========================================================================
-            // 3. walk quantum: free-flight walk over the majorant supergrid (Medium::
-            //    sample_interaction and its ratio-tracking / DRT siblings) until kWalkQuantum
-            //    lanes have finished
-            // ==========================================================================
+            // ---- 2. step cells until kWalkQuantum lanes have finished (or a short-handed warp can refill) ----
             const int n0 = __popc(m_walk);
             const int n_stop = n0 > kWalkQuantum ? n0 - kWalkQuantum : 0;
-            for (int guard = 0;; ++guard) {
-                if (guard > kPoolWalkLimit) { trip(0x400u); wstate = W_IDLE; break; }
-                // ---- kPoolSubSteps supergrid cells per iteration (branch-free DDA) ----
+            const bool short_handed = n0 <= 32 - kWalkQuantum;
+            for (int it = 1;; ++it) {
 #pragma unroll
-                for (int sub = 0; sub < kPoolSubSteps; ++sub) {
-                    if (wstate == W_WALKING) {
+                for (int sub = 0; sub < kWalkSubSteps; ++sub) {
+                    if (wst == W_WALKING) {
+                        // empty cell with only empty cells ahead (or the border): no further collision
+                        const bool gone = (int) e < 0 && (e & obit) != 0u;
                         const bool yx = tny < tnx;
                         float tn = yx ? tny : tnx;
                         const bool zb = tnz < tn;
                         tn = zb ? tnz : tn;
-                        const float t_end = tn < tmax ? tn : tmax;
-                        float len = t_end - wt;
-                        len = len < 0.0f ? 0.0f : len;
-                        const float dtau = sb * len;
-                        if (sb > 0.0f && tau < dtau) {
-                            float t = wt + tau / sb;
-                            wt = t > t_end ? t_end : t;
-                            wstate = W_PENDING;
+                        const bool more = tn < tmax;
+                        const float t_end = more ? tn : tmax;
+                        const float len = fmaxf(t_end - wt, 0.0f);
+                        const bool dense = (int) e > 0;
+                        const float dtau = __uint_as_float(e) * len;
+                        // tau is used up inside this cell: the tap handler takes over
+                        const bool hit = dense && tau < dtau;
+                        if (gone || hit) {
+                            wst = gone ? W_END : W_HIT;
                         } else {
-                            if (sb > 0.0f) tau -= dtau;
-                            wt = t_end > wt ? t_end : wt;
-                            const bool a0 = !zb && !yx, a1 = !zb && yx;
-                            ci += a0 ? sxl : (a1 ? syl : szl);
-                            nrem -= a0 ? 1u : (a1 ? (1u << 10) : (1u << 20));
-                            tnx = a0 ? tnx + adx : tnx;
-                            tny = a1 ? tny + ady : tny;
+                            tau = dense ? tau - dtau : tau;
+                            wt = fmaxf(wt, t_end);
+                            // the step is harmless when t_exit has been reached (!more): the lane ends anyway
+                            ci += zb ? szl : (yx ? syl : sxl);
+                            tnx = (!zb && !yx) ? tnx + adx : tnx;
+                            tny = (!zb && yx) ? tny + ady : tny;
                             tnz = zb ? tnz + adz : tnz;
-                            // segment end (no further collision): t_exit reached, or the walk left the grid
-                            if (!(tn < tmax) || (nrem & kGuard3) != kGuard3) {
-                                wstate = W_IDLE;
+                            if (more) {
+                                e = __ldg(P.wtab + ci);
+                                if (COUNT && (e & 0x80000100u) != 0x80000100u) K.add(C_MAJ, 1);
                             } else {
-                                K.add(C_MAJ, 1);
-                                sb = __ldg(P.maj + ci);
+                                wst = W_END;
                             }
                         }
                     }
                 }
-                const int n_walk = __popc(__ballot_sync(FULL, wstate != W_IDLE));
-                const int n_pend = __popc(__ballot_sync(FULL, wstate == W_PENDING));
-                const bool leave = n_walk <= n_stop;
-                // ---- tentative collisions: sigma_t tap + per-mode decision ----
-                if (n_pend >= kPoolTapBatch || (n_pend > 0 && (n_pend == n_walk || leave))) {
-                    if (wstate == W_PENDING) {
-                        wstate = W_WALKING;
-                        const float px = fmaf(wt, dx, ox), py = fmaf(wt, dy, oy), pz = fmaf(wt, dz, oz);
-                        // one extra draw for delta tracking (accept test, :359) and for DRT (reservoir, drawn
-                        // before the lookup); the lookup itself draws nothing, so the order is immaterial
-                        float u = 0.0f;
-                        if (mode == PM_DELTA || mode == PM_DRT) u = draw(rng, K);
-                        const float st = sigma_tap(P, px, py, pz);
-                        K.add(C_SIGMA, 1);
-                        // sigma_t / sigma_bar (delta tracking) or sigma_n / sigma_bar (ratio tracking, DRT): one
-                        // division site for all modes
-                        const float sn = sb - st;
-                        const float q = (mode == PM_DELTA ? st : sn) / sb;
-                        bool cont = true;
-                        if (mode == PM_DELTA) {
-                            // :354-361 real vs null collision
-                            if (!(u >= q)) {
-                                did_scatter = true;
-                                sigma_t = st;
-                                cont = false;
-                            }
-                        } else {
-                            if (HAS_DRT && mode == PM_DRT) {
-                                // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
-                                const float wi = T / sb;
-                                drt_D += wi;
-                                if (u <= wi / drt_D) {
-                                    drt_t = wt;
-                                    drt_st = st;
-                                    drt_found = true;
-                                }
-                            } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
-                                // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)
-                                scatter_sigma(P, px, py, pz, -asum / sn);
-                                K.add(C_SSCAT, 1);
-                            }
-                            // ratio tracking (:461-502) / running transmittance of the DRT walk
-                            T *= q;
-                            if (mode == PM_DRT ? !(T > 0.0f) : T == 0.0f) cont = false;
-                        }
-                        if (cont) tau = neg_log1m(draw(rng, K));
-                        else wstate = W_IDLE;
-                    }
-                    if (leave || __ballot_sync(FULL, wstate != W_IDLE) == 0u) break;
-                } else if (leave) {
-                    break;
+                const int n_walk = __popc(__ballot_sync(FULL, wst == W_WALKING));
+                if (n_walk <= n_stop) break;
+                if ((it & 7) == 0) {
+                    if (it > kPoolWalkLimit) { trip(0x400u); wst = W_END; break; }
+                    // a warp that started short of lanes leaves as soon as the queue can fill them
+                    if (short_handed &&
+                        __shfl_sync(FULL, (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0, 0) >= kWalkQuantum)
+                        break;
                 }
             }
-            // ---- write back finished walks; the slot goes on to its next queue ----
-            if (wslot >= 0 && wstate == W_IDLE) {
+            // ---- 3. hand finished lanes on: a tentative collision saves the words that changed ----
+            unsigned s = 0;
+            int next = -1;
+            if (wslot >= 0 && wst != W_WALKING) {
                 s = (unsigned) wslot;
-                PU(F_RNG_LO, s) = (uint32_t) rng.state;
-                PU(F_RNG_HI, s) = (uint32_t) (rng.state >> 32);
-                PSET(F_WT, s, wt);
-                if (mode == PM_DELTA) {
-                    PSET(F_ST, s, sigma_t);
-                    PU(F_FLAGS, s) = did_scatter ? (wflags | FL_DID_SCATTER) : (wflags & ~FL_DID_SCATTER);
-                    // vertices of the adjoint replay scatter gradients: they get their own queue so that
-                    // the scatter loop of a batch runs with all lanes
-                    next = (HAS_ADJ && (wflags & FL_PASS_MASK) == (unsigned) PP_ADJ) ? Q_VERTEX_ADJ : Q_VERTEX;
-                } else if (mode == PM_NEE) {
-                    PSET(F_T, s, T);
-                    next = Q_NEE_END;
-                } else if (HAS_ADJ && mode == PM_NEE_ADJ) {
-                    PU(F_FLAGS, s) = wflags | FL_SPAWN_PHASE;
-                    next = Q_SPAWN;
-                } else if (HAS_DRT && mode == PM_DRT) {
-                    PSET(F_DRT_D, s, drt_D); PSET(F_DRT_T, s, drt_t); PSET(F_DRT_ST, s, drt_st);
-                    PU(F_FLAGS, s) = drt_found ? (wflags | FL_DRT_FOUND) : (wflags & ~FL_DRT_FOUND);
-                    next = Q_VERTEX;  // the vertex handler serves the DRT vertex as well
+                if (wst == W_HIT) {
+                    uint32_t* rec = cont + s * C_WORDS;
+                    *reinterpret_cast<uint4*>(rec) = make_uint4(__float_as_uint(tnx), __float_as_uint(tny), __float_as_uint(tnz),
+                                                                __float_as_uint(tau));
+                    *reinterpret_cast<uint2*>(rec + C_CI) = make_uint2((unsigned) ci | (oct << 28), __float_as_uint(wt));
+                    next = Q_TAP;
+                } else {
+                    next = wendq;
                 }
                 wslot = -1;
+                wst = W_IDLE;
             }
             route(s, next);
         }
     } else {
         // ==================================================================================
         // HANDLER WARPS: a FULL batch of a transition queue if there is one; partial batches only
-        // once the global sample queue is exhausted.  Before exhaustion no slot retires, so
-        // "no full queue and nothing to walk anywhere" cannot happen: NSLOT > (Q_NUM - 1) * 31
+        // once the global sample queue is exhausted or while the walkers run dry.  Before exhaustion no
+        // slot retires, so "no full queue and nothing to walk anywhere" cannot happen: NSLOT > (Q_NUM - 1) * 31
         // slots cannot all sit in non-full queues.
         // ==================================================================================
+#if UIVR_POOL_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegHandler));
+#endif
         int last_work = Q_FREE;
         unsigned idle_ns = 32;
         for (;;) {
@@ -547,11 +503,82 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             Rng alt;
             alt.state = alt.inc = 0;
             // ==========================================================================
-            // 4. transition handlers (one batch of up to 32 slots of queue `work`)
+            // transition handlers (one batch of up to 32 slots of queue `work`)
             // ==========================================================================
             const int got = q_pop(work, 32, exact, s);
             const bool act = (int) lane < got;
-            if (work == Q_VERTEX || work == Q_VERTEX_ADJ) {
+            if (work == Q_TAP) {
+                // ---- tentative collision: its position inside the cell, the sigma_t tap and the per-mode
+                //      decision (:347-367 delta tracking, :465-502 ratio tracking, App. B.6 DRT) ----
+                if (act) {
+                    unsigned fl = PU(F_FLAGS, s);
+                    const int mode = (int) ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT);
+                    const float sb = __uint_as_float(__ldg(P.wtab + (CU(C_CI, s) & kCiMask)));
+                    // end of the cell along the ray, as the walker saw it
+                    const float tnx = CF(C_TNX, s), tny = CF(C_TNY, s), tnz = CF(C_TNZ, s), tmax = CF(C_TMAX, s);
+                    float tn = tny < tnx ? tny : tnx;
+                    tn = tnz < tn ? tnz : tn;
+                    const float t_end = tn < tmax ? tn : tmax;
+                    const float t = CF(C_WT, s) + CF(C_TAU, s) / sb;
+                    const float wt = t > t_end ? t_end : t;
+                    CSET(C_WT, s, wt);
+                    const float px = fmaf(wt, PF(F_DX, s), PF(F_OX, s)), py = fmaf(wt, PF(F_DY, s), PF(F_OY, s)),
+                                pz = fmaf(wt, PF(F_DZ, s), PF(F_OZ, s));
+                    Rng r;
+                    r.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
+                    r.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
+                    // one extra draw for delta tracking (accept test, :359) and for DRT (reservoir, drawn
+                    // before the lookup); the lookup itself draws nothing, so the order is immaterial
+                    float u = 0.0f;
+                    if (mode == PM_DELTA || (HAS_DRT && mode == PM_DRT)) u = draw(r, K);
+                    const float st = sigma_tap(P, px, py, pz);
+                    K.add(C_SIGMA, 1);
+                    // sigma_t / sigma_bar (delta tracking) or sigma_n / sigma_bar (ratio tracking, DRT): one
+                    // division site for all modes
+                    const float sn = sb - st;
+                    const float q = (mode == PM_DELTA ? st : sn) / sb;
+                    bool go_on = true;
+                    if (mode == PM_DELTA) {
+                        // :354-361 real vs null collision
+                        if (!(u >= q)) {
+                            PSET(F_ST, s, st);
+                            fl |= FL_DID_SCATTER;
+                            go_on = false;
+                        }
+                    } else {
+                        const int ft = (HAS_ADJ && mode == PM_NEE_ADJ) ? F_T2 : F_T;
+                        float T = PF(ft, s);
+                        if (HAS_DRT && mode == PM_DRT) {
+                            // sample_interaction_drt (App. B.6): candidate weight T/sigma_bar, size-1 reservoir
+                            const float wi = T / sb;
+                            const float D = PF(F_DRT_D, s) + wi;
+                            PSET(F_DRT_D, s, D);
+                            if (u <= wi / D) {
+                                PSET(F_DRT_T, s, wt);
+                                PSET(F_DRT_ST, s, st);
+                                fl |= FL_DRT_FOUND;
+                            }
+                        } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
+                            // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)
+                            scatter_sigma(P, px, py, pz, -PF(F_ASUM, s) / sn);
+                            K.add(C_SSCAT, 1);
+                        }
+                        // ratio tracking (:461-502) / running transmittance of the DRT walk
+                        T *= q;
+                        PSET(ft, s, T);
+                        if ((HAS_DRT && mode == PM_DRT) ? !(T > 0.0f) : T == 0.0f) go_on = false;
+                    }
+                    if (go_on) {
+                        CSET(C_TAU, s, neg_log1m(draw(r, K)));
+                        next = Q_WALK;  // the walker resumes in the same cell
+                    } else {
+                        next = (int) ((fl & FL_ENDQ_MASK) >> FL_ENDQ_SHIFT);
+                    }
+                    PU(F_RNG_LO, s) = (uint32_t) r.state;
+                    PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                    PU(F_FLAGS, s) = fl;
+                }
+            } else if (work == Q_VERTEX || work == Q_VERTEX_ADJ) {
                 // ---- end of a delta-tracking segment (:130-245) or of the DRT walk (:550-558) ----
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
@@ -564,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const int fo = is_drt ? F_RSOX : F_OX, fd = is_drt ? F_RSDX : F_DX;
                     const float sox = PF(fo, s), soy = PF(fo + 1, s), soz = PF(fo + 2, s);
                     const float sdx = PF(fd, s), sdy = PF(fd + 1, s), sdz = PF(fd + 2, s);
-                    const float swt = PF(is_drt ? F_DRT_T : F_WT, s);
+                    const float swt = is_drt ? PF(F_DRT_T, s) : CF(C_WT, s);
                     const float vx = fmaf(swt, sdx, sox), vy = fmaf(swt, sdy, soy), vz = fmaf(swt, sdz, soz);
                     float albedo[3] = {1.0f, 1.0f, 1.0f};
                     if (ds) {
@@ -581,11 +608,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             fl = P.use_nee ? (fl & ~FL_SPAWN_PHASE) : (fl | FL_SPAWN_PHASE);
                             next = Q_SPAWN;
                         } else {
-                            fl &= ~FL_RESTART;
                             next = Q_FREE;
                         }
                     } else {
-                        const float stmax = PF(F_TMAX, s);
+                        const float stmax = CF(C_TMAX, s);
                         const float beta[3] = {PF(F_B0, s), PF(F_B1, s), PF(F_B2, s)};
                         if (ds) {
                             fl |= FL_HAS_SCATTERED;
@@ -729,7 +755,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                     }
                     next = Q_FREE;
-                    fl &= ~FL_RESTART;
                     if (pass == PP_PRIMAL) {
                         const uint32_t idx = PU(F_IDX, s), pix = idx / P.spp;
                         if (P.sample_L) {
@@ -737,16 +762,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             P.sample_L[3 * (size_t) idx + 1] = R[1];
                             P.sample_L[3 * (size_t) idx + 2] = R[2];
                         }
-                        if (KIND == KIND_FWD) {
-                            if (P.image) {  // (null when this launch is the primal replay of the split backward)
-                                atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
-                                atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
-                                atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
-                            }
-                        } else {
-                            // batched.py:309-318: sample(Backward, state_in = L)
-                            PSET(F_R0, s, R[0]); PSET(F_R1, s, R[1]); PSET(F_R2, s, R[2]);
-                            fl = (fl & ~FL_PASS_MASK) | (unsigned) PP_ADJ | FL_RESTART;
+                        if (P.image) {  // (null when this launch is the primal replay of the backward)
+                            atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                            atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                            atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
                         }
                     } else if (HAS_ADJ && pass == PP_ADJ) {
                         if (use_rsv && (fl & FL_RS_VALID)) {
@@ -759,18 +778,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 const float W = (d != 0.0f) ? (ws * wcur[c]) / d : 0.0f;
                                 PSET(F_DL0 + c, s, W * PF(F_DL0 + c, s));
                             }
-                            if (KIND == KIND_ADJ) {
-                                want_rec = true;  // the DRT pass is a separate launch: hand the sample over through HBM
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 7; ++k) PU(F_OX + k, s) = PU(F_RSOX + k, s);  // o, d, tmax
-                                PU(F_DEPTH, s) = (dw & 0xFFFF0000u) | (dw >> 16);
-                                // everything from here on draws from the alt stream
-                                PU(F_RNG_LO, s) = PU(F_ALT_LO, s); PU(F_RNG_HI, s) = PU(F_ALT_HI, s);
-                                PU(F_SEQ, s) = PU(F_ASEQ, s);
-                                fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_DRT << FL_MODE_SHIFT);
-                                next = Q_WALK;
-                            }
+                            want_rec = true;  // the DRT pass is a separate launch: hand the sample over through HBM
                         }
                     } else if (HAS_DRT) {  // PP_REC: Li complete -> DRT gradient (:571-581)
                         const float dst = PF(F_DRT_ST, s), dD = PF(F_DRT_D, s), dt = PF(F_DRT_T, s);
@@ -835,7 +843,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const bool ok = make_segment(P, PF(F_VPX, s), PF(F_VPY, s), PF(F_VPZ, s), wx, wy, wz, sg) && worked;
                     PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
                     PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
-                    PSET(F_TMAX, s, sg.tmax);
+                    CSET(C_TMAX, s, sg.tmax);
                     bool active = (fl & FL_ACTIVE) != 0u;
                     bool rr = false;  // Russian-roulette draw + zero-throughput test of the next loop iteration
                     if (!phase) {
@@ -878,162 +886,136 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_FLAGS, s) = fl;
                 }
             } else {
-                // ---- Q_FREE: next sample from the global queue / adjoint re-start: ray generation +
-                //      reach_medium (batched.py:426-467, volpathsimple.py:292-319) ----
-                if (KIND == KIND_DRT) {
-                    // split pipeline, DRT launch: the work items are the reservoir records of the adjoint launch
-                    bool none_left = true;
-                    const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
-                    const unsigned fresh = __ballot_sync(FULL, act);
-                    if (exh == 0 && fresh) {
-                        const int leader = __ffs(fresh) - 1;
-                        unsigned base = 0;
-                        if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
-                        base = __shfl_sync(FULL, base, leader);
-                        const uint64_t item = (uint64_t) base + __popc(fresh & lt_mask);
-                        if (act && item < total) {
-                            none_left = false;
-                            const uint4* r4 = reinterpret_cast<const uint4*>(P.records + (size_t) item * kRecWords);
-                            const uint4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
-                            // DRT on the stored segment (:543-581): the walk draws from the alt stream
-                            PU(F_OX, s) = a.x; PU(F_OY, s) = a.y; PU(F_OZ, s) = a.z; PU(F_DX, s) = a.w;
-                            PU(F_DY, s) = b.x; PU(F_DZ, s) = b.y; PU(F_TMAX, s) = b.z;
-                            PU(F_RSOX, s) = a.x; PU(F_RSOY, s) = a.y; PU(F_RSOZ, s) = a.z; PU(F_RSDX, s) = a.w;
-                            PU(F_RSDY, s) = b.x; PU(F_RSDZ, s) = b.y;
-                            PU(F_DL0, s) = b.w; PU(F_DL1, s) = c.x; PU(F_DL2, s) = c.y;
-                            PU(F_RNG_LO, s) = c.z; PU(F_RNG_HI, s) = c.w; PU(F_SEQ, s) = d.x;
-                            PU(F_DEPTH, s) = d.y;
-                            PU(F_FLAGS, s) = (unsigned) PP_ADJ | ((unsigned) PM_DRT << FL_MODE_SHIFT);
-                            next = Q_WALK;
-                        }
-                        if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
-                    }
-                    const unsigned retire = __ballot_sync(FULL, act && none_left);
-                    if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
-                } else {
-                unsigned fl = act ? PU(F_FLAGS, s) : 0u;
-                const bool restart = act && (fl & FL_RESTART);
-                bool have = restart;
-                uint32_t idx = 0, pix = 0;
-                if (restart) { idx = PU(F_IDX, s); pix = idx / P.spp; }
-                const unsigned fresh = __ballot_sync(FULL, act && !restart);
-                if (fresh) {
-                    bool none_left = true;
-                    const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
-                    if (exh == 0) {
-                        const int leader = __ffs(fresh) - 1;
-                        unsigned base = 0;
-                        if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
-                        base = __shfl_sync(FULL, base, leader);
-                        if (act && !restart) {
-                            const uint64_t item = (uint64_t) base + __popc(fresh & lt_mask);
-                            if (item < total) {
-                                none_left = false;
-                                const uint32_t it = (uint32_t) item;
-                                if (slot_to_pixel(P, it / P.spp, pix)) {
-                                    idx = pix * P.spp + it % P.spp;
-                                    have = true;
-                                    fl = (unsigned) (KIND == KIND_ADJ ? PP_ADJ : PP_PRIMAL);
-                                    if (HAS_PRIMAL) K.add(C_SAMPLES, 1);
-                                } else {
-                                    next = Q_FREE;  // padding slot of a shard: try again
-                                }
-                            }
-                        }
-                        if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
-                    }
-                    // no more samples: the slot retires
-                    const unsigned retire = __ballot_sync(FULL, act && !restart && none_left);
-                    if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
+                // ---- Q_FREE: next work item from the global queue ----
+                bool none_left = true;
+                const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
+                const unsigned fresh = __ballot_sync(FULL, act);
+                uint64_t item = 0;
+                bool mine = false;
+                if (exh == 0 && fresh) {
+                    const int leader = __ffs(fresh) - 1;
+                    unsigned base = 0;
+                    if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
+                    base = __shfl_sync(FULL, base, leader);
+                    item = (uint64_t) base + __popc(fresh & lt_mask);
+                    mine = act && item < total;
+                    if (mine) none_left = false;
+                    if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
                 }
-                if (have) {
-                    const int pass = (int) (fl & FL_PASS_MASK);
-                    const bool adj = HAS_ADJ && pass == PP_ADJ;
-                    Rng r;
-                    r.state = r.inc = 0;
-#pragma unroll 1
-                    for (int k = adj ? 1 : 0; k >= 0; --k) {  // sampler.seed(seed, wavefront) [+ the alt sampler, :100-107]
-                        r.seed_sampler(k ? P.alt_seed : P.seed, idx);
-                        if (k) {
-                            PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
-                            PU(F_ASEQ, s) = (uint32_t) (r.inc >> 1);
-                        }
-                    }
-                    if (adj) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            PSET(F_DL0 + c, s, __ldg(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
-                            PSET(F_RSW0 + c, s, 0.0f);
-                            PSET(F_RSC0 + c, s, 0.0f);
-                            // split pipeline: state_in = radiance of the primal replay launch (batched.py:255-264)
-                            if (KIND == KIND_ADJ) PSET(F_R0 + c, s, P.sample_L[3 * (size_t) idx + c]);
-                        }
-                    } else {
-                        PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
-                    }
-                    Seg sg;
-                    int status;
-                    if (P.sensors) {
-                        // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
-                        status = batch_segment(P, pix, idx, sg);
-                    } else {
-                        const float jx = draw(r, K), jy = draw(r, K);
-                        status = camera_segment(P, pix, jx, jy, sg);
-                    }
-                    draw(r, K);  // :71
-                    const bool active = status == 1;
-                    const bool escaped = status == 0;
-                    fl = (unsigned) pass | ((unsigned) PM_DELTA << FL_MODE_SHIFT) | (escaped ? FL_ESCAPED : 0u) |
-                         (active ? FL_ACTIVE : 0u);
-                    if (active) {
-                        draw(r, K);  // :99 alt_seed_rnd
-                        if (pass == PP_PRIMAL) K.add(C_HITS, 1);
-                        draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
-                        PU(F_IDX, s) = idx;
-                        PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
-                        PU(F_SEQ, s) = (uint32_t) (r.inc >> 1);
-                        PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
-                        PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
-                        PSET(F_TMAX, s, sg.tmax);
-                        PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
-                        PU(F_DEPTH, s) = 0u;
+                // no more work items: the slot retires
+                const unsigned retire = __ballot_sync(FULL, act && none_left);
+                if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
+                if (KIND == KIND_DRT) {
+                    // DRT launch: the work items are the reservoir records of the adjoint launch
+                    if (mine) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(P.records + (size_t) item * kRecWords);
+                        const uint4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+                        // DRT on the stored segment (:543-581): the walk draws from the alt stream
+                        PU(F_OX, s) = a.x; PU(F_OY, s) = a.y; PU(F_OZ, s) = a.z; PU(F_DX, s) = a.w;
+                        PU(F_DY, s) = b.x; PU(F_DZ, s) = b.y; CU(C_TMAX, s) = b.z;
+                        PU(F_RSOX, s) = a.x; PU(F_RSOY, s) = a.y; PU(F_RSOZ, s) = a.z; PU(F_RSDX, s) = a.w;
+                        PU(F_RSDY, s) = b.x; PU(F_RSDZ, s) = b.y;
+                        PU(F_DL0, s) = b.w; PU(F_DL1, s) = c.x; PU(F_DL2, s) = c.y;
+                        PU(F_RNG_LO, s) = c.z; PU(F_RNG_HI, s) = c.w; PU(F_SEQ, s) = d.x;
+                        PU(F_DEPTH, s) = d.y;
+                        PU(F_FLAGS, s) = (unsigned) PP_ADJ | ((unsigned) PM_DRT << FL_MODE_SHIFT);
                         next = Q_WALK;
-                    } else {
-                        if (pass == PP_PRIMAL) {
-                            // the ray misses the medium: finish the sample right here
-                            float R[3] = {0.0f, 0.0f, 0.0f};
-                            if (escaped && !P.hide_emitters) {
-                                if (ENV) {
-                                    float pdf;
-                                    env_eval(P, sg.dx, sg.dy, sg.dz, R, pdf);  // no scattering: MIS weight 1
-                                } else {
+                    }
+                } else {
+                    // ray generation + reach_medium (batched.py:426-467, volpathsimple.py:292-319)
+                    uint32_t idx = 0, pix = 0;
+                    bool have = false;
+                    if (mine) {
+                        const uint32_t it = (uint32_t) item;
+                        if (slot_to_pixel(P, it / P.spp, pix)) {
+                            idx = pix * P.spp + it % P.spp;
+                            have = true;
+                            if (KIND == KIND_FWD) K.add(C_SAMPLES, 1);
+                        } else {
+                            next = Q_FREE;  // padding slot of a shard: try again
+                        }
+                    }
+                    if (have) {
+                        const int pass = KIND == KIND_ADJ ? PP_ADJ : PP_PRIMAL;
+                        Rng r;
+                        r.state = r.inc = 0;
+#pragma unroll 1
+                        for (int k = HAS_ADJ ? 1 : 0; k >= 0; --k) {  // sampler.seed(seed, wavefront) [+ the alt sampler, :100-107]
+                            pool_seed_sampler(r, k ? P.alt_seed : P.seed, idx);
+                            if (k) {
+                                PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
+                                PU(F_ASEQ, s) = (uint32_t) (r.inc >> 1);
+                            }
+                        }
+                        if (HAS_ADJ) {
 #pragma unroll
-                                    for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                            for (int c = 0; c < 3; ++c) {
+                                PSET(F_DL0 + c, s, ldg_tap(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
+                                PSET(F_RSW0 + c, s, 0.0f);
+                                PSET(F_RSC0 + c, s, 0.0f);
+                                // state_in = radiance of the primal replay launch (batched.py:255-264)
+                                PSET(F_R0 + c, s, __ldcs(P.sample_L + 3 * (size_t) idx + c));
+                            }
+                        } else {
+                            PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
+                        }
+                        Seg sg;
+                        float F[15], fu, fv;
+                        if (P.sensors) {
+                            // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
+                            batch_film_position(P, pix, idx, F, fu, fv);
+                        } else {
+                            const float jx = draw(r, K), jy = draw(r, K);
+                            sensor_film_position(P, pix, jx, jy, F, fu, fv);
+                        }
+                        const int status = camera_segment_frame(P, F, fu, fv, sg);
+                        draw(r, K);  // :71
+                        const bool active = status == 1;
+                        const bool escaped = status == 0;
+                        unsigned fl = (unsigned) pass | ((unsigned) PM_DELTA << FL_MODE_SHIFT) | (escaped ? FL_ESCAPED : 0u) |
+                                      (active ? FL_ACTIVE : 0u);
+                        if (active) {
+                            draw(r, K);  // :99 alt_seed_rnd
+                            if (pass == PP_PRIMAL) K.add(C_HITS, 1);
+                            draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
+                            PU(F_IDX, s) = idx;
+                            PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                            PU(F_SEQ, s) = (uint32_t) (r.inc >> 1);
+                            PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
+                            PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
+                            CSET(C_TMAX, s, sg.tmax);
+                            PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
+                            PU(F_DEPTH, s) = 0u;
+                            next = Q_WALK;
+                        } else {
+                            if (pass == PP_PRIMAL) {
+                                // the ray misses the medium: finish the sample right here
+                                float R[3] = {0.0f, 0.0f, 0.0f};
+                                if (escaped && !P.hide_emitters) {
+                                    if (ENV) {
+                                        float pdf;
+                                        env_eval(P, sg.dx, sg.dy, sg.dz, R, pdf);  // no scattering: MIS weight 1
+                                    } else {
+#pragma unroll
+                                        for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                                    }
                                 }
-                            }
-                            if (P.sample_L) {
-                                P.sample_L[3 * (size_t) idx + 0] = R[0];
-                                P.sample_L[3 * (size_t) idx + 1] = R[1];
-                                P.sample_L[3 * (size_t) idx + 2] = R[2];
-                            }
-                            if (KIND == KIND_FWD) {
+                                if (P.sample_L) {
+                                    P.sample_L[3 * (size_t) idx + 0] = R[0];
+                                    P.sample_L[3 * (size_t) idx + 1] = R[1];
+                                    P.sample_L[3 * (size_t) idx + 2] = R[2];
+                                }
                                 if (P.image) {
                                     atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
                                     atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
                                     atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
                                 }
-                            } else if (COUNT) {
-                                // the adjoint pass of a missed ray draws jitter + :71 and nothing else
-                                K.add(C_DRAWS, P.sensors ? 1 : 3);
                             }
+                            fl = 0u;
+                            next = Q_FREE;
                         }
-                        fl = 0u;
-                        next = Q_FREE;
+                        PU(F_FLAGS, s) = fl;
                     }
-                    PU(F_FLAGS, s) = fl;
-                } else if (next == Q_FREE) {
-                    PU(F_FLAGS, s) = 0u;
-                }
                 }
             }
 
@@ -1063,22 +1045,75 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_ALT_HI, s) = (uint32_t) (alt.state >> 32);
                 }
             }
+
+            // ---- set-up of a new free-flight walk (one code site; Medium::sample_interaction set-up, App. B.5):
+            //      first cell, next-boundary times and their increments, the first optical depth tau ----
+            if (work != Q_TAP && __ballot_sync(FULL, next == Q_WALK)) {
+                if (next == Q_WALK) {
+                    const float ox = PF(F_OX, s), oy = PF(F_OY, s), oz = PF(F_OZ, s);
+                    const float dx = PF(F_DX, s), dy = PF(F_DY, s), dz = PF(F_DZ, s);
+                    const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
+                    const float iy = dy != 0.0f ? 1.0f / dy : UIVR_INF;
+                    const float iz = dz != 0.0f ? 1.0f / dz : UIVR_INF;
+                    int cx, cy, cz;
+                    float tnx, tny, tnz;
+                    walk_axis_init(ox, dx, ix, P.fmres[0], P.mcs[0], P.mres[0], cx, tnx);
+                    walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
+                    walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
+                    const unsigned oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+                    const unsigned cw = (unsigned) (((cz + 1) * P.pm[1] + (cy + 1)) * P.pm[0] + (cx + 1)) | (oct << 28);
+                    K.add(C_MAJ, 1);  // the first cell (read by the walker)
+                    Rng r;
+                    r.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
+                    r.inc = ((uint64_t) PU(F_SEQ, s) << 1) | 1ull;
+                    const float tau0 = neg_log1m(draw(r, K));
+                    PU(F_RNG_LO, s) = (uint32_t) r.state;
+                    PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                    // per-mode walk state, and the queue the slot goes to when the walk ends
+                    unsigned fl = PU(F_FLAGS, s);
+                    const int mode = (int) ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT);
+                    int endq = Q_VERTEX;
+                    if (mode == PM_DELTA) {
+                        // vertices of the adjoint replay scatter gradients: they get their own queue so that
+                        // the scatter loop of a batch runs with all lanes
+                        if (HAS_ADJ && (fl & FL_PASS_MASK) == (unsigned) PP_ADJ) endq = Q_VERTEX_ADJ;
+                    } else if (mode == PM_NEE) {
+                        endq = Q_NEE_END;
+                    } else if (HAS_ADJ && mode == PM_NEE_ADJ) {
+                        endq = Q_SPAWN;
+                        fl |= FL_SPAWN_PHASE;
+                        PSET(F_T2, s, 1.0f);
+                    } else if (HAS_DRT && mode == PM_DRT) {
+                        PSET(F_T, s, 1.0f);
+                        PSET(F_DRT_D, s, 0.0f);
+                    }
+                    fl = (fl & ~(FL_ENDQ_MASK | FL_DID_SCATTER | FL_DRT_FOUND)) | ((unsigned) endq << FL_ENDQ_SHIFT);
+                    PU(F_FLAGS, s) = fl;
+                    // the continuation record (C_TMAX was written with the segment)
+                    uint32_t* rec = cont + s * C_WORDS;
+                    *reinterpret_cast<uint4*>(rec) = make_uint4(__float_as_uint(tnx), __float_as_uint(tny), __float_as_uint(tnz),
+                                                                __float_as_uint(tau0));
+                    rec[C_ADX] = __float_as_uint(fabsf(P.mcs[0] * ix));
+                    rec[C_ADY] = __float_as_uint(fabsf(P.mcs[1] * iy));
+                    rec[C_ADZ] = __float_as_uint(fabsf(P.mcs[2] * iz));
+                    *reinterpret_cast<uint4*>(rec + C_CI) = make_uint4(cw, 0u /* t = 0 */, (unsigned) endq, 0u);
+                }
+            }
             route(s, next);
         }
     }
 #undef PU
 #undef PF
 #undef PSET
+#undef CU
+#undef CF
+#undef CSET
     K.flush(P.counters);
 }
 
-// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 46 words/slot -> 768 slots = 138 KB
-// (+ 18 KB of queue rings) of the 227 KB shared memory, which leaves ~90 KB of L1 for the supergrid
-// and the taps; forward: 24 words/slot.  Measured optimum on config 3 (scripts/sweep_pool.sh).
-constexpr int kPoolSlotsBwd = UIVR_POOL_SLOTS_BWD;
-constexpr int kPoolSlotsFwd = UIVR_POOL_SLOTS_FWD;
-
-// kind: KIND_FWD / KIND_BWD / KIND_ADJ / KIND_DRT
+// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 54 words/slot (+ 8 ring words), forward: 32
+// (+ 8); what is left of the 227 KB is L1 for the walk table and the taps.
+// kind: KIND_FWD / KIND_ADJ / KIND_DRT
 inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
     const bool env = P.env_data != nullptr;
@@ -1098,8 +1133,7 @@ inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cu
         }                                                                                               \
     } while (0)
     switch (kind) {
-        case KIND_FWD: UIVR_POOL_LAUNCH2(KIND_FWD, kPoolSlotsFwd, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD); break;
-        case KIND_BWD: UIVR_POOL_LAUNCH2(KIND_BWD, kPoolSlotsBwd, UIVR_POOL_BLOCK_BWD, UIVR_POOL_HANDLERS_BWD); break;
+        case KIND_FWD: UIVR_POOL_LAUNCH2(KIND_FWD, UIVR_POOL_SLOTS_FWD, UIVR_POOL_BLOCK_FWD, UIVR_POOL_HANDLERS_FWD); break;
         case KIND_ADJ: UIVR_POOL_LAUNCH2(KIND_ADJ, UIVR_POOL_SLOTS_ADJ, UIVR_POOL_BLOCK_ADJ, UIVR_POOL_HANDLERS_ADJ); break;
         case KIND_DRT: UIVR_POOL_LAUNCH2(KIND_DRT, UIVR_POOL_SLOTS_DRT, UIVR_POOL_BLOCK_DRT, UIVR_POOL_HANDLERS_DRT); break;
         default: return -1;

@@ -13,6 +13,8 @@ include/uivr.h).  There is no CPU or eager fallback.
 """
 from __future__ import annotations
 
+import weakref
+
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -86,11 +88,16 @@ class Scene:
         return desc
 
     def update_medium(self, sigma_t: torch.Tensor, force: bool = False):
-        """params.update(): rebuild octets + majorant supergrid if sigma_t changed."""
-        key = (sigma_t.data_ptr(), sigma_t._version)
-        if force or key != self._medium_key:
+        """params.update(): rebuild the octet copy of sigma_t, the majorant supergrid and the walk table unless
+        this very tensor OBJECT, unmodified, is what they were built from.  The key must not alias: a fresh
+        tensor (params[k] = softplus(raw), fd-style params[k] = new) has version 0 and usually gets the freed
+        address of its predecessor back from the caching allocator, so (data_ptr, _version) is not enough --
+        identity is tracked with a weak reference.  Code that writes through raw pointers (optimize.Adam ->
+        uivr_adam_step) bumps the version counter itself (torch.autograd.graph.increment_version)."""
+        ref = self._medium_key[0]() if self._medium_key is not None else None
+        if force or ref is not sigma_t or self._medium_key[1:] != (sigma_t.data_ptr(), sigma_t._version):
             self.ctx.update_medium(sigma_t.data_ptr(), _stream())
-            self._medium_key = key
+            self._medium_key = (weakref.ref(sigma_t), sigma_t.data_ptr(), sigma_t._version)
 
 
     def update_medium_after_reshape(self, sigma_t: torch.Tensor):

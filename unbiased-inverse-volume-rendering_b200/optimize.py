@@ -111,6 +111,8 @@ class Adam:
             ctx.adam_step(p.data_ptr(), g.data_ptr(), self.m[k].data_ptr(), self.v[k].data_ptr(), p.numel(),
                           self.lr[k], self.beta_1, self.beta_2, self.epsilon, self.t[k], lo,
                           hi if hi != float("inf") else 3.4028234663852886e38, _stream())
+            # the kernel wrote through the raw pointer: tell torch (and Scene.update_medium's cache key)
+            torch.autograd.graph.increment_version(p)
 
 
 class SGD:

@@ -229,20 +229,25 @@ def cube_test_scene(resx=128, resy=128, density_scale=1.0, res=(3, 3, 3)) -> Vol
                        scale=density_scale, majorant_resolution_factor=0)
 
 
-def synthetic_grids(n: int, seed: int = 20220721):
+def synthetic_grids(n: int, seed: int = 20220721, dense: bool = False):
     """Deterministic heterogeneous sigma_t / albedo grids, SURVEY §8(d) recipe.
-    Returns torch CPU tensors (sigma_t (n,n,n,1) in [0,1], albedo (n,n,n,3))."""
+    Returns torch CPU tensors (sigma_t (n,n,n,1) in [0,1], albedo (n,n,n,3)).
+    dense: a medium without empty space (no spherical fall-off, no `< 0.05 -> 0` cut; d = 0.5 + 0.5 f):
+    the second, HBM-heavier bench workload."""
     import torch
     import torch.nn.functional as F
     g = torch.Generator().manual_seed(seed)
     c = torch.rand(1, 1, 16, 16, 16, generator=g)
     f = F.interpolate(c, size=(n, n, n), mode="trilinear", align_corners=True)[0, 0]
-    ax = (torch.arange(n, dtype=torch.float32) + 0.5) / n - 0.5
-    r2 = ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2
-    fall = torch.clamp(1.0 - r2 / 0.25, 0.0, 1.0)
-    d = f * f * fall
-    d = d / d.max()
-    d[d < 0.05] = 0.0
+    if dense:
+        d = 0.5 + 0.5 * f
+    else:
+        ax = (torch.arange(n, dtype=torch.float32) + 0.5) / n - 0.5
+        r2 = ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2
+        fall = torch.clamp(1.0 - r2 / 0.25, 0.0, 1.0)
+        d = f * f * fall
+        d = d / d.max()
+        d[d < 0.05] = 0.0
     a = torch.rand(1, 3, 8, 8, 8, generator=g)
     a = F.interpolate(a, size=(n, n, n), mode="trilinear", align_corners=True)[0]
     albedo = (0.2 + 0.75 * a).permute(1, 2, 3, 0).contiguous()
