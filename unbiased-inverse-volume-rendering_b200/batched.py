@@ -106,23 +106,26 @@ class _BatchedRenderOp(torch.autograd.Function):
     decorrelated set of rays through the same pixels."""
 
     @staticmethod
-    def forward(ctx, sigma_t, albedo, scene, integrator, batch, seed, seed_grad, spp, spp_grad, keys):
+    def forward(ctx, sigma_t, albedo, scene, integrator, batch, seed, seed_grad, spp, spp_grad, keys, shard, reducer):
         params = {keys[0]: sigma_t, keys[1]: albedo}
-        image = _launch(scene, integrator, params, batch, seed, spp, None, None)
+        image = _launch(scene, integrator, params, batch, seed, spp, None, None, shard)
         ctx.save_for_backward(sigma_t, albedo)
-        ctx.meta = (scene, integrator, batch, seed_grad, spp_grad, keys)
+        ctx.meta = (scene, integrator, batch, seed_grad, spp_grad, keys, shard, reducer)
         return image
 
     @staticmethod
     def backward(ctx, grad_image):
         sigma_t, albedo = ctx.saved_tensors
-        scene, integrator, batch, seed_grad, spp_grad, keys = ctx.meta
+        scene, integrator, batch, seed_grad, spp_grad, keys, shard, reducer = ctx.meta
         params = {keys[0]: sigma_t, keys[1]: albedo}
-        dsig, dalb = _launch(scene, integrator, params, batch, seed_grad, spp_grad, grad_image, None)
-        return (dsig, dalb) + (None,) * 8
+        dsig, dalb = _launch(scene, integrator, params, batch, seed_grad, spp_grad, grad_image, None, shard)
+        if reducer is not None:
+            dsig, dalb = reducer(dsig, dalb)
+        return (dsig, dalb) + (None,) * 10
 
 
-def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, seed, spp, grad_image, sample_out):
+def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, seed, spp, grad_image, sample_out,
+            shard=None):
     table, film_size, batch_size, batch_seed = batch
     nerf = isinstance(integrator, NeRFIntegrator)  # render_batch takes any registered integrator (batched.py:110-112)
     sig, alb = scene.check_params(params, integrator.second_suffix)
@@ -135,9 +138,9 @@ def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, se
         if grad_image is None:
             image = torch.empty((batch_size, 3), dtype=torch.float32, device=sig.device)
             if nerf:
-                scene.ctx.nerf_forward(props, alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, None, _stream())
+                scene.ctx.nerf_forward(props, alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, shard, _stream())
             else:
-                scene.ctx.render_forward(alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, None, _stream())
+                scene.ctx.render_forward(alb.detach().data_ptr(), seed, spp, image.data_ptr(), sp, shard, _stream())
             return image
         g = grad_image.to(dtype=torch.float32).contiguous()
         if tuple(g.shape) != (batch_size, 3):
@@ -145,10 +148,10 @@ def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, se
         dsig, dalb = torch.empty_like(sig), torch.empty_like(alb)
         if nerf:
             scene.ctx.nerf_backward(props, alb.detach().data_ptr(), g.data_ptr(), seed, spp, dsig.data_ptr(),
-                                    dalb.data_ptr(), sp, None, _stream())
+                                    dalb.data_ptr(), sp, shard, _stream())
         else:
             scene.ctx.render_backward(alb.detach().data_ptr(), g.data_ptr(), seed, spp, dsig.data_ptr(),
-                                      dalb.data_ptr(), sp, None, _stream())
+                                      dalb.data_ptr(), sp, shard, _stream())
         return dsig, dalb
     finally:
         scene.ctx.set_batch(None)
@@ -156,10 +159,17 @@ def _launch(scene: Scene, integrator: VolpathSimpleIntegrator, params, batch, se
 
 def render_batch(batch_size: int, scene: Scene, sensors: Sequence[Sensor], params: Dict[str, torch.Tensor],
                  integrator: VolpathSimpleIntegrator, seed: int = 0, seed_grad: int = 0, spp: int = 0,
-                 spp_grad: int = 0):
+                 spp_grad: int = 0, shard=None, reducer=None):
     """batched.py:88-131.  Returns (image [B, 3] differentiable w.r.t. the two grids, sensor_idx [B],
     pixels [B, 2]) -- the reference returns the same triple next to its film / sampler objects
-    (batched.py:53-56), the indices feeding gather_ref_values (optimize.py:341)."""
+    (batched.py:53-56), the indices feeding gather_ref_values (optimize.py:341).
+
+    Data-parallel ray batches (the reference's production mode on several GPUs): every rank calls this with
+    the SAME seed -- hence the same (sensor, pixel) batch and the same counter-based RNG streams -- and its own
+    `shard` = sharding.pixel_shard(rank, world): batch element b is rendered by rank (b // block) % world, the
+    other rows of this rank's image stay 0 (a per-element loss needs no forward collective; `gather_image` sums
+    the partial images when the whole batch is wanted).  `reducer(dsig, dalb)` (e.g. sharding.all_reduce_pair)
+    runs on the parameter gradients in the backward pass."""
     if spp <= 0:
         raise ValueError("spp must be positive")
     if spp_grad == 0:
@@ -175,5 +185,5 @@ def render_batch(batch_size: int, scene: Scene, sensors: Sequence[Sensor], param
     k_sig, k_alb = _find_key(params, SIGMA_T_SUFFIX), _find_key(params, integrator.second_suffix)
     batch = (table, film_size, int(batch_size), seed & 0xFFFFFFFF)
     image = _BatchedRenderOp.apply(params[k_sig], params[k_alb], scene, integrator, batch, seed, seed_grad,
-                                   spp, spp_grad, (k_sig, k_alb))
+                                   spp, spp_grad, (k_sig, k_alb), shard, reducer)
     return image, sensor_idx, pixels

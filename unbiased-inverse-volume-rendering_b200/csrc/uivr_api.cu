@@ -26,7 +26,9 @@ struct uivr_ctx {
     size_t oct_cells = 0;
     float* maj = nullptr;
     size_t maj_cells = 0;
-    uint32_t* wtab = nullptr;       // walk table: padded supergrid + exit masks (Params::wtab)
+    uint32_t* wtab_alloc = nullptr; // walk table: padded supergrid + exit masks, with `wtab_slack` border words on
+    uint32_t* wtab = nullptr;       // either side (speculative look-ahead reads); wtab = cell 0 (Params::wtab)
+    int wtab_slack = 0;
     uint8_t* emask[2] = {nullptr, nullptr};  // ping-pong buffers of the exit-mask sweeps
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
@@ -248,7 +250,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -419,11 +421,13 @@ int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream) {
     const int mx = ctx->mres[0], my = ctx->mres[1], mz = ctx->mres[2];
     const size_t pcells = (size_t) (mx + 2) * (my + 2) * (mz + 2);
     if (mcells != ctx->maj_cells) {
-        cudaFree(ctx->maj); cudaFree(ctx->wtab); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]);
-        ctx->maj = nullptr; ctx->wtab = nullptr; ctx->emask[0] = ctx->emask[1] = nullptr;
+        cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]);
+        ctx->maj = nullptr; ctx->wtab = ctx->wtab_alloc = nullptr; ctx->emask[0] = ctx->emask[1] = nullptr;
         ctx->maj_cells = 0;
+        ctx->wtab_slack = (mx + 2) * (my + 2);
         UIVR_CUDA(ctx, cudaMalloc(&ctx->maj, mcells * sizeof(float)));
-        UIVR_CUDA(ctx, cudaMalloc(&ctx->wtab, pcells * sizeof(uint32_t)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->wtab_alloc, (pcells + 2 * (size_t) ctx->wtab_slack) * sizeof(uint32_t)));
+        ctx->wtab = ctx->wtab_alloc + ctx->wtab_slack;
         UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[0], mcells));
         UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[1], mcells));
         ctx->maj_cells = mcells;
@@ -436,7 +440,7 @@ int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream) {
     k_exit_sweep<<<(my * mz + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, nullptr, ctx->emask[0], mx, 1, my, (size_t) mx, mz, sxy, 1);
     k_exit_sweep<<<(mx * mz + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, ctx->emask[0], ctx->emask[1], my, (size_t) mx, mx, 1, mz, sxy, 2);
     k_exit_sweep<<<(mx * my + kBlock - 1) / kBlock, kBlock, 0, st>>>(ctx->maj, ctx->emask[1], ctx->emask[0], mz, sxy, mx, 1, my, (size_t) mx, 4);
-    k_build_walk_table<<<grid, kBlock, 0, st>>>(ctx->maj, ctx->emask[0], ctx->wtab, mx, my, mz);
+    k_build_walk_table<<<grid, kBlock, 0, st>>>(ctx->maj, ctx->emask[0], ctx->wtab, mx, my, mz, ctx->wtab_slack);
     ctx->launches += 6;
     UIVR_CUDA(ctx, cudaGetLastError());
     ctx->have_medium = true;

@@ -217,11 +217,11 @@ UIVR_DEV float draw(Rng& r, Counters<COUNT>& K) {
 // grid lookups
 // --------------------------------------------------------------------------------------
 // Taps are gathers with little reuse (one 32-byte sector per sigma_t tap out of 537 MB, 8 x 12 bytes per albedo
-// tap): they read through the non-coherent path WITHOUT allocating in L1, so that what is left of the L1 /
-// shared-memory carve-out next to the slot pool keeps the walk table (157 KB at 256^3 / 8), which every DDA
-// step reads.  UIVR_TAP_NOALLOC=0 restores plain __ldg for A/B runs.
+// tap).  UIVR_TAP_NOALLOC=1 reads them through the non-coherent path WITHOUT allocating in L1 (to keep the L1 for
+// the walk table): measured SLOWER on config 3 (460 vs 484 Msamples/s, profiles/r02_history.md), so plain __ldg
+// is the default.
 #ifndef UIVR_TAP_NOALLOC
-#define UIVR_TAP_NOALLOC 1
+#define UIVR_TAP_NOALLOC 0
 #endif
 UIVR_DEV float4 ldg_tap4(const float4* p) {
 #if UIVR_TAP_NOALLOC

@@ -103,17 +103,22 @@ __global__ void __launch_bounds__(kBlock) k_exit_sweep(const float* __restrict__
     }
 }
 
+// `wtab` points at cell 0 of the padded grid; `slack` words before and after it belong to the allocation too and
+// are filled with border words: the walkers request the word of the cell AFTER the next one speculatively, which
+// for a walk standing next to the border lies one stride (<= (mx+2)(my+2) words) outside the padded grid.
 __global__ void __launch_bounds__(kBlock) k_build_walk_table(const float* __restrict__ maj, const uint8_t* __restrict__ mask,
-                                                             uint32_t* __restrict__ wtab, int mx, int my, int mz) {
+                                                             uint32_t* __restrict__ wtab, int mx, int my, int mz, int slack) {
     const int px = mx + 2, py = my + 2, pz = mz + 2;
     const int n = px * py * pz;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int x = i % px - 1, y = (i / px) % py - 1, z = i / (px * py) - 1;
+    for (int i = -slack + (int) (blockIdx.x * blockDim.x + threadIdx.x); i < n + slack; i += gridDim.x * blockDim.x) {
         uint32_t w = kWalkBorder;
-        if (x >= 0 && x < mx && y >= 0 && y < my && z >= 0 && z < mz) {
-            const size_t c = ((size_t) z * my + y) * mx + x;
-            const float m = maj[c];
-            w = m > 0.0f ? __float_as_uint(m) : (kWalkEmpty | (uint32_t) mask[c]);
+        if (i >= 0 && i < n) {
+            const int x = i % px - 1, y = (i / px) % py - 1, z = i / (px * py) - 1;
+            if (x >= 0 && x < mx && y >= 0 && y < my && z >= 0 && z < mz) {
+                const size_t c = ((size_t) z * my + y) * mx + x;
+                const float m = maj[c];
+                w = m > 0.0f ? __float_as_uint(m) : (kWalkEmpty | (uint32_t) mask[c]);
+            }
         }
         wtab[i] = w;
     }

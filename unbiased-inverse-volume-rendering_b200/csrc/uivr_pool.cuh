@@ -35,31 +35,31 @@ namespace uivr {
 
 // tuning knobs (overridable at build time for sweeps: scripts/sweep_pool.sh)
 #ifndef UIVR_POOL_BLOCK_ADJ
-#define UIVR_POOL_BLOCK_ADJ 1024
+#define UIVR_POOL_BLOCK_ADJ 896
 #endif
 #ifndef UIVR_POOL_HANDLERS_ADJ
 #define UIVR_POOL_HANDLERS_ADJ 12
 #endif
 #ifndef UIVR_POOL_SLOTS_ADJ
-#define UIVR_POOL_SLOTS_ADJ 512
+#define UIVR_POOL_SLOTS_ADJ 832
 #endif
 #ifndef UIVR_POOL_BLOCK_DRT
-#define UIVR_POOL_BLOCK_DRT 1024
+#define UIVR_POOL_BLOCK_DRT 896
 #endif
 #ifndef UIVR_POOL_HANDLERS_DRT
 #define UIVR_POOL_HANDLERS_DRT 12
 #endif
 #ifndef UIVR_POOL_SLOTS_DRT
-#define UIVR_POOL_SLOTS_DRT 512
+#define UIVR_POOL_SLOTS_DRT 832
 #endif
 #ifndef UIVR_POOL_BLOCK_FWD
-#define UIVR_POOL_BLOCK_FWD 1024
+#define UIVR_POOL_BLOCK_FWD 896
 #endif
 #ifndef UIVR_POOL_HANDLERS_FWD
 #define UIVR_POOL_HANDLERS_FWD 12
 #endif
 #ifndef UIVR_POOL_SLOTS_FWD
-#define UIVR_POOL_SLOTS_FWD 1024
+#define UIVR_POOL_SLOTS_FWD 1280
 #endif
 #ifndef UIVR_POOL_QUANTUM
 #define UIVR_POOL_QUANTUM 16
@@ -74,7 +74,7 @@ namespace uivr {
 #define UIVR_POOL_SETMAXNREG 1
 #endif
 #ifndef UIVR_POOL_WALKER_REGS
-#define UIVR_POOL_WALKER_REGS 48
+#define UIVR_POOL_WALKER_REGS 56
 #endif
 #ifndef UIVR_POOL_HANDLERS_LAST
 #define UIVR_POOL_HANDLERS_LAST 0   // 1: the handler warps are the LAST warps of the CTA (scheduler priority A/B)
@@ -86,10 +86,14 @@ constexpr int kWalkQuantum = UIVR_POOL_QUANTUM;   // a walker warp hands its fin
 constexpr int kWalkSubSteps = UIVR_POOL_SUBSTEPS; // supergrid cells per lane between two warp votes
 // walker lane states
 enum : int { W_IDLE = 0, W_WALKING = 1, W_HIT = 2, W_END = 3 };
-constexpr unsigned kPoolEmpty = 0xFFFFFFFFu;
+constexpr unsigned kPoolEmpty = 0xFFFFu;
 constexpr int kPoolMinBatch = UIVR_POOL_MINBATCH;    // smallest handler batch while the walk queue runs dry
 constexpr int kPoolStarveBelow = UIVR_POOL_STARVE;   // "runs dry": fewer walk jobs than this are queued
 constexpr unsigned kPoolHandlerSleepMax = 512;   // ns; idle handler warps back off up to this
+#ifndef UIVR_POOL_WALKER_SLEEP_MAX
+#define UIVR_POOL_WALKER_SLEEP_MAX 512
+#endif
+constexpr unsigned kPoolWalkerSleepMax = UIVR_POOL_WALKER_SLEEP_MAX;  // ns; the same for idle walker warps
 constexpr int kPoolSpinLimit = 1 << 22;          // watchdog: mailbox spins
 constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one walk quantum
 constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
@@ -109,7 +113,7 @@ enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
 enum : int {
     F_IDX = 0, F_RNG_LO, F_RNG_HI, F_SEQ,
     F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ,
-    F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_TS, F_FLAGS, F_DEPTH, F_VPX, F_VPY, F_VPZ,
+    F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_TS, F_FLAGS, F_DEPTH,
     F_NUM_FWD,
     // adjoint-only state
     F_ALT_LO = F_NUM_FWD, F_ALT_HI, F_ASEQ,
@@ -129,10 +133,10 @@ enum : int {
 // words maps 8 consecutive quarter-warps onto distinct bank quads) and saves a tentative collision with one
 // 128-bit + one 64-bit store.
 enum : int {
-    C_TNX = 0, C_TNY, C_TNZ, C_TAU,    // next-boundary times of the three axes, remaining optical depth
+    C_TNX = 0, C_TNY, C_TNZ, C_TAU,    // boundary times of the three axes (as seen from the NEXT cell), remaining optical depth
     C_ADX, C_ADY, C_ADZ, C_TMAX,       // their increments per cell, segment end t_exit
-    C_CI, C_WT, C_ENDQ, C_PAD,         // cell index | octant << 28, position t, queue at the end of the walk
-    C_WORDS
+    C_CI, C_WT, C_CIN, C_TCUR,         // current cell | octant << 28, position t, next cell | end queue << 28, time the
+    C_WORDS                            // ray leaves the current cell
 };
 
 // F_FLAGS bits
@@ -153,6 +157,22 @@ struct PoolCtl {
     int exhausted;   // the global sample queue is empty
     int abort;       // watchdog tripped: every warp leaves
 };
+
+// One decision of the supergrid DDA: the axis whose boundary the ray crosses first (ties: x before y before z, as
+// in the oracle's walk_next), the time of that crossing (= when the ray leaves the current cell) and the cell
+// behind it; the boundary time of that axis moves on by one cell.
+UIVR_DEV void walk_decide(float& tnx, float& tny, float& tnz, float adx, float ady, float adz, int sxl, int syl,
+                          int szl, int ci, float& tcur, int& cin) {
+    const bool yx = tny < tnx;
+    float tn = yx ? tny : tnx;
+    const bool zb = tnz < tn;
+    tn = zb ? tnz : tn;
+    tcur = tn;
+    cin = ci + (zb ? szl : (yx ? syl : sxl));
+    tnx = (!zb && !yx) ? tnx + adx : tnx;
+    tny = (!zb && yx) ? tny + ady : tny;
+    tnz = zb ? tnz + adz : tnz;
+}
 
 // sampler.seed(seed, wavefront) for one lane, out of line: TEA + the PCG32 seeding sequence are ~150 instructions
 // and FETCH / ray-batch generation need them at several places (instruction-cache footprint of the handlers)
@@ -190,7 +210,7 @@ constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) a
 // throughput * phase * mis * Le / pdf of the direction sampled at Q_SPAWN until Q_NEE_END
 template <bool BWD, int NSLOT, bool ENV = false>
 constexpr size_t pool_smem_bytes() {
-    return 128 + (size_t) Q_NUM * NSLOT * sizeof(unsigned) +
+    return 128 + (size_t) Q_NUM * NSLOT * sizeof(uint16_t) +
            (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0) + C_WORDS) * NSLOT * sizeof(uint32_t);
 }
 
@@ -209,8 +229,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     static_assert(Q_NUM <= 8, "the handler scheduler packs the queue id into 3 bits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PoolCtl* const ctl = reinterpret_cast<PoolCtl*>(smem_raw);
-    unsigned* const ring = reinterpret_cast<unsigned*>(smem_raw + 128);  // one mailbox cell per ring position
-    uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * NSLOT * sizeof(unsigned));
+    // one 16-bit mailbox cell per ring position.  A position has exactly one producer and one consumer per lap
+    // (both reserved it through the atomic tail / head counters), so the cells need no atomics: the producer
+    // waits for kPoolEmpty and stores the id, the consumer waits for an id and stores kPoolEmpty back.
+    volatile uint16_t* const ring = reinterpret_cast<volatile uint16_t*>(smem_raw + 128);
+    uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * NSLOT * sizeof(uint16_t));
+    static_assert(NSLOT < 65535 && (Q_NUM * NSLOT * sizeof(uint16_t)) % 16 == 0, "16-bit slot ids; the pool stays 16-byte aligned");
     uint32_t* const cont = pool + (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT;  // [slot][C_WORDS]
     static_assert(NSLOT % 4 == 0, "the continuation records must stay 16-byte aligned");
 
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 
     // ---- pool / queue initialisation: every slot starts in Q_FREE ----
     for (int i = threadIdx.x; i < Q_NUM * NSLOT; i += kPoolBlock)
-        ring[i] = (i < NSLOT) ? (unsigned) i : kPoolEmpty;   // ring 0 == Q_FREE
+        ring[i] = (uint16_t) ((i < NSLOT) ? (unsigned) i : kPoolEmpty);   // ring 0 == Q_FREE
     for (int i = threadIdx.x; i < NSLOT; i += kPoolBlock) PU(F_FLAGS, i) = 0u;
     if (threadIdx.x < Q_NUM) {
         ctl->head[threadIdx.x] = 0u;
@@ -258,13 +282,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         if ((int) lane < got) {
             unsigned pos = base % (unsigned) NSLOT + lane;  // (head runs free; the ring has NSLOT cells)
             pos -= pos >= (unsigned) NSLOT ? (unsigned) NSLOT : 0u;
-            unsigned* cell = &ring[q * NSLOT + pos];
+            volatile uint16_t* cell = &ring[q * NSLOT + pos];
             unsigned v;
             int spins = 0;
             // the position is reserved by a producer; its store may still be in flight
-            while ((v = atomicExch(cell, kPoolEmpty)) == kPoolEmpty) {
+            while ((v = *cell) == kPoolEmpty) {
                 if (++spins > kPoolSpinLimit) { trip(0x200u + (unsigned) q); v = 0; break; }
             }
+            *cell = (uint16_t) kPoolEmpty;
             slot = v;
         }
         __threadfence_block();
@@ -285,13 +310,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             if (next == q) {
                 unsigned pos = base % (unsigned) NSLOT + __popc(m & lt_mask);
                 pos -= pos >= (unsigned) NSLOT ? (unsigned) NSLOT : 0u;
-                unsigned* cell = &ring[q * NSLOT + pos];
+                volatile uint16_t* cell = &ring[q * NSLOT + pos];
                 int spins = 0;
                 // the cell is free unless the consumer of the previous lap has not taken its id yet
-                while (atomicCAS(cell, kPoolEmpty, s) != kPoolEmpty) {
+                while (*cell != kPoolEmpty) {
                     if (++spins > kPoolSpinLimit) { trip(0x100u + (unsigned) q); break; }
                 }
+                *cell = (uint16_t) s;
             }
+            __threadfence_block();  // the ids before the count that makes them poppable
             __syncwarp();
             if ((int) lane == leader) atomicAdd(&ctl->count[q], __popc(m));
             todo &= ~m;
@@ -309,9 +336,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     // lane needs ~30 registers, a handler lane wants ~100; launched with 64 per thread (1024 threads), the
     // walkers give registers up and the handlers take them.  HANDLERS must be a multiple of 4.
 #if UIVR_POOL_SETMAXNREG
-    static_assert(HANDLERS % 4 == 0 && BLOCK == 1024, "setmaxnreg works on aligned warpgroups");
+    static_assert(HANDLERS % 4 == 0 && (BLOCK / 32 - HANDLERS) % 4 == 0 && BLOCK % 128 == 0,
+                  "setmaxnreg works on aligned warpgroups of 4 warps");
+    // the CTA's register pool is what it was launched with: (registers per thread under __launch_bounds__(BLOCK, 1),
+    // a multiple of 8) x BLOCK; the walkers keep kRegWalker each, the handlers share the rest
+    constexpr int kRegLaunch = (65536 / BLOCK) / 8 * 8 > 255 ? 248 : (65536 / BLOCK) / 8 * 8;
     constexpr int kRegWalker = UIVR_POOL_WALKER_REGS;
-    constexpr int kRegHandler = ((2048 - (32 - HANDLERS) * kRegWalker) / HANDLERS) / 8 * 8;
+    constexpr int kRegHandlerRaw = ((kRegLaunch * (BLOCK / 32) - (BLOCK / 32 - HANDLERS) * kRegWalker) / HANDLERS) / 8 * 8;
+    constexpr int kRegHandler = kRegHandlerRaw > 232 ? 232 : kRegHandlerRaw;
+    static_assert(kRegWalker <= kRegLaunch && kRegHandler >= kRegLaunch, "walkers give registers up, handlers take them");
 #endif
     if (!is_handler) {
 #if UIVR_POOL_SETMAXNREG
@@ -325,9 +358,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         int wendq = 0;             // queue of the slot when the walk ends without a collision
         float tnx = 0.0f, tny = 0.0f, tnz = 0.0f, adx = 0.0f, ady = 0.0f, adz = 0.0f;
         float tau = 0.0f, wt = 0.0f, tmax = 0.0f;
-        int ci = 0, sxl = 0, syl = 0, szl = 0;
-        unsigned e = 0u, obit = 0u, oct = 0u;
+        float tcur = 0.0f;         // time the ray leaves the current cell
+        int ci = 0, cin = 0, sxl = 0, syl = 0, szl = 0;
+        unsigned e = 0u, en = 0u, obit = 0u, oct = 0u;   // walk-table words of the current / the next cell
         unsigned widle_ns = 64;
+        int wphase = 0, wcur = 0;  // register-pair roles of the DDA loop (see dda_step)
         for (;;) {
             if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
             // ---- 1. idle lanes pick up walk continuations from Q_WALK ----
@@ -351,8 +386,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             ci = (int) (rc.x & kCiMask);
                             oct = rc.x >> 28;
                             wt = __uint_as_float(rc.y);
-                            wendq = (int) rc.z;
+                            cin = (int) (rc.z & kCiMask);
+                            wendq = (int) (rc.z >> 28);
+                            tcur = __uint_as_float(rc.w);
                             e = __ldg(P.wtab + ci);
+                            en = __ldg(P.wtab + cin);
                             obit = 1u << oct;
                             const int px = P.pm[0], pxy = P.pm[0] * P.pm[1];
                             sxl = (oct & 1u) ? -1 : 1;
@@ -368,7 +406,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 if (__shfl_sync(FULL, *((volatile int*) &ctl->live), 0) <= 0) break;
                 if (__shfl_sync(FULL, clock64() - t_progress > kPoolIdleLimit ? 1 : 0, 0)) { trip(0x300u); break; }
                 __nanosleep(widle_ns);
-                widle_ns = widle_ns < kPoolHandlerSleepMax ? widle_ns * 2 : widle_ns;  // back off: polling costs issue slots
+                widle_ns = widle_ns < kPoolWalkerSleepMax ? widle_ns * 2 : widle_ns;  // back off: polling costs issue slots
                 continue;
             }
             widle_ns = 64;
@@ -377,50 +415,63 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             const int n0 = __popc(m_walk);
             const int n_stop = n0 > kWalkQuantum ? n0 - kWalkQuantum : 0;
             const bool short_handed = n0 <= 32 - kWalkQuantum;
-            for (int it = 1;; ++it) {
-#pragma unroll
-                for (int sub = 0; sub < kWalkSubSteps; ++sub) {
-                    if (wst == W_WALKING) {
-                        // empty cell with only empty cells ahead (or the border): no further collision
-                        const bool gone = (int) e < 0 && (e & obit) != 0u;
-                        const bool yx = tny < tnx;
-                        float tn = yx ? tny : tnx;
-                        const bool zb = tnz < tn;
-                        tn = zb ? tnz : tn;
-                        const bool more = tn < tmax;
-                        const float t_end = more ? tn : tmax;
-                        const float len = fmaxf(t_end - wt, 0.0f);
-                        const bool dense = (int) e > 0;
-                        const float dtau = __uint_as_float(e) * len;
-                        // tau is used up inside this cell: the tap handler takes over
-                        const bool hit = dense && tau < dtau;
-                        if (gone || hit) {
-                            wst = gone ? W_END : W_HIT;
+            // One DDA step of this lane (ec / cc: walk-table word and index of the current cell, en / cn: of the next
+            // one, whose word was requested one step earlier).  The caller alternates the roles of the two register
+            // pairs from step to step, so that entering the next cell moves no registers.
+            auto dda_step = [&](unsigned& ec, unsigned& en_, int& cc, int& cn) {
+                if (wst == W_WALKING) {
+                    // empty cell with only empty cells ahead (or the border): no further collision
+                    const bool gone = (int) ec < 0 && (ec & obit) != 0u;
+                    const bool more = tcur < tmax;
+                    const float t_end = more ? tcur : tmax;
+                    const float len = fmaxf(t_end - wt, 0.0f);
+                    const bool dense = (int) ec > 0;
+                    const float dtau = __uint_as_float(ec) * len;
+                    // tau is used up inside this cell: the tap handler takes over
+                    const bool hit = dense && tau < dtau;
+                    if (gone || hit) {
+                        wst = gone ? W_END : W_HIT;
+                        wcur = &ec == &e ? 0 : 1;
+                    } else {
+                        tau = dense ? tau - dtau : tau;
+                        wt = fmaxf(wt, t_end);
+                        if (more) {
+                            // enter the next cell (its word is en_); decide the step after it and request that
+                            // cell's word now: the load latency hides behind a whole step
+                            if (COUNT && (en_ & 0x80000100u) != 0x80000100u) K.add(C_MAJ, 1);
+                            walk_decide(tnx, tny, tnz, adx, ady, adz, sxl, syl, szl, cn, tcur, cc);
+                            ec = __ldg(P.wtab + cc);
                         } else {
-                            tau = dense ? tau - dtau : tau;
-                            wt = fmaxf(wt, t_end);
-                            // the step is harmless when t_exit has been reached (!more): the lane ends anyway
-                            ci += zb ? szl : (yx ? syl : sxl);
-                            tnx = (!zb && !yx) ? tnx + adx : tnx;
-                            tny = (!zb && yx) ? tny + ady : tny;
-                            tnz = zb ? tnz + adz : tnz;
-                            if (more) {
-                                e = __ldg(P.wtab + ci);
-                                if (COUNT && (e & 0x80000100u) != 0x80000100u) K.add(C_MAJ, 1);
-                            } else {
-                                wst = W_END;
-                            }
+                            wst = W_END;  // t_exit reached
                         }
                     }
                 }
-                const int n_walk = __popc(__ballot_sync(FULL, wst == W_WALKING));
-                if (n_walk <= n_stop) break;
-                if ((it & 7) == 0) {
-                    if (it > kPoolWalkLimit) { trip(0x400u); wst = W_END; break; }
+            };
+            for (int it = 1;; ++it) {
+                // even steps: (e, ci) current, (en, cin) next; odd steps: the other way round
+                dda_step(e, en, ci, cin);
+                int n_walk = __popc(__ballot_sync(FULL, wst == W_WALKING));
+                if (n_walk <= n_stop) { wphase = 1; break; }
+                dda_step(en, e, cin, ci);
+                n_walk = __popc(__ballot_sync(FULL, wst == W_WALKING));
+                if (n_walk <= n_stop) { wphase = 0; break; }
+                if ((it & 3) == 0) {
+                    if (it > kPoolWalkLimit) { trip(0x400u); wst = W_END; wphase = 0; break; }
                     // a warp that started short of lanes leaves as soon as the queue can fill them
                     if (short_handed &&
-                        __shfl_sync(FULL, (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0, 0) >= kWalkQuantum)
+                        __shfl_sync(FULL, (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0, 0) >= kWalkQuantum) {
+                        wphase = 0;
                         break;
+                    }
+                }
+            }
+            // Back to the canonical naming ((e, ci) current, (en, cin) next) for the lanes that walk on; a lane that
+            // stopped (hit / end) recorded which pair held its current cell.
+            {
+                const bool swap = wst == W_WALKING ? wphase == 1 : wcur == 1;
+                if (swap) {
+                    const unsigned te = e; e = en; en = te;
+                    const int tc = ci; ci = cin; cin = tc;
                 }
             }
             // ---- 3. hand finished lanes on: a tentative collision saves the words that changed ----
@@ -432,7 +483,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     uint32_t* rec = cont + s * C_WORDS;
                     *reinterpret_cast<uint4*>(rec) = make_uint4(__float_as_uint(tnx), __float_as_uint(tny), __float_as_uint(tnz),
                                                                 __float_as_uint(tau));
-                    *reinterpret_cast<uint2*>(rec + C_CI) = make_uint2((unsigned) ci | (oct << 28), __float_as_uint(wt));
+                    *reinterpret_cast<uint4*>(rec + C_CI) = make_uint4((unsigned) ci | (oct << 28), __float_as_uint(wt),
+                                                                       (unsigned) cin | ((unsigned) wendq << 28),
+                                                                       __float_as_uint(tcur));
                     next = Q_TAP;
                 } else {
                     next = wendq;
@@ -515,9 +568,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const int mode = (int) ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT);
                     const float sb = __uint_as_float(__ldg(P.wtab + (CU(C_CI, s) & kCiMask)));
                     // end of the cell along the ray, as the walker saw it
-                    const float tnx = CF(C_TNX, s), tny = CF(C_TNY, s), tnz = CF(C_TNZ, s), tmax = CF(C_TMAX, s);
-                    float tn = tny < tnx ? tny : tnx;
-                    tn = tnz < tn ? tnz : tn;
+                    const float tn = CF(C_TCUR, s), tmax = CF(C_TMAX, s);
                     const float t_end = tn < tmax ? tn : tmax;
                     const float t = CF(C_WT, s) + CF(C_TAU, s) / sb;
                     const float wt = t > t_end ? t_end : t;
@@ -597,7 +648,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (ds) {
                         albedo_tap(P, vx, vy, vz, albedo);
                         K.add(C_ALBEDO, 1);
-                        PSET(F_VPX, s, vx); PSET(F_VPY, s, vy); PSET(F_VPZ, s, vz);
+                        // the vertex becomes the origin of whatever leaves it (NEE segment, then the phase-sampled one)
+                        PSET(F_OX, s, vx); PSET(F_OY, s, vy); PSET(F_OZ, s, vz);
                     }
                     if (is_drt) {
                         if (ds) {
@@ -840,7 +892,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         uniform_sphere(xi1, xi2, wx, wy, wz);
                     }
                     Seg sg;
-                    const bool ok = make_segment(P, PF(F_VPX, s), PF(F_VPY, s), PF(F_VPZ, s), wx, wy, wz, sg) && worked;
+                    const bool ok = make_segment(P, PF(F_OX, s), PF(F_OY, s), PF(F_OZ, s), wx, wy, wz, sg) && worked;
                     PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
                     PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
                     CSET(C_TMAX, s, sg.tmax);
@@ -1061,7 +1113,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     walk_axis_init(oy, dy, iy, P.fmres[1], P.mcs[1], P.mres[1], cy, tny);
                     walk_axis_init(oz, dz, iz, P.fmres[2], P.mcs[2], P.mres[2], cz, tnz);
                     const unsigned oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
-                    const unsigned cw = (unsigned) (((cz + 1) * P.pm[1] + (cy + 1)) * P.pm[0] + (cx + 1)) | (oct << 28);
+                    const unsigned ci0 = (unsigned) (((cz + 1) * P.pm[1] + (cy + 1)) * P.pm[0] + (cx + 1));
                     K.add(C_MAJ, 1);  // the first cell (read by the walker)
                     Rng r;
                     r.state = (uint64_t) PU(F_RNG_LO, s) | ((uint64_t) PU(F_RNG_HI, s) << 32);
@@ -1089,14 +1141,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     }
                     fl = (fl & ~(FL_ENDQ_MASK | FL_DID_SCATTER | FL_DRT_FOUND)) | ((unsigned) endq << FL_ENDQ_SHIFT);
                     PU(F_FLAGS, s) = fl;
-                    // the continuation record (C_TMAX was written with the segment)
+                    // the continuation record (C_TMAX was written with the segment): the first step is decided here
+                    const int ppx = P.pm[0], ppxy = P.pm[0] * P.pm[1];
+                    const float adx = fabsf(P.mcs[0] * ix), ady = fabsf(P.mcs[1] * iy), adz = fabsf(P.mcs[2] * iz);
+                    float tcur;
+                    int cin;
+                    walk_decide(tnx, tny, tnz, adx, ady, adz, (oct & 1u) ? -1 : 1, (oct & 2u) ? -ppx : ppx,
+                                (oct & 4u) ? -ppxy : ppxy, (int) ci0, tcur, cin);
                     uint32_t* rec = cont + s * C_WORDS;
                     *reinterpret_cast<uint4*>(rec) = make_uint4(__float_as_uint(tnx), __float_as_uint(tny), __float_as_uint(tnz),
                                                                 __float_as_uint(tau0));
-                    rec[C_ADX] = __float_as_uint(fabsf(P.mcs[0] * ix));
-                    rec[C_ADY] = __float_as_uint(fabsf(P.mcs[1] * iy));
-                    rec[C_ADZ] = __float_as_uint(fabsf(P.mcs[2] * iz));
-                    *reinterpret_cast<uint4*>(rec + C_CI) = make_uint4(cw, 0u /* t = 0 */, (unsigned) endq, 0u);
+                    rec[C_ADX] = __float_as_uint(adx);
+                    rec[C_ADY] = __float_as_uint(ady);
+                    rec[C_ADZ] = __float_as_uint(adz);
+                    *reinterpret_cast<uint4*>(rec + C_CI) = make_uint4(ci0 | (oct << 28), 0u /* t = 0 */,
+                                                                       (unsigned) cin | ((unsigned) endq << 28),
+                                                                       __float_as_uint(tcur));
                 }
             }
             route(s, next);
@@ -1111,8 +1171,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     K.flush(P.counters);
 }
 
-// NSLOT: in-flight samples per CTA (one CTA per SM).  Backward: 54 words/slot (+ 8 ring words), forward: 32
-// (+ 8); what is left of the 227 KB is L1 for the walk table and the taps.
+// NSLOT: in-flight samples per CTA (one CTA per SM).  Per slot: 41 (backward) / 19 (forward) pool words + the 12-word
+// continuation record + 8 16-bit ring cells; what is left of the 227 KB is L1 for the walk table and the taps.
 // kind: KIND_FWD / KIND_ADJ / KIND_DRT
 inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
@@ -1122,6 +1182,12 @@ inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cu
         const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N, E>();                                  \
         e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
+        if (UIVR_POOL_SETMAXNREG) {                                                                     \
+            /* setmaxnreg.inc waits for registers of the CTA's pool: the pool must be what the budget assumes */ \
+            cudaFuncAttributes fa;                                                                      \
+            if (cudaFuncGetAttributes(&fa, k_pool<KD, C, N, T, H, E>) != cudaSuccess ||                 \
+                fa.numRegs != (65536 / (T)) / 8 * 8) return -3;                                         \
+        }                                                                                               \
         k_pool<KD, C, N, T, H, E><<<num_sms, T, smem, st>>>(P);                                         \
     } while (0)
 #define UIVR_POOL_LAUNCH2(KD, N, T, H)                                                                  \

@@ -76,3 +76,12 @@ def gather_image(image: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
     return image
+
+
+def all_reduce_pair(dsigma: torch.Tensor, dalbedo: torch.Tensor, group=None):
+    """`reducer` for render(..., reducer=) / render_batch(..., reducer=): sum the two parameter gradients over
+    the ranks (two collectives; GradientBuffer packs them into one for the bench loop)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(dsigma, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(dalbedo, op=dist.ReduceOp.SUM, group=group)
+    return dsigma, dalbedo
