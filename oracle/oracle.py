@@ -182,6 +182,37 @@ def render_backward(desc, props, sigma_t, albedo, grad_image, seed_grad: int, sp
     return dsig, dalb, samples, dict(zip(COUNTER_NAMES, (int(c) for c in counters)))
 
 
+def last_backward_primal_counters() -> Dict[str, int]:
+    """Events of the primal pass (batched.py:255-264) inside the most recent backward call of this process; they
+    are included in that call's counters."""
+    out = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    lib().uivr_oracle_last_backward_primal_counters(_ptr(out, C.c_uint64))
+    return dict(zip(COUNTER_NAMES, (int(c) for c in out)))
+
+
+def last_backward_replay_counters() -> Dict[str, int]:
+    """Events of the NEE adjoint's second walk over the shadow segments (volpathsimple.py:393-401) inside the most
+    recent backward call."""
+    out = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+    lib().uivr_oracle_last_backward_replay_counters(_ptr(out, C.c_uint64))
+    return dict(zip(COUNTER_NAMES, (int(c) for c in out)))
+
+
+def fused_backward_counters(total: Dict[str, int]) -> Dict[str, int]:
+    """Event counts of the CUDA slot-pool backward, from the counts of the backward just computed here: its adjoint
+    replay gathers the primal radiance itself (no primal pass: those events are not executed; samples and camera
+    hits are counted once) and logs the tentative collisions of every NEE shadow walk instead of walking the
+    segment a second time for the adjoint (no second set of supergrid reads / taps / draws; the scatters stay)."""
+    primal = last_backward_primal_counters()
+    replay = last_backward_replay_counters()
+    out = {k: total[k] - primal[k] for k in total}
+    out["camera_hits"] = total["camera_hits"]
+    out["samples"] = total["samples"]
+    for k in ("sigma_taps", "majorant_reads", "rng_draws"):
+        out[k] -= replay[k]
+    return out
+
+
 # ---- primitives ----
 
 def tea(v0: int, v1: int):
@@ -258,6 +289,11 @@ def build_exit_mask(majorant) -> np.ndarray:
 def set_exit_mask(enable: bool) -> None:
     """Test hook: walks stop early in empty space (default) or always run to the medium boundary."""
     lib().uivr_oracle_set_exit_mask(1 if enable else 0)
+
+
+def set_remaining_by_difference(enable: bool) -> None:
+    """Test hook: Li of the adjoint as L - gathered (the CUDA pipeline's form) instead of the running subtraction."""
+    lib().uivr_oracle_set_remaining_by_difference(1 if enable else 0)
 
 
 def adam_step(param, grad, m, v, lr, beta1, beta2, eps, t, lo, hi):

@@ -217,6 +217,7 @@ typedef struct {
 
 typedef struct {
     uint64_t c[UIVR_ORC_NUM_COUNTERS];
+    uint64_t r[UIVR_ORC_NUM_COUNTERS]; /* the share of c spent re-walking NEE segments for their adjoint (:393-401) */
 } counters_t;
 
 /* ------------------------------------------------------------------------------------ */
@@ -704,8 +705,11 @@ static void nee(const ctx_t* C, counters_t* K, const float p[3], const float bet
         float adj[3];
         for (int c = 0; c < 3; ++c) adj[c] = dL[c] * contrib[c];
         uint64_t d0 = clone.draws;
+        counters_t before = *K;
         ratio_track(C, K, &s, &clone, adj);
         rng->draws += clone.draws - d0; /* the replay consumes (cloned) draws too */
+        for (int k = 0; k < UIVR_ORC_NUM_COUNTERS; ++k) K->r[k] += K->c[k] - before.c[k];
+        K->r[UIVR_ORC_RNG_DRAWS] += clone.draws - d0;
     }
 }
 
@@ -780,10 +784,18 @@ typedef struct {
 
 /* adjoint == 0: primal (result accumulates, envmap added at the end).
  * adjoint == 1: `R` enters as the primal radiance (state_in) and is consumed by path replay. */
+/* test hook: the adjoint takes "radiance still to come" as L - (radiance gathered so far) instead of subtracting
+ * every NEE contribution from a running L (:214).  Same quantity, different rounding; this is the form the CUDA
+ * slot-pool pipeline uses (its adjoint replay gathers L itself).  tests/test_oracle.py bounds the difference. */
+static int g_remaining_by_difference = 0;
+void uivr_oracle_set_remaining_by_difference(int enable) { g_remaining_by_difference = enable; }
+
 static void path_loop(const ctx_t* C, counters_t* K, int adjoint, rng_t* rng, rng_t* alt,
                       path_state_t ps, const float dL[3], float R[3]) {
     const uivr_oracle_scene* sc = C->sc;
     float beta[3] = {1.0f, 1.0f, 1.0f};
+    const float L0[3] = {R[0], R[1], R[2]};
+    float gathered[3] = {0.0f, 0.0f, 0.0f};
     seg_t seg = ps.seg;
     int depth = ps.depth, active = ps.active, escaped = ps.escaped;
     int has_scattered = ps.has_scattered;
@@ -877,6 +889,11 @@ static void path_loop(const ctx_t* C, counters_t* K, int adjoint, rng_t* rng, rn
             float contrib[3];
             nee(C, K, p, beta, rng, adjoint ? dL : NULL, contrib);
             for (int c = 0; c < 3; ++c) R[c] = adjoint ? R[c] - contrib[c] : R[c] + contrib[c];
+            if (adjoint && g_remaining_by_difference)
+                for (int c = 0; c < 3; ++c) {
+                    gathered[c] = gathered[c] + contrib[c];
+                    R[c] = L0[c] - gathered[c];
+                }
         }
 
         /* :221-235 phase sampling (draws masked by did_scatter, not by active) */
@@ -1188,7 +1205,22 @@ typedef struct {
     float* sample_L;
     uint32_t* next_pixel;
     counters_t K;
+    counters_t Kp;     /* backward: the share of K spent in the primal pass (batched.py:255-264) */
 } job_t;
+
+/* Events of the primal pass inside the most recent backward call (included in its `counters`).  The CUDA path's
+ * adjoint replay gathers the primal radiance itself instead of running that pass, so its event counts are those
+ * of the backward minus these -- which is how the parity tests compare them. */
+static uint64_t g_last_backward_primal[UIVR_ORC_NUM_COUNTERS];
+void uivr_oracle_last_backward_primal_counters(uint64_t* out) {
+    memcpy(out, g_last_backward_primal, sizeof(g_last_backward_primal));
+}
+/* ... and of the NEE adjoint's second walk over every shadow segment (:393-401): the CUDA path logs the
+ * tentative collisions of the first walk instead of walking again */
+static uint64_t g_last_backward_replay[UIVR_ORC_NUM_COUNTERS];
+void uivr_oracle_last_backward_replay_counters(uint64_t* out) {
+    memcpy(out, g_last_backward_replay, sizeof(g_last_backward_replay));
+}
 
 static void* worker(void* arg) {
     job_t* J = (job_t*) arg;
@@ -1205,8 +1237,9 @@ static void* worker(void* arg) {
         for (uint32_t s = 0; s < J->spp; ++s) {
             uint32_t idx = pix * J->spp + s;
             float L[3] = {0, 0, 0};
-            if (J->C->nerf) nerf_sample(J->C, &J->K, 0, J->seed, idx, J->spp, NULL, L);
-            else sample_from_camera(J->C, &J->K, 0, J->seed, 0, idx, J->spp, NULL, L);
+            counters_t* Kprimal = J->backward ? &J->Kp : &J->K;
+            if (J->C->nerf) nerf_sample(J->C, Kprimal, 0, J->seed, idx, J->spp, NULL, L);
+            else sample_from_camera(J->C, Kprimal, 0, J->seed, 0, idx, J->spp, NULL, L);
             J->K.c[UIVR_ORC_SAMPLES]++;
             if (J->sample_L) memcpy(J->sample_L + 3 * (size_t) idx, L, sizeof(L));
             if (!J->backward) {
@@ -1273,9 +1306,18 @@ static int run(ctx_t* C, int backward, uint32_t seed, uint32_t spp, const uivr_o
     }
     worker(&jobs[0]);
     for (int i = 1; i < nthreads; ++i) pthread_join(th[i], NULL);
-    if (counters)
-        for (int i = 0; i < nthreads; ++i)
-            for (int k = 0; k < UIVR_ORC_NUM_COUNTERS; ++k) counters[k] += jobs[i].K.c[k];
+    if (backward) {
+        memset(g_last_backward_primal, 0, sizeof(g_last_backward_primal));
+        memset(g_last_backward_replay, 0, sizeof(g_last_backward_replay));
+    }
+    for (int i = 0; i < nthreads; ++i)
+        for (int k = 0; k < UIVR_ORC_NUM_COUNTERS; ++k) {
+            if (counters) counters[k] += jobs[i].K.c[k] + jobs[i].Kp.c[k];
+            if (backward) {
+                g_last_backward_primal[k] += jobs[i].Kp.c[k];
+                g_last_backward_replay[k] += jobs[i].K.r[k];
+            }
+        }
     free(jobs);
     free(th);
     return 0;

@@ -128,6 +128,12 @@ void  uivr_oracle_build_majorant(const float* sigma_t, const int32_t res[3], flo
  * ray direction negative along axis a): lets a walk stop as soon as nothing but empty space is ahead */
 void  uivr_oracle_build_exit_mask(const float* majorant, const int32_t mres[3], uint8_t* out);
 void  uivr_oracle_set_exit_mask(int enable);  /* test hook (default on) */
+void  uivr_oracle_set_remaining_by_difference(int enable);  /* test hook (default off), see path_loop */
+
+/* events of the primal pass inside the most recent backward call (they are part of its `counters`) */
+void  uivr_oracle_last_backward_primal_counters(uint64_t* out);
+/* ... and of the second walk the NEE adjoint makes over every shadow segment (volpathsimple.py:393-401) */
+void  uivr_oracle_last_backward_replay_counters(uint64_t* out);
 
 /* ---- the path ---- */
 /* image_out: H*W*3 (overwritten; pixels outside the shard are zero).

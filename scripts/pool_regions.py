@@ -11,9 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "unbiased-inverse-volume-rendering_b200", "csrc", "uivr_pool.cuh")
 MARKS = [("w-top", "WALKER WARPS:"), ("pickup", "1. idle lanes pick up"), ("w-idle", "const unsigned m_walk ="),
          ("DDA-loop", "for (int it = 1;; ++it)"), ("flush", "3. hand finished lanes on"),
-         ("h-sched+pop", "HANDLER WARPS:"), ("TAP", "if (work == Q_TAP)"), ("VERTEX", "} else if (work == Q_VERTEX"),
+         ("h-sched+pop", "HANDLER WARPS:"), ("TAP", "if (work == Q_TAP)"), ("SCATTER-stage", "} else if (HAS_ADJ && work == Q_SCATTER)"),
+         ("VERTEX", "} else if (work == Q_VERTEX"),
          ("NEE_END", "} else if (work == Q_NEE_END)"), ("PATH_END", "} else if (work == Q_PATH_END)"),
-         ("SPAWN", "} else if (work == Q_SPAWN)"), ("FETCH", "Q_FREE: next work item"),
+         ("FETCH", "Q_FREE: next work item"), ("SPAWN", "one code site: for the batch of"),
          ("scatter", "gradient scatter of the batch"), ("walk-setup", "set-up of a new free-flight walk"),
          ("end", "#undef PU")]
 

@@ -61,6 +61,10 @@ def main():
             out[f"{combo}/dalbedo"] = da
             out[f"{combo}/counters_fwd"] = np.array([cf[k] for k in O.COUNTER_NAMES], dtype=np.uint64)
             out[f"{combo}/counters_bwd"] = np.array([cb[k] for k in O.COUNTER_NAMES], dtype=np.uint64)
+            cp = O.last_backward_primal_counters()   # the share of the primal pass inside the backward
+            out[f"{combo}/counters_bwd_primal"] = np.array([cp[k] for k in O.COUNTER_NAMES], dtype=np.uint64)
+            cr = O.last_backward_replay_counters()   # ... and of the second NEE walks
+            out[f"{combo}/counters_bwd_replay"] = np.array([cr[k] for k in O.COUNTER_NAMES], dtype=np.uint64)
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, "written")
     # integer known answers (KA5)

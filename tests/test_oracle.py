@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import FLAG_COMBOS, hetero_grids, loss_grad
+from helpers import FLAG_COMBOS, hetero_grids, loss_grad, rel_linf
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -276,6 +276,37 @@ def test_ka3_white_furnace(uivr, oracle):
     alb2 = np.full_like(alb, 0.5)
     ds2, _, _, _ = oracle.render_backward(vol.as_dict(), props, sig, alb2, gimg, 6, spp)
     assert np.abs(ds.sum()) < 0.03 * np.abs(ds2.sum())
+
+
+def test_radiance_still_to_come_must_be_subtracted_in_path_order(oracle, uivr):
+    """Why the CUDA adjoint (which gathers L itself instead of running the reference's primal pass first) keeps the
+    reference's ORDER of subtractions (volpathsimple.py:214) when it scatters the vertex gradients afterwards:
+    "L - (gathered so far)" is the same quantity with another rounding, harmless on ordinary media (1e-7), but
+    the free-flight gradient divides by max(albedo, 1e-8) (:159-161), and where a channel's albedo is exactly 0
+    -- the reference's own 3^3 fixture has such a slab -- the radiance still to come is 0 up to rounding and the
+    quotient is that rounding noise times 1e8.  Matching the reference there means matching its rounding."""
+    out = {}
+    for name in ("hetero", "cube3"):
+        if name == "cube3":
+            sig, alb = uivr.cube_test_grids()
+            vol = uivr.cube_test_scene(12, 12, density_scale=2.0)
+        else:
+            sig, alb = hetero_grids(8, seed=2)
+            vol = uivr.cube_test_scene(12, 12, density_scale=4.0, res=(8, 8, 8))
+        props = dict(max_depth=8, use_nee=True, **FLAG_COMBOS["volpathsimple-drt"])
+        img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 7, 8)
+        res = []
+        try:
+            for by_difference in (False, True):
+                oracle.set_remaining_by_difference(by_difference)
+                res.append(oracle.render_backward(vol.as_dict(), props, sig, alb, loss_grad(img), 8, 8, nthreads=1)[:2])
+        finally:
+            oracle.set_remaining_by_difference(False)
+        out[name] = (rel_linf(res[1][0], res[0][0]), rel_linf(res[1][1], res[0][1]))
+    assert out["hetero"][0] < 1e-6 and out["hetero"][1] < 1e-6
+    assert out["cube3"][0] < 1e-6          # sigma_t: the factor albedo / max(albedo, 1e-8) is 0 there
+    assert out["cube3"][1] > 1e-4          # albedo channel with zeros: rounding noise x 1e8
+    assert float(uivr.cube_test_grids()[1].min()) == 0.0
 
 
 # ---------------------------------------------------------------------------------------

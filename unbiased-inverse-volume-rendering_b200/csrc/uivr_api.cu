@@ -33,12 +33,11 @@ struct uivr_ctx {
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
     unsigned int* debug = nullptr;  // [64] watchdog record of the slot-pool kernel
-    // scratch of the split backward pipeline (variant 3): per-sample radiance of the primal replay
-    // and the reservoir records handed from the adjoint launch to the DRT launch
-    float* scratch_L = nullptr;
-    size_t scratch_L_samples = 0;
+    // scratch of the backward pipeline: the reservoir records handed from the adjoint launch to the DRT launch
     uint32_t* records = nullptr;
     size_t records_cap = 0;
+    uint4* desc = nullptr;          // vertex descriptors of the adjoint launch: [SM][slot][max_depth + 1][4]
+    size_t desc_vecs = 0;
     int variant = 3;
     // ray-batch mode (uivr_set_batch)
     bool batch_on = false;
@@ -250,7 +249,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->scratch_L); cudaFree(ctx->records); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -513,7 +512,9 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
         return fail(ctx, UIVR_ERR_INVALID, "ray-batch rendering is not available for use_drt_subsampling = False "
                                            "(the O(n^2) mode runs on the one-sample-per-lane kernels, which generate sensor rays only)");
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
-    if (quadratic || !pool_ok(ctx)) {
+    // (the slot-pool adjoint keeps max_depth + 1 vertex descriptors per in-flight sample: deeper paths than 255
+    // vertices go to the one-sample-per-lane kernels)
+    if (quadratic || !pool_ok(ctx) || ctx->props.max_depth > 255) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);
@@ -522,20 +523,10 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             k_backward_v1<false><<<grid, kBlock, 0, st>>>(P);
         }
     } else {
-        // pipeline: primal replay (forward kernel, radiance per sample to HBM) -> adjoint replay (reservoir
-        // records to HBM) -> DRT pass.  Work counters: [0] primal, [1] adjoint, [2] DRT, [3] records.
+        // pipeline: adjoint replay (gathers the primal radiance itself, scatters the free-flight / transmittance /
+        // NEE gradients, reservoir records to HBM) -> DRT pass.  Work counters: [1] adjoint, [2] DRT, [3] records.
         const bool drt_pass = ctx->props.use_drt != 0;
-        const size_t n_global = (size_t) P.npix * P.spp, n_local = (size_t) P.n_slots * P.spp;
-        if (!P.sample_L) {
-            if (ctx->scratch_L_samples < n_global) {
-                cudaFree(ctx->scratch_L);
-                ctx->scratch_L = nullptr;
-                ctx->scratch_L_samples = 0;
-                UIVR_CUDA(ctx, cudaMalloc(&ctx->scratch_L, n_global * 3 * sizeof(float)));
-                ctx->scratch_L_samples = n_global;
-            }
-            P.sample_L = ctx->scratch_L;
-        }
+        const size_t n_local = (size_t) P.n_slots * P.spp;
         if (drt_pass && ctx->records_cap < n_local) {
             cudaFree(ctx->records);
             ctx->records = nullptr;
@@ -543,14 +534,20 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             UIVR_CUDA(ctx, cudaMalloc(&ctx->records, n_local * kRecWords * sizeof(uint32_t)));
             ctx->records_cap = n_local;
         }
+        const size_t desc_vecs = (size_t) ctx->num_sms * UIVR_POOL_SLOTS_ADJ * (size_t) (ctx->props.max_depth + 1) * kDescVec;
+        if (ctx->desc_vecs < desc_vecs) {
+            cudaFree(ctx->desc);
+            ctx->desc = nullptr;
+            ctx->desc_vecs = 0;
+            UIVR_CUDA(ctx, cudaMalloc(&ctx->desc, desc_vecs * sizeof(uint4)));
+            ctx->desc_vecs = desc_vecs;
+        }
+        P.desc = ctx->desc;
+        P.desc_cap = ctx->props.max_depth + 1;
         P.records = ctx->records;
         P.rec_count = ctx->work_counter + 3;
-        Params PA = P;
-        PA.image = nullptr;
-        if ((rc = launch_pool(ctx->num_sms, KIND_FWD, ctx->counting != 0, PA, st))) return fail(ctx, rc, "pool kernel launch failed");
         P.work_counter = ctx->work_counter + 1;
         if ((rc = launch_pool(ctx->num_sms, KIND_ADJ, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
-        ctx->launches += 1;
         if (drt_pass) {
             P.work_counter = ctx->work_counter + 2;
             if ((rc = launch_pool(ctx->num_sms, KIND_DRT, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");

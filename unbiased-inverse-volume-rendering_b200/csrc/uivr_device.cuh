@@ -70,7 +70,9 @@ struct Params {
     float* dalbedo;           // [Z,Y,X,3]
     unsigned long long* counters;
     unsigned int* work_counter;
-    uint32_t* records;        // split backward: reservoir records (kRecWords words each), adjoint -> DRT launch
+    uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
+    int desc_cap;             // descriptors per slot = max_depth + 1
+    uint32_t* records;        // backward: reservoir records (kRecWords words each), adjoint -> DRT launch
     unsigned int* rec_count;  // number of records appended
     unsigned int* debug;      // [64] watchdog record of the slot-pool kernel (word 0 != 0: tripped)
 };

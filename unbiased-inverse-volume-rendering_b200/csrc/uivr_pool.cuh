@@ -76,6 +76,12 @@ namespace uivr {
 #ifndef UIVR_POOL_WALKER_REGS
 #define UIVR_POOL_WALKER_REGS 56
 #endif
+#ifndef UIVR_POOL_INLINE_SPAWN
+#define UIVR_POOL_INLINE_SPAWN 1   // emitter / phase sampling right after the vertex / NEE-end handler (no queue hop)
+#endif
+#ifndef UIVR_POOL_FOCUS
+#define UIVR_POOL_FOCUS 1          // 1: the handler warps of a CTA prefer to serve the same queue (instruction cache)
+#endif
 #ifndef UIVR_POOL_HANDLERS_LAST
 #define UIVR_POOL_HANDLERS_LAST 0   // 1: the handler warps are the LAST warps of the CTA (scheduler priority A/B)
 #endif
@@ -99,6 +105,9 @@ constexpr int kPoolWalkLimit = 1 << 24;          // watchdog: iterations of one 
 constexpr long long kPoolIdleLimit = 4000000000ll;  // watchdog: cycles without any progress of a warp
 
 enum : int { Q_FREE = 0, Q_WALK, Q_TAP, Q_VERTEX, Q_VERTEX_ADJ, Q_SPAWN, Q_NEE_END, Q_PATH_END, Q_NUM };
+// KIND_ADJ only: a finished path waits here while its deferred gradient scatter runs, one vertex per visit (the
+// adjoint kernel has no plain Q_VERTEX traffic: all its vertices go through Q_VERTEX_ADJ)
+constexpr int Q_SCATTER = Q_VERTEX;
 enum : int { PM_DELTA = 0, PM_NEE, PM_NEE_ADJ, PM_DRT };
 enum : int { PP_PRIMAL = 0, PP_ADJ, PP_DRTV, PP_REC };
 
@@ -156,6 +165,7 @@ struct PoolCtl {
     int live;        // slots that may still carry work
     int exhausted;   // the global sample queue is empty
     int abort;       // watchdog tripped: every warp leaves
+    int focus;       // (UIVR_POOL_FOCUS) queue the handler warps currently prefer
 };
 
 // One decision of the supergrid DDA: the axis whose boundary the ray crosses first (ties: x before y before z, as
@@ -205,6 +215,13 @@ __device__ __noinline__ void pool_trip(PoolCtl* ctl, unsigned* debug, unsigned w
 // < 15 % of the HBM roofline) for three lean kernels with fewer live modes each.
 enum : int { KIND_FWD = 0, KIND_ADJ = 2, KIND_DRT = 3 };
 constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) alt seq(1) depth(1) pad(2)
+// Vertex descriptor of the adjoint kernel (4 x uint4, global memory, one area of max_depth + 1 descriptors per
+// slot): what the free-flight (:152-172) and transmittance (:181-189) gradients of one path segment need apart from
+// the radiance that is still to come -- which is only known when the path has ended.
+//   {alt state lo, hi, sigma_t at the collision (0: the segment escaped), interval} {o.xyz, d.x} {d.yz, c.xy}
+//   {c.z, albedo.xyz}    c = contribution of the next-event estimation that follows this vertex (written by the
+//                        NEE handler; 0 without one): what the reference subtracts from L after the vertex (:214)
+constexpr int kDescVec = 4;
 
 // ENV (envmap emitter, uivr_env.cuh): three more fields per slot hold the NEE weight
 // throughput * phase * mis * Le / pdf of the direction sampled at Q_SPAWN until Q_NEE_END
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         ctl->tail[threadIdx.x] = threadIdx.x == Q_FREE ? (unsigned) NSLOT : 0u;
         ctl->count[threadIdx.x] = threadIdx.x == Q_FREE ? NSLOT : 0;
     }
-    if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; }
+    if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; ctl->focus = Q_FREE; }
     __syncthreads();
 
     // ---- queue primitives (warp-collective; each is instantiated ONCE per role to keep the code small) ----
@@ -524,6 +541,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
                 best = __shfl_sync(FULL, best, 0);
+#if UIVR_POOL_FOCUS
+                const int focus = __shfl_sync(FULL, *((volatile int*) &ctl->focus), 0) & 7;
+                if (__shfl_sync(FULL, cnt, focus) >= 32) {
+                    work = focus;
+                } else if ((best >> 3) >= 32) {
+                    work = best & 7;
+                    if (lane == 0) ctl->focus = work;
+                } else
+#endif
                 if (c_last >= 32) {
                     work = last_work;
                 } else if ((best >> 3) >= min_batch) {
@@ -548,6 +574,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             // per-lane result of the work item: slot `s` goes to queue `next` (-1: nothing to route)
             unsigned s = 0;
             int next = -1;
+            bool resume = false;  // next == Q_WALK continues a walk after a null collision (no set-up)
             // gradient scatter request of the handlers (executed at one site below)
             bool sc_taps = false, sc_ff = false;
             float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
@@ -622,12 +649,59 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (go_on) {
                         CSET(C_TAU, s, neg_log1m(draw(r, K)));
                         next = Q_WALK;  // the walker resumes in the same cell
+                        resume = true;
                     } else {
                         next = (int) ((fl & FL_ENDQ_MASK) >> FL_ENDQ_SHIFT);
                     }
                     PU(F_RNG_LO, s) = (uint32_t) r.state;
                     PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
                     PU(F_FLAGS, s) = fl;
+                }
+            } else if (HAS_ADJ && work == Q_SCATTER) {
+                // ---- deferred gradients of one described vertex of a finished path (see the vertex handler) ----
+                if (act) {
+                    // vertices in path order: F_R holds L minus the NEE contributions of the vertices before this one,
+                    // subtracted one by one exactly like the reference's replay does (:214)
+                    const unsigned tw = PU(F_TS, s), k = tw & 0xFFFFu, n_desc = tw >> 16;
+                    PU(F_TS, s) = tw + 1u;
+                    const uint4* dsc = P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + k) * kDescVec;
+                    const uint4 d0 = __ldcg(dsc + 0), d1 = __ldcg(dsc + 1), d2 = __ldcg(dsc + 2), d3 = __ldcg(dsc + 3);
+                    alt.state = (uint64_t) d0.x | ((uint64_t) d0.y << 32);
+                    alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
+                    const float st = __uint_as_float(d0.z);
+                    const bool ds = d0.z != 0u;
+                    sc_int = __uint_as_float(d0.w);
+                    sc_ox = __uint_as_float(d1.x); sc_oy = __uint_as_float(d1.y); sc_oz = __uint_as_float(d1.z);
+                    sc_dx = __uint_as_float(d1.w); sc_dy = __uint_as_float(d2.x); sc_dz = __uint_as_float(d2.y);
+                    const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
+                    const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
+                    PSET(F_R0, s, R[0] - __uint_as_float(d2.z));
+                    PSET(F_R1, s, R[1] - __uint_as_float(d2.w));
+                    PSET(F_R2, s, R[2] - __uint_as_float(d3.x));
+                    const float albedo[3] = {__uint_as_float(d3.y), __uint_as_float(d3.z), __uint_as_float(d3.w)};
+                    next = k + 1u < n_desc ? Q_SCATTER : Q_FREE;
+                    // :152-172 free-flight scattering gradient
+                    if ((!P.use_drt || P.use_drt_mis) && ds) {
+                        float m = 1.0f;
+                        if (P.use_drt && P.use_drt_mis) {
+                            const float s2 = st * st;
+                            m = s2 / (1.0f + s2);
+                        }
+                        const float inv_pdf = 1.0f / st;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float Li = R[c] / (albedo[c] > 1e-8f ? albedo[c] : 1e-8f);
+                            const float term = ((m * dL[c]) * Li) * inv_pdf;
+                            sc_gs = fmaf(term, albedo[c], sc_gs);
+                            sc_ga[c] = term * st;
+                        }
+                        sc_ff = true;
+                        sc_vx = fmaf(sc_int, sc_dx, sc_ox); sc_vy = fmaf(sc_int, sc_dy, sc_oy); sc_vz = fmaf(sc_int, sc_dz, sc_oz);
+                    }
+                    // :181-189, :584-607 transmittance gradient: 4 uniform taps on the segment
+                    const float aw = fmaf(dL[2], R[2], fmaf(dL[1], R[1], dL[0] * R[0]));
+                    sc_g = -(aw * (sc_int * 0.25f));
+                    sc_taps = true;
                 }
             } else if (work == Q_VERTEX || work == Q_VERTEX_ADJ) {
                 // ---- end of a delta-tracking segment (:130-245) or of the DRT walk (:550-558) ----
@@ -672,8 +746,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         if (HAS_ADJ && pass == PP_ADJ) {
                             alt.state = (uint64_t) PU(F_ALT_LO, s) | ((uint64_t) PU(F_ALT_HI, s) << 32);
                             alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
-                            const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
-                            const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
                             const float st = PF(F_ST, s);
                             if (use_rsv) {
                                 // DRTReservoir.update (:745-753), weight = throughput before this vertex
@@ -695,30 +767,25 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                     fl |= FL_RS_VALID;
                                 }
                             }
-                            // :152-172 free-flight scattering gradient
-                            if ((!P.use_drt || P.use_drt_mis) && ds) {
-                                float m = 1.0f;
-                                if (P.use_drt && P.use_drt_mis) {
-                                    const float s2 = st * st;
-                                    m = s2 / (1.0f + s2);
-                                }
-                                const float inv_pdf = 1.0f / st;
-#pragma unroll
-                                for (int c = 0; c < 3; ++c) {
-                                    const float Li = R[c] / (albedo[c] > 1e-8f ? albedo[c] : 1e-8f);
-                                    const float term = ((m * dL[c]) * Li) * inv_pdf;
-                                    sc_gs = fmaf(term, albedo[c], sc_gs);
-                                    sc_ga[c] = term * st;
-                                }
-                                sc_ff = true;
-                                sc_vx = vx; sc_vy = vy; sc_vz = vz;
+                            // The free-flight (:152-172) and transmittance (:181-189) gradients of this segment need
+                            // the radiance the path gathers from here on, Li = L - (what was gathered before).  The
+                            // reference gets L from a separate primal pass (batched.py:255-264) and subtracts as it
+                            // replays; here the replay itself gathers L, so the vertex is only DESCRIBED now and its
+                            // gradients are scattered when the path has ended (Q_SCATTER): no primal replay launch.
+                            {
+                                uint4* dsc = P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + depth) * kDescVec;
+                                __stcg(dsc + 0, make_uint4((uint32_t) alt.state, (uint32_t) (alt.state >> 32),
+                                                           ds ? __float_as_uint(st) : 0u, __float_as_uint(ds ? swt : stmax)));
+                                __stcg(dsc + 1, make_uint4(__float_as_uint(sox), __float_as_uint(soy), __float_as_uint(soz),
+                                                           __float_as_uint(sdx)));
+                                __stcg(dsc + 2, make_uint4(__float_as_uint(sdy), __float_as_uint(sdz), 0u, 0u));
+                                __stcg(dsc + 3, make_uint4(0u, __float_as_uint(albedo[0]), __float_as_uint(albedo[1]),
+                                                           __float_as_uint(albedo[2])));
+                                // the four tap positions are drawn from the alt stream when the gradients are scattered
+                                alt.next(); alt.next(); alt.next(); alt.next();
+                                PU(F_ALT_LO, s) = (uint32_t) alt.state;
+                                PU(F_ALT_HI, s) = (uint32_t) (alt.state >> 32);
                             }
-                            // :181-189, :584-607 transmittance gradient: 4 uniform taps on the segment
-                            sc_int = ds ? swt : stmax;
-                            const float aw = fmaf(dL[2], R[2], fmaf(dL[1], R[1], dL[0] * R[0]));
-                            sc_g = -(aw * (sc_int * 0.25f));
-                            sc_ox = sox; sc_oy = soy; sc_oz = soz; sc_dx = sdx; sc_dy = sdy; sc_dz = sdz;
-                            sc_taps = true;
                         }
                         // :193-200
                         if (ds) {
@@ -760,9 +827,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (HAS_DRT && pass == PP_DRTV) {
                         PSET(F_LI0, s, contrib[0]); PSET(F_LI1, s, contrib[1]); PSET(F_LI2, s, contrib[2]);
                     } else if (HAS_ADJ && pass == PP_ADJ) {
-                        PSET(F_R0, s, PF(F_R0, s) - contrib[0]);  // path replay (:214)
-                        PSET(F_R1, s, PF(F_R1, s) - contrib[1]);
-                        PSET(F_R2, s, PF(F_R2, s) - contrib[2]);
+                        PSET(F_R0, s, PF(F_R0, s) + contrib[0]);  // gathered like the primal pass; :214 subtracts it from L
+                        PSET(F_R1, s, PF(F_R1, s) + contrib[1]);  // instead, which Q_SCATTER does in the same order
+                        PSET(F_R2, s, PF(F_R2, s) + contrib[2]);
+                        {
+                            const unsigned k = (PU(F_DEPTH, s) & 0xFFFFu) - 1u;  // the vertex this NEE belongs to
+                            float* c = reinterpret_cast<float*>(P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + k) * kDescVec) + 10;
+                            __stcg(c + 0, contrib[0]); __stcg(c + 1, contrib[1]); __stcg(c + 2, contrib[2]);
+                        }
                         if (fl & FL_NEE_VALID) {
                             const float a = (PF(F_DL0, s) * contrib[0] + PF(F_DL1, s) * contrib[1]) + PF(F_DL2, s) * contrib[2];
                             PSET(F_ASUM, s, a);
@@ -781,13 +853,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 }
             } else if (work == Q_PATH_END) {
                 bool want_rec = false;
+                float wdl[3] = {0.0f, 0.0f, 0.0f};  // reservoir weight * dL: the adjoint handed to the DRT pass
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
                     const int pass = (int) (fl & FL_PASS_MASK);
                     const unsigned dw = PU(F_DEPTH, s);
                     const int depth = (int) (dw & 0xFFFFu);
                     float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
-                    if (pass == PP_PRIMAL || (HAS_DRT && pass == PP_REC)) {
+                    if (pass == PP_PRIMAL || (HAS_DRT && pass == PP_REC) || (HAS_ADJ && pass == PP_ADJ)) {
                         // :263-285 envmap
                         if ((fl & FL_ESCAPED) && !(depth <= 0 && P.hide_emitters)) {
                             if (ENV) {
@@ -820,6 +893,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
                         }
                     } else if (HAS_ADJ && pass == PP_ADJ) {
+                        // R is now the primal radiance L of this sample (state_in of sample(Backward), batched.py:309-318)
+                        if (P.sample_L) {
+                            const uint32_t idx = PU(F_IDX, s);
+                            P.sample_L[3 * (size_t) idx + 0] = R[0];
+                            P.sample_L[3 * (size_t) idx + 1] = R[1];
+                            P.sample_L[3 * (size_t) idx + 2] = R[2];
+                        }
                         if (use_rsv && (fl & FL_RS_VALID)) {
                             // DRTReservoir.get (:756-760) and adjoint = weight * dL (:255)
                             const float wcur[3] = {PF(F_RSC0, s), PF(F_RSC1, s), PF(F_RSC2, s)};
@@ -828,9 +908,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
                                 const float W = (d != 0.0f) ? (ws * wcur[c]) / d : 0.0f;
-                                PSET(F_DL0 + c, s, W * PF(F_DL0 + c, s));
+                                wdl[c] = W * PF(F_DL0 + c, s);
                             }
                             want_rec = true;  // the DRT pass is a separate launch: hand the sample over through HBM
+                        }
+                        // deferred gradient scatter: one descriptor per segment end (every real collision, + the escape)
+                        const unsigned n_desc = (unsigned) depth + ((fl & FL_ESCAPED) ? 1u : 0u);
+                        if (n_desc) {
+                            PSET(F_R0, s, R[0]); PSET(F_R1, s, R[1]); PSET(F_R2, s, R[2]);
+                            PU(F_TS, s) = n_desc << 16;  // next vertex to scatter (low half) of n_desc (high half)
+                            next = Q_SCATTER;
                         }
                     } else if (HAS_DRT) {  // PP_REC: Li complete -> DRT gradient (:571-581)
                         const float dst = PF(F_DRT_ST, s), dD = PF(F_DRT_D, s), dt = PF(F_DRT_T, s);
@@ -861,15 +948,150 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             uint32_t* rec = P.records + (size_t) (base + __popc(m & lt_mask)) * kRecWords;
                             uint4* r4 = reinterpret_cast<uint4*>(rec);
                             r4[0] = make_uint4(PU(F_RSOX, s), PU(F_RSOY, s), PU(F_RSOZ, s), PU(F_RSDX, s));
-                            r4[1] = make_uint4(PU(F_RSDY, s), PU(F_RSDZ, s), PU(F_RSTMAX, s), PU(F_DL0, s));
-                            r4[2] = make_uint4(PU(F_DL1, s), PU(F_DL2, s), PU(F_ALT_LO, s), PU(F_ALT_HI, s));
+                            r4[1] = make_uint4(PU(F_RSDY, s), PU(F_RSDZ, s), PU(F_RSTMAX, s), __float_as_uint(wdl[0]));
+                            r4[2] = make_uint4(__float_as_uint(wdl[1]), __float_as_uint(wdl[2]), PU(F_ALT_LO, s), PU(F_ALT_HI, s));
                             r4[3] = make_uint4(PU(F_ASEQ, s), PU(F_DEPTH, s) >> 16, 0u, 0u);
                         }
                     }
                 }
-            } else if (work == Q_SPAWN) {
-                // ---- emitter sampling (:406-433) / phase sampling (:221-245, :626-652) ----
-                if (act) {
+            } else if (work == Q_FREE) {
+                // ---- Q_FREE: next work item from the global queue ----
+                bool none_left = true;
+                const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
+                const unsigned fresh = __ballot_sync(FULL, act);
+                uint64_t item = 0;
+                bool mine = false;
+                if (exh == 0 && fresh) {
+                    const int leader = __ffs(fresh) - 1;
+                    unsigned base = 0;
+                    if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
+                    base = __shfl_sync(FULL, base, leader);
+                    item = (uint64_t) base + __popc(fresh & lt_mask);
+                    mine = act && item < total;
+                    if (mine) none_left = false;
+                    if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
+                }
+                // no more work items: the slot retires
+                const unsigned retire = __ballot_sync(FULL, act && none_left);
+                if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
+                if (KIND == KIND_DRT) {
+                    // DRT launch: the work items are the reservoir records of the adjoint launch
+                    if (mine) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(P.records + (size_t) item * kRecWords);
+                        const uint4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+                        // DRT on the stored segment (:543-581): the walk draws from the alt stream
+                        PU(F_OX, s) = a.x; PU(F_OY, s) = a.y; PU(F_OZ, s) = a.z; PU(F_DX, s) = a.w;
+                        PU(F_DY, s) = b.x; PU(F_DZ, s) = b.y; CU(C_TMAX, s) = b.z;
+                        PU(F_RSOX, s) = a.x; PU(F_RSOY, s) = a.y; PU(F_RSOZ, s) = a.z; PU(F_RSDX, s) = a.w;
+                        PU(F_RSDY, s) = b.x; PU(F_RSDZ, s) = b.y;
+                        PU(F_DL0, s) = b.w; PU(F_DL1, s) = c.x; PU(F_DL2, s) = c.y;
+                        PU(F_RNG_LO, s) = c.z; PU(F_RNG_HI, s) = c.w; PU(F_SEQ, s) = d.x;
+                        PU(F_DEPTH, s) = d.y;
+                        PU(F_FLAGS, s) = (unsigned) PP_ADJ | ((unsigned) PM_DRT << FL_MODE_SHIFT);
+                        next = Q_WALK;
+                    }
+                } else {
+                    // ray generation + reach_medium (batched.py:426-467, volpathsimple.py:292-319)
+                    uint32_t idx = 0, pix = 0;
+                    bool have = false;
+                    if (mine) {
+                        const uint32_t it = (uint32_t) item;
+                        if (slot_to_pixel(P, it / P.spp, pix)) {
+                            idx = pix * P.spp + it % P.spp;
+                            have = true;
+                            K.add(C_SAMPLES, 1);
+                        } else {
+                            next = Q_FREE;  // padding slot of a shard: try again
+                        }
+                    }
+                    if (have) {
+                        const int pass = KIND == KIND_ADJ ? PP_ADJ : PP_PRIMAL;
+                        Rng r;
+                        r.state = r.inc = 0;
+#pragma unroll 1
+                        for (int k = HAS_ADJ ? 1 : 0; k >= 0; --k) {  // sampler.seed(seed, wavefront) [+ the alt sampler, :100-107]
+                            pool_seed_sampler(r, k ? P.alt_seed : P.seed, idx);
+                            if (k) {
+                                PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
+                                PU(F_ASEQ, s) = (uint32_t) (r.inc >> 1);
+                            }
+                        }
+                        if (HAS_ADJ) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                PSET(F_DL0 + c, s, ldg_tap(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
+                                PSET(F_RSW0 + c, s, 0.0f);
+                                PSET(F_RSC0 + c, s, 0.0f);
+                                PSET(F_R0 + c, s, 0.0f);  // the replay gathers the primal radiance itself
+                            }
+                        } else {
+                            PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
+                        }
+                        Seg sg;
+                        float F[15], fu, fv;
+                        if (P.sensors) {
+                            // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
+                            batch_film_position(P, pix, idx, F, fu, fv);
+                        } else {
+                            const float jx = draw(r, K), jy = draw(r, K);
+                            sensor_film_position(P, pix, jx, jy, F, fu, fv);
+                        }
+                        const int status = camera_segment_frame(P, F, fu, fv, sg);
+                        draw(r, K);  // :71
+                        const bool active = status == 1;
+                        const bool escaped = status == 0;
+                        unsigned fl = (unsigned) pass | ((unsigned) PM_DELTA << FL_MODE_SHIFT) | (escaped ? FL_ESCAPED : 0u) |
+                                      (active ? FL_ACTIVE : 0u);
+                        if (active) {
+                            draw(r, K);  // :99 alt_seed_rnd
+                            K.add(C_HITS, 1);
+                            draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
+                            PU(F_IDX, s) = idx;
+                            PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
+                            PU(F_SEQ, s) = (uint32_t) (r.inc >> 1);
+                            PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
+                            PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
+                            CSET(C_TMAX, s, sg.tmax);
+                            PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
+                            PU(F_DEPTH, s) = 0u;
+                            next = Q_WALK;
+                        } else {
+                            {
+                                // the ray misses the medium: finish the sample right here (no gradient)
+                                float R[3] = {0.0f, 0.0f, 0.0f};
+                                if (escaped && !P.hide_emitters) {
+                                    if (ENV) {
+                                        float pdf;
+                                        env_eval(P, sg.dx, sg.dy, sg.dz, R, pdf);  // no scattering: MIS weight 1
+                                    } else {
+#pragma unroll
+                                        for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
+                                    }
+                                }
+                                if (P.sample_L) {
+                                    P.sample_L[3 * (size_t) idx + 0] = R[0];
+                                    P.sample_L[3 * (size_t) idx + 1] = R[1];
+                                    P.sample_L[3 * (size_t) idx + 2] = R[2];
+                                }
+                                if (P.image) {
+                                    atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
+                                    atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
+                                    atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
+                                }
+                            }
+                            fl = 0u;
+                            next = Q_FREE;
+                        }
+                        PU(F_FLAGS, s) = fl;
+                    }
+                }
+            }
+
+            // ---- emitter sampling (:406-433) / phase sampling (:221-245, :626-652), one code site: for the batch of
+            //      Q_SPAWN itself (end of a NEE-adjoint replay walk) and, without a queue hop in between, for the slots a
+            //      vertex or NEE-end handler has just sent on to it ----
+            if (__ballot_sync(FULL, act && (work == Q_SPAWN || (UIVR_POOL_INLINE_SPAWN && next == Q_SPAWN)))) {
+                if (act && (work == Q_SPAWN || (UIVR_POOL_INLINE_SPAWN && next == Q_SPAWN))) {
                     unsigned fl = PU(F_FLAGS, s);
                     const bool phase = (fl & FL_SPAWN_PHASE) != 0u;
                     Rng r;
@@ -937,138 +1159,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
                     PU(F_FLAGS, s) = fl;
                 }
-            } else {
-                // ---- Q_FREE: next work item from the global queue ----
-                bool none_left = true;
-                const int exh = __shfl_sync(FULL, *((volatile int*) &ctl->exhausted), 0);
-                const unsigned fresh = __ballot_sync(FULL, act);
-                uint64_t item = 0;
-                bool mine = false;
-                if (exh == 0 && fresh) {
-                    const int leader = __ffs(fresh) - 1;
-                    unsigned base = 0;
-                    if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
-                    base = __shfl_sync(FULL, base, leader);
-                    item = (uint64_t) base + __popc(fresh & lt_mask);
-                    mine = act && item < total;
-                    if (mine) none_left = false;
-                    if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
-                }
-                // no more work items: the slot retires
-                const unsigned retire = __ballot_sync(FULL, act && none_left);
-                if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
-                if (KIND == KIND_DRT) {
-                    // DRT launch: the work items are the reservoir records of the adjoint launch
-                    if (mine) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(P.records + (size_t) item * kRecWords);
-                        const uint4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
-                        // DRT on the stored segment (:543-581): the walk draws from the alt stream
-                        PU(F_OX, s) = a.x; PU(F_OY, s) = a.y; PU(F_OZ, s) = a.z; PU(F_DX, s) = a.w;
-                        PU(F_DY, s) = b.x; PU(F_DZ, s) = b.y; CU(C_TMAX, s) = b.z;
-                        PU(F_RSOX, s) = a.x; PU(F_RSOY, s) = a.y; PU(F_RSOZ, s) = a.z; PU(F_RSDX, s) = a.w;
-                        PU(F_RSDY, s) = b.x; PU(F_RSDZ, s) = b.y;
-                        PU(F_DL0, s) = b.w; PU(F_DL1, s) = c.x; PU(F_DL2, s) = c.y;
-                        PU(F_RNG_LO, s) = c.z; PU(F_RNG_HI, s) = c.w; PU(F_SEQ, s) = d.x;
-                        PU(F_DEPTH, s) = d.y;
-                        PU(F_FLAGS, s) = (unsigned) PP_ADJ | ((unsigned) PM_DRT << FL_MODE_SHIFT);
-                        next = Q_WALK;
-                    }
-                } else {
-                    // ray generation + reach_medium (batched.py:426-467, volpathsimple.py:292-319)
-                    uint32_t idx = 0, pix = 0;
-                    bool have = false;
-                    if (mine) {
-                        const uint32_t it = (uint32_t) item;
-                        if (slot_to_pixel(P, it / P.spp, pix)) {
-                            idx = pix * P.spp + it % P.spp;
-                            have = true;
-                            if (KIND == KIND_FWD) K.add(C_SAMPLES, 1);
-                        } else {
-                            next = Q_FREE;  // padding slot of a shard: try again
-                        }
-                    }
-                    if (have) {
-                        const int pass = KIND == KIND_ADJ ? PP_ADJ : PP_PRIMAL;
-                        Rng r;
-                        r.state = r.inc = 0;
-#pragma unroll 1
-                        for (int k = HAS_ADJ ? 1 : 0; k >= 0; --k) {  // sampler.seed(seed, wavefront) [+ the alt sampler, :100-107]
-                            pool_seed_sampler(r, k ? P.alt_seed : P.seed, idx);
-                            if (k) {
-                                PU(F_ALT_LO, s) = (uint32_t) r.state; PU(F_ALT_HI, s) = (uint32_t) (r.state >> 32);
-                                PU(F_ASEQ, s) = (uint32_t) (r.inc >> 1);
-                            }
-                        }
-                        if (HAS_ADJ) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                PSET(F_DL0 + c, s, ldg_tap(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
-                                PSET(F_RSW0 + c, s, 0.0f);
-                                PSET(F_RSC0 + c, s, 0.0f);
-                                // state_in = radiance of the primal replay launch (batched.py:255-264)
-                                PSET(F_R0 + c, s, __ldcs(P.sample_L + 3 * (size_t) idx + c));
-                            }
-                        } else {
-                            PSET(F_R0, s, 0.0f); PSET(F_R1, s, 0.0f); PSET(F_R2, s, 0.0f);
-                        }
-                        Seg sg;
-                        float F[15], fu, fv;
-                        if (P.sensors) {
-                            // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
-                            batch_film_position(P, pix, idx, F, fu, fv);
-                        } else {
-                            const float jx = draw(r, K), jy = draw(r, K);
-                            sensor_film_position(P, pix, jx, jy, F, fu, fv);
-                        }
-                        const int status = camera_segment_frame(P, F, fu, fv, sg);
-                        draw(r, K);  // :71
-                        const bool active = status == 1;
-                        const bool escaped = status == 0;
-                        unsigned fl = (unsigned) pass | ((unsigned) PM_DELTA << FL_MODE_SHIFT) | (escaped ? FL_ESCAPED : 0u) |
-                                      (active ? FL_ACTIVE : 0u);
-                        if (active) {
-                            draw(r, K);  // :99 alt_seed_rnd
-                            if (pass == PP_PRIMAL) K.add(C_HITS, 1);
-                            draw(r, K);  // :120 Russian-roulette draw of the first loop iteration
-                            PU(F_IDX, s) = idx;
-                            PU(F_RNG_LO, s) = (uint32_t) r.state; PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
-                            PU(F_SEQ, s) = (uint32_t) (r.inc >> 1);
-                            PSET(F_OX, s, sg.ox); PSET(F_OY, s, sg.oy); PSET(F_OZ, s, sg.oz);
-                            PSET(F_DX, s, sg.dx); PSET(F_DY, s, sg.dy); PSET(F_DZ, s, sg.dz);
-                            CSET(C_TMAX, s, sg.tmax);
-                            PSET(F_B0, s, 1.0f); PSET(F_B1, s, 1.0f); PSET(F_B2, s, 1.0f);
-                            PU(F_DEPTH, s) = 0u;
-                            next = Q_WALK;
-                        } else {
-                            if (pass == PP_PRIMAL) {
-                                // the ray misses the medium: finish the sample right here
-                                float R[3] = {0.0f, 0.0f, 0.0f};
-                                if (escaped && !P.hide_emitters) {
-                                    if (ENV) {
-                                        float pdf;
-                                        env_eval(P, sg.dx, sg.dy, sg.dz, R, pdf);  // no scattering: MIS weight 1
-                                    } else {
-#pragma unroll
-                                        for (int c = 0; c < 3; ++c) R[c] = fmaf(1.0f, P.radiance[c], 0.0f);
-                                    }
-                                }
-                                if (P.sample_L) {
-                                    P.sample_L[3 * (size_t) idx + 0] = R[0];
-                                    P.sample_L[3 * (size_t) idx + 1] = R[1];
-                                    P.sample_L[3 * (size_t) idx + 2] = R[2];
-                                }
-                                if (P.image) {
-                                    atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
-                                    atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
-                                    atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
-                                }
-                            }
-                            fl = 0u;
-                            next = Q_FREE;
-                        }
-                        PU(F_FLAGS, s) = fl;
-                    }
-                }
             }
 
             // ---- gradient scatter of the batch (one code site): 4 transmittance taps, then the
@@ -1092,16 +1182,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                     }
                 }
-                if (sc_taps) {
-                    PU(F_ALT_LO, s) = (uint32_t) alt.state;
-                    PU(F_ALT_HI, s) = (uint32_t) (alt.state >> 32);
-                }
             }
 
             // ---- set-up of a new free-flight walk (one code site; Medium::sample_interaction set-up, App. B.5):
             //      first cell, next-boundary times and their increments, the first optical depth tau ----
-            if (work != Q_TAP && __ballot_sync(FULL, next == Q_WALK)) {
-                if (next == Q_WALK) {
+            if (__ballot_sync(FULL, next == Q_WALK && !resume)) {
+                if (next == Q_WALK && !resume) {
                     const float ox = PF(F_OX, s), oy = PF(F_OY, s), oz = PF(F_OZ, s);
                     const float dx = PF(F_DX, s), dy = PF(F_DY, s), dz = PF(F_DZ, s);
                     const float ix = dx != 0.0f ? 1.0f / dx : UIVR_INF;
