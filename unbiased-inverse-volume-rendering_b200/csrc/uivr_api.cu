@@ -38,6 +38,7 @@ struct uivr_ctx {
     size_t records_cap = 0;
     uint4* desc = nullptr;          // vertex descriptors of the adjoint launch: [SM][slot][max_depth + 1][4]
     size_t desc_vecs = 0;
+    float2* neelog = nullptr;       // NEE collision log of the adjoint launch: [SM][slot][kNeeLog]
     int variant = 3;
     // ray-batch mode (uivr_set_batch)
     bool batch_on = false;
@@ -249,7 +250,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->neelog); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -542,8 +543,11 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             UIVR_CUDA(ctx, cudaMalloc(&ctx->desc, desc_vecs * sizeof(uint4)));
             ctx->desc_vecs = desc_vecs;
         }
+        if (!ctx->neelog)
+            UIVR_CUDA(ctx, cudaMalloc(&ctx->neelog, (size_t) ctx->num_sms * UIVR_POOL_SLOTS_ADJ * kNeeLog * sizeof(float2)));
         P.desc = ctx->desc;
         P.desc_cap = ctx->props.max_depth + 1;
+        P.neelog = ctx->neelog;
         P.records = ctx->records;
         P.rec_count = ctx->work_counter + 3;
         P.work_counter = ctx->work_counter + 1;

@@ -72,6 +72,7 @@ struct Params {
     unsigned int* work_counter;
     uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
     int desc_cap;             // descriptors per slot = max_depth + 1
+    float2* neelog;           // adjoint launch: NEE collision log, [CTA][slot][kNeeLog] (t, sigma_n)
     uint32_t* records;        // backward: reservoir records (kRecWords words each), adjoint -> DRT launch
     unsigned int* rec_count;  // number of records appended
     unsigned int* debug;      // [64] watchdog record of the slot-pool kernel (word 0 != 0: tripped)

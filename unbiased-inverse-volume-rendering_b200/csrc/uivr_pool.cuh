@@ -134,7 +134,8 @@ enum : int {
     // aliases
     F_ST = F_TS, F_T = F_TS, F_ASUM = F_TS,
     F_LI0 = F_RSW0, F_LI1 = F_RSW1, F_LI2 = F_RSW2, F_AL0 = F_RSC0, F_AL1 = F_RSC1, F_AL2 = F_RSC2,
-    F_T2 = F_CLONE_LO, F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI
+    F_T2 = F_CLONE_LO, F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI,
+    F_NLOG = F_DRT_ST   // adjoint kernel: tentative collisions of the current NEE walk (F_DRT_ST lives in the DRT kernel)
 };
 
 // The CONTINUATION of the free-flight walk is a 12-word record per slot (array of structures, 48 bytes): a
@@ -222,6 +223,12 @@ constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) a
 //   {c.z, albedo.xyz}    c = contribution of the next-event estimation that follows this vertex (written by the
 //                        NEE handler; 0 without one): what the reference subtracts from L after the vertex (:214)
 constexpr int kDescVec = 4;
+// NEE adjoint (volpathsimple.py:393-401, :483-492): the reference walks every shadow segment a second time, from a
+// cloned sampler, to scatter -sum(adjoint)/sigma_n at each tentative collision once the contribution is known.
+// The adjoint kernel instead LOGS the tentative collisions of the first walk (t, sigma_n; kNeeLog per slot, global
+// memory) and scatters from the log at the NEE end: same positions, same values, no second walk.  A shadow walk
+// with more collisions than the log holds falls back to the replay walk.
+constexpr int kNeeLog = 32;
 
 // ENV (envmap emitter, uivr_env.cuh): three more fields per slot hold the NEE weight
 // throughput * phase * mis * Le / pdf of the direction sampled at Q_SPAWN until Q_NEE_END
@@ -580,6 +587,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
             float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
             float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
+            unsigned nee_n = 0u;  // NEE end: logged tentative collisions of the shadow walk to scatter, weight nee_a
+            float nee_a = 0.0f;
             Rng alt;
             alt.state = alt.inc = 0;
             // ==========================================================================
@@ -637,9 +646,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 fl |= FL_DRT_FOUND;
                             }
                         } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
-                            // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)
+                            // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)   [replay walk: log overflow only]
                             scatter_sigma(P, px, py, pz, -PF(F_ASUM, s) / sn);
                             K.add(C_SSCAT, 1);
+                        } else if (HAS_ADJ && mode == PM_NEE && q > 0.0f) {
+                            // log the collision for the NEE adjoint (scattered at the NEE end, when its weight is known)
+                            const unsigned nl = PU(F_NLOG, s);
+                            if (nl < (unsigned) kNeeLog)
+                                __stcg(P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLog + nl, make_float2(wt, sn));
+                            PU(F_NLOG, s) = nl + 1u;
                         }
                         // ratio tracking (:461-502) / running transmittance of the DRT walk
                         T *= q;
@@ -837,11 +852,18 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                         if (fl & FL_NEE_VALID) {
                             const float a = (PF(F_DL0, s) * contrib[0] + PF(F_DL1, s) * contrib[1]) + PF(F_DL2, s) * contrib[2];
-                            PSET(F_ASUM, s, a);
-                            PU(F_RNG_LO, s) = PU(F_CLONE_LO, s);  // the replay consumes exactly the same draws again
-                            PU(F_RNG_HI, s) = PU(F_CLONE_HI, s);
-                            fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE_ADJ << FL_MODE_SHIFT);
-                            next = Q_WALK;
+                            nee_n = PU(F_NLOG, s);
+                            if (nee_n > (unsigned) kNeeLog) {
+                                // more collisions than the log holds: walk the segment again (:393-401)
+                                nee_n = 0u;
+                                PSET(F_ASUM, s, a);
+                                PU(F_RNG_LO, s) = PU(F_CLONE_LO, s);  // the replay consumes exactly the same draws again
+                                PU(F_RNG_HI, s) = PU(F_CLONE_HI, s);
+                                fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE_ADJ << FL_MODE_SHIFT);
+                                next = Q_WALK;
+                            } else {
+                                nee_a = a;  // scattered from the log below; the sampler already stands behind the walk
+                            }
                         }
                     } else {
                         PSET(F_R0, s, PF(F_R0, s) + contrib[0]);
@@ -1087,6 +1109,26 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 }
             }
 
+            // ---- NEE adjoint from the collision log: d sigma_t(p_i) += -sum(adjoint) / sigma_n(p_i)  (:483-492) ----
+            if (HAS_ADJ && work == Q_NEE_END) {
+                unsigned n_max = nee_n;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, o));
+                if (n_max) {
+                    const float2* lg = P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLog;
+                    const float ox = nee_n ? PF(F_OX, s) : 0.0f, oy = nee_n ? PF(F_OY, s) : 0.0f, oz = nee_n ? PF(F_OZ, s) : 0.0f;
+                    const float dx = nee_n ? PF(F_DX, s) : 0.0f, dy = nee_n ? PF(F_DY, s) : 0.0f, dz = nee_n ? PF(F_DZ, s) : 0.0f;
+#pragma unroll 1
+                    for (unsigned i = 0; i < n_max; ++i) {
+                        if (i < nee_n) {
+                            const float2 e = __ldcg(lg + i);
+                            scatter_sigma(P, fmaf(e.x, dx, ox), fmaf(e.x, dy, oy), fmaf(e.x, dz, oz), -nee_a / e.y);
+                            K.add(C_SSCAT, 1);
+                        }
+                    }
+                }
+            }
+
             // ---- emitter sampling (:406-433) / phase sampling (:221-245, :626-652), one code site: for the batch of
             //      Q_SPAWN itself (end of a NEE-adjoint replay walk) and, without a queue hop in between, for the slots a
             //      vertex or NEE-end handler has just sent on to it ----
@@ -1125,6 +1167,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             // sampler.clone() position for the adjoint replay (:383)
                             PU(F_CLONE_LO, s) = (uint32_t) r.state;
                             PU(F_CLONE_HI, s) = (uint32_t) (r.state >> 32);
+                            PU(F_NLOG, s) = 0u;
                         }
                         fl = ok ? (fl | FL_NEE_VALID) : (fl & ~FL_NEE_VALID);
                         fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE << FL_MODE_SHIFT);
