@@ -28,7 +28,7 @@ struct uivr_ctx {
     size_t maj_cells = 0;
     uint32_t* wtab_alloc = nullptr; // walk table: padded supergrid + exit masks, with `wtab_slack` border words on
     uint32_t* wtab = nullptr;       // either side (speculative look-ahead reads); wtab = cell 0 (Params::wtab)
-    int wtab_slack = 0;
+    int wtab_slack = 0, wtab_words = 0;
     uint8_t* emask[2] = {nullptr, nullptr};  // ping-pong buffers of the exit-mask sweeps
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
@@ -39,6 +39,8 @@ struct uivr_ctx {
     uint4* desc = nullptr;          // vertex descriptors of the adjoint launch: [SM][slot][max_depth + 1][4]
     size_t desc_vecs = 0;
     float2* neelog = nullptr;       // NEE collision log of the adjoint launch: [SM][slot][kNeeLog]
+    float4* dalbedo4 = nullptr;     // (UIVR_DALBEDO_V4 builds) RGBA-padded d albedo
+    size_t dalbedo4_vox = 0;
     int variant = 3;
     // ray-batch mode (uivr_set_batch)
     bool batch_on = false;
@@ -122,6 +124,8 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.maj = ctx->maj;
     P.wtab = ctx->wtab;
     for (int a = 0; a < 3; ++a) P.pm[a] = ctx->mres[a] + 2;
+    P.wtab_slack = ctx->wtab_slack;
+    P.wtab_words = ctx->wtab_words;
     P.scale = s.scale;
     P.tan_x = s.tan_x;
     P.tan_y = s.tan_y;
@@ -250,7 +254,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->neelog); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->neelog); cudaFree(ctx->dalbedo4); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -424,9 +428,11 @@ int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream) {
         cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]);
         ctx->maj = nullptr; ctx->wtab = ctx->wtab_alloc = nullptr; ctx->emask[0] = ctx->emask[1] = nullptr;
         ctx->maj_cells = 0;
-        ctx->wtab_slack = (mx + 2) * (my + 2);
+        ctx->wtab_slack = ((mx + 2) * (my + 2) + 3) / 4 * 4;   // (a multiple of 4 words keeps cell 0 16-byte aligned)
+        ctx->wtab_words = (int) ((pcells + 2 * (size_t) ctx->wtab_slack + 3) / 4 * 4);
         UIVR_CUDA(ctx, cudaMalloc(&ctx->maj, mcells * sizeof(float)));
-        UIVR_CUDA(ctx, cudaMalloc(&ctx->wtab_alloc, (pcells + 2 * (size_t) ctx->wtab_slack) * sizeof(uint32_t)));
+        UIVR_CUDA(ctx, cudaMalloc(&ctx->wtab_alloc, (size_t) ctx->wtab_words * sizeof(uint32_t)));
+        UIVR_CUDA(ctx, cudaMemsetAsync(ctx->wtab_alloc, 0xFF, (size_t) ctx->wtab_words * sizeof(uint32_t), st));
         ctx->wtab = ctx->wtab_alloc + ctx->wtab_slack;
         UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[0], mcells));
         UIVR_CUDA(ctx, cudaMalloc(&ctx->emask[1], mcells));
@@ -548,6 +554,17 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
         P.desc = ctx->desc;
         P.desc_cap = ctx->props.max_depth + 1;
         P.neelog = ctx->neelog;
+#if UIVR_DALBEDO_V4
+        if (ctx->dalbedo4_vox < vox) {
+            cudaFree(ctx->dalbedo4);
+            ctx->dalbedo4 = nullptr;
+            ctx->dalbedo4_vox = 0;
+            UIVR_CUDA(ctx, cudaMalloc(&ctx->dalbedo4, vox * sizeof(float4)));
+            ctx->dalbedo4_vox = vox;
+        }
+        UIVR_CUDA(ctx, cudaMemsetAsync(ctx->dalbedo4, 0, vox * sizeof(float4), st));
+        P.dalbedo4 = ctx->dalbedo4;
+#endif
         P.records = ctx->records;
         P.rec_count = ctx->work_counter + 3;
         P.work_counter = ctx->work_counter + 1;
@@ -557,6 +574,10 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             if ((rc = launch_pool(ctx->num_sms, KIND_DRT, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
             ctx->launches += 1;
         }
+#if UIVR_DALBEDO_V4
+        k_rgba_to_rgb<<<ctx->num_sms * 8, kBlock, 0, st>>>(ctx->dalbedo4, d_dalbedo, vox);
+        ctx->launches += 1;
+#endif
     }
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], st));
     ctx->ev_valid[1] = true;

@@ -31,6 +31,8 @@ struct Params {
     // octant o; octant bit a = direction negative along axis a).  Border: kWalkBorder (ends every walk).
     const uint32_t* __restrict__ wtab;
     int   pm[3];             // padded dims = mres + 2
+    int   wtab_slack;        // border words in front of cell 0 (and behind the last cell)
+    int   wtab_words;        // words of the whole allocation (a multiple of 4)
     int   mres[3];
     float fmres[3];          // (float) mres
     float mcs[3];            // 1 / mres
@@ -68,6 +70,7 @@ struct Params {
     const float* __restrict__ grad_image;
     float* dsigma;            // [Z,Y,X]
     float* dalbedo;           // [Z,Y,X,3]
+    float4* dalbedo4;         // (UIVR_DALBEDO_V4 builds) RGBA-padded accumulation buffer, else NULL
     unsigned long long* counters;
     unsigned int* work_counter;
     uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
@@ -304,21 +307,74 @@ UIVR_DEV void albedo_tap(const Params& P, float px, float py, float pz, float a[
     }
 }
 
-// adjoint of the lookups: scatter-add g*w_k into the 8 voxels
+// adjoint of the lookups: scatter-add g*w_k into the 8 voxels.
+// A/B switches of the two scatter variants BASELINE.json's north_star names (profiles/r02_scatter_ab.txt):
+//   UIVR_SCATTER_MATCH  1: warp-aggregate with __match_any_sync -- lanes of the batch that hit the same voxel are
+//                          summed by the lowest of them, one RED per distinct voxel
+//   UIVR_DALBEDO_V4     1: d albedo accumulated RGBA-padded (Params::dalbedo4), one red.global.add.v4.f32 per corner
+//                          instead of three scalar REDs; k_rgba_to_rgb folds it into the caller's (Z,Y,X,3) tensor
+#ifndef UIVR_SCATTER_MATCH
+#define UIVR_SCATTER_MATCH 0
+#endif
+#ifndef UIVR_DSIGMA_V2
+#define UIVR_DSIGMA_V2 1   // the two x-neighbours of a d sigma_t scatter go out as ONE red.global.add.v2.f32 when they
+#endif                     // are adjacent and 8-byte aligned (about half of the scatters)
+#ifndef UIVR_DALBEDO_V4
+#define UIVR_DALBEDO_V4 1
+#endif
+
+UIVR_DEV void red_add(float* base, size_t idx, float v) {
+#if UIVR_SCATTER_MATCH
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(active, (unsigned long long) idx);
+    if (__any_sync(active, peers != (1u << lane))) {
+        // some lanes share a voxel: the lowest lane of every group sums its group (uniform loop over the lanes)
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int b = 0; b < 32; ++b) {
+            if (!((active >> b) & 1u)) continue;
+            const float x = __shfl_sync(active, v, b);
+            if ((peers >> b) & 1u) sum += x;
+        }
+        if ((unsigned) (__ffs(peers) - 1) == lane) atomicAdd(base + idx, sum);
+        return;
+    }
+#endif
+    atomicAdd(base + idx, v);
+}
+
 UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float g) {
     GridCell c;
     if (!grid_cell(P, px, py, pz, c)) return;
     const float gs = P.scale * g;
     const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
     const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
-    atomicAdd(P.dsigma + c.z0 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * uz));
-    atomicAdd(P.dsigma + c.z0 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * uz));
-    atomicAdd(P.dsigma + c.z0 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * uz));
-    atomicAdd(P.dsigma + c.z0 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * uz));
-    atomicAdd(P.dsigma + c.z1 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * c.wz));
-    atomicAdd(P.dsigma + c.z1 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * c.wz));
-    atomicAdd(P.dsigma + c.z1 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * c.wz));
-    atomicAdd(P.dsigma + c.z1 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * c.wz));
+#if UIVR_DSIGMA_V2 && !UIVR_SCATTER_MATCH
+    const bool adjacent = c.x1 == c.x0 + 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t row = ((k & 2) ? c.z1 : c.z0) * sz + ((k & 1) ? c.y1 : c.y0) * sy;
+        const float wyz = ((k & 1) ? c.wy : uy), wz = ((k & 2) ? c.wz : uz);
+        const float a = gs * ((ux * wyz) * wz), b = gs * ((c.wx * wyz) * wz);
+        const size_t i0 = row + c.x0;
+        if (adjacent && ((uintptr_t) (P.dsigma + i0) & 7u) == 0u) {
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(P.dsigma + i0), "f"(a), "f"(b) : "memory");
+        } else {
+            atomicAdd(P.dsigma + i0, a);
+            atomicAdd(P.dsigma + row + c.x1, b);
+        }
+    }
+#else
+    red_add(P.dsigma, c.z0 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * uz));
+    red_add(P.dsigma, c.z0 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * uz));
+    red_add(P.dsigma, c.z0 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * uz));
+    red_add(P.dsigma, c.z0 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * uz));
+    red_add(P.dsigma, c.z1 * sz + c.y0 * sy + c.x0, gs * ((ux * uy) * c.wz));
+    red_add(P.dsigma, c.z1 * sz + c.y0 * sy + c.x1, gs * ((c.wx * uy) * c.wz));
+    red_add(P.dsigma, c.z1 * sz + c.y1 * sy + c.x0, gs * ((ux * c.wy) * c.wz));
+    red_add(P.dsigma, c.z1 * sz + c.y1 * sy + c.x1, gs * ((c.wx * c.wy) * c.wz));
+#endif
 }
 
 UIVR_DEV void scatter_albedo(const Params& P, float px, float py, float pz, const float g[3]) {
@@ -330,6 +386,13 @@ UIVR_DEV void scatter_albedo(const Params& P, float px, float py, float pz, cons
     for (int k = 0; k < 8; ++k) {
         const int x = (k & 1) ? c.x1 : c.x0, y = (k & 2) ? c.y1 : c.y0, z = (k & 4) ? c.z1 : c.z0;
         const float w = (((k & 1) ? c.wx : ux) * ((k & 2) ? c.wy : uy)) * ((k & 4) ? c.wz : uz);
+#if UIVR_DALBEDO_V4
+        if (P.dalbedo4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.dalbedo4 + (z * sz + y * sy + x)),
+                         "f"(g[0] * w), "f"(g[1] * w), "f"(g[2] * w), "f"(0.0f) : "memory");
+            continue;
+        }
+#endif
         float* dst = P.dalbedo + 3 * (z * sz + y * sy + x);
         atomicAdd(dst + 0, g[0] * w);
         atomicAdd(dst + 1, g[1] * w);

@@ -124,6 +124,16 @@ __global__ void __launch_bounds__(kBlock) k_build_walk_table(const float* __rest
     }
 }
 
+// (UIVR_DALBEDO_V4 builds) fold the RGBA-padded accumulation buffer into the caller's (Z,Y,X,3) gradient
+__global__ void __launch_bounds__(kBlock) k_rgba_to_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        out[3 * i + 0] += v.x;
+        out[3 * i + 1] += v.y;
+        out[3 * i + 2] += v.z;
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_scale(float* __restrict__ x, size_t n, float s) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
         x[i] = x[i] * s;

@@ -82,6 +82,9 @@ namespace uivr {
 #ifndef UIVR_POOL_FOCUS
 #define UIVR_POOL_FOCUS 1          // 1: the handler warps of a CTA prefer to serve the same queue (instruction cache)
 #endif
+#ifndef UIVR_POOL_SMEMTAB
+#define UIVR_POOL_SMEMTAB 0   // 1 (A/B build): the whole walk table lives in shared memory, loaded once per CTA with
+#endif                        //    cp.async.bulk (TMA bulk copy) + mbarrier; needs small pools (the table is 166 KB at 256^3 / 8)
 #ifndef UIVR_POOL_HANDLERS_LAST
 #define UIVR_POOL_HANDLERS_LAST 0   // 1: the handler warps are the LAST warps of the CTA (scheduler priority A/B)
 #endif
@@ -261,6 +264,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     static_assert(NSLOT < 65535 && (Q_NUM * NSLOT * sizeof(uint16_t)) % 16 == 0, "16-bit slot ids; the pool stays 16-byte aligned");
     uint32_t* const cont = pool + (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT;  // [slot][C_WORDS]
     static_assert(NSLOT % 4 == 0, "the continuation records must stay 16-byte aligned");
+#if UIVR_POOL_SMEMTAB
+    // walk table in shared memory (+ its slack on either side): one elected thread issues TMA bulk copies, the bytes
+    // land asynchronously and complete the transaction count of an mbarrier every thread then waits on
+    uint32_t* const wtab_s = cont + (size_t) NSLOT * C_WORDS + P.wtab_slack;   // cell 0
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + 120);
+#define WT(ci) wtab_s[(ci)]
+#else
+#define WT(ci) __ldg(P.wtab + (ci))
+#endif
 
     Counters<COUNT> K;
     const unsigned lane = threadIdx.x & 31u;
@@ -286,6 +298,31 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         ctl->count[threadIdx.x] = threadIdx.x == Q_FREE ? NSLOT : 0;
     }
     if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; ctl->focus = Q_FREE; }
+#if UIVR_POOL_SMEMTAB
+    {
+        const uint32_t mb = (uint32_t) __cvta_generic_to_shared(mbar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t) P.wtab_words * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            const char* src = reinterpret_cast<const char*>(P.wtab - P.wtab_slack);
+            const uint32_t dst = (uint32_t) __cvta_generic_to_shared(wtab_s - P.wtab_slack);
+            for (uint32_t off = 0; off < bytes; off += 16384u) {
+                const uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + off), "l"(src + off), "r"(n), "r"(mb) : "memory");
+            }
+        }
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(mb) : "memory");
+    }
+#endif
     __syncthreads();
 
     // ---- queue primitives (warp-collective; each is instantiated ONCE per role to keep the code small) ----
@@ -413,8 +450,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             cin = (int) (rc.z & kCiMask);
                             wendq = (int) (rc.z >> 28);
                             tcur = __uint_as_float(rc.w);
-                            e = __ldg(P.wtab + ci);
-                            en = __ldg(P.wtab + cin);
+                            e = WT(ci);
+                            en = WT(cin);
                             obit = 1u << oct;
                             const int px = P.pm[0], pxy = P.pm[0] * P.pm[1];
                             sxl = (oct & 1u) ? -1 : 1;
@@ -464,7 +501,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             // cell's word now: the load latency hides behind a whole step
                             if (COUNT && (en_ & 0x80000100u) != 0x80000100u) K.add(C_MAJ, 1);
                             walk_decide(tnx, tny, tnz, adx, ady, adz, sxl, syl, szl, cn, tcur, cc);
-                            ec = __ldg(P.wtab + cc);
+                            ec = WT(cc);
                         } else {
                             wst = W_END;  // t_exit reached
                         }
@@ -602,7 +639,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
                     const int mode = (int) ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT);
-                    const float sb = __uint_as_float(__ldg(P.wtab + (CU(C_CI, s) & kCiMask)));
+                    const float sb = __uint_as_float(WT(CU(C_CI, s) & kCiMask));
                     // end of the cell along the ray, as the walker saw it
                     const float tn = CF(C_TCUR, s), tmax = CF(C_TMAX, s);
                     const float t_end = tn < tmax ? tn : tmax;
@@ -1291,6 +1328,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             route(s, next);
         }
     }
+#undef WT
 #undef PU
 #undef PF
 #undef PSET
@@ -1308,7 +1346,9 @@ inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cu
     const bool env = P.env_data != nullptr;
 #define UIVR_POOL_LAUNCH(KD, C, N, T, H, E)                                                             \
     do {                                                                                                \
-        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N, E>();                                  \
+        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N, E>() +                                 \
+                            (UIVR_POOL_SMEMTAB ? (size_t) P.wtab_words * 4 : 0);                        \
+        if (smem > 232448) return -4; /* the walk table does not fit next to the pool */                \
         e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
         if (UIVR_POOL_SETMAXNREG) {                                                                     \
