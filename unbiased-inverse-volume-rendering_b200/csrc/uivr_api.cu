@@ -41,6 +41,8 @@ struct uivr_ctx {
     float2* neelog = nullptr;       // NEE collision log of the adjoint launch: [SM][slot][kNeeLog]
     float4* dalbedo4 = nullptr;     // (UIVR_DALBEDO_V4 builds) RGBA-padded d albedo
     size_t dalbedo4_vox = 0;
+    float4* dsigma4 = nullptr;      // (UIVR_DSIGMA_TILED builds) d sigma_t in 2 x 2 tiles, four copies
+    size_t dsigma4_tiles = 0;
     int variant = 3;
     // ray-batch mode (uivr_set_batch)
     bool batch_on = false;
@@ -254,7 +256,7 @@ int uivr_create(int device, uivr_ctx** out) {
 int uivr_destroy(uivr_ctx* ctx) {
     if (!ctx) return UIVR_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->neelog); cudaFree(ctx->dalbedo4); cudaFree(ctx->d_sensors);
+    cudaFree(ctx->oct); cudaFree(ctx->maj); cudaFree(ctx->wtab_alloc); cudaFree(ctx->emask[0]); cudaFree(ctx->emask[1]); cudaFree(ctx->counters); cudaFree(ctx->work_counter); cudaFree(ctx->debug); cudaFree(ctx->records); cudaFree(ctx->desc); cudaFree(ctx->neelog); cudaFree(ctx->dalbedo4); cudaFree(ctx->dsigma4); cudaFree(ctx->d_sensors);
     cudaFree(ctx->d_env_data); cudaFree(ctx->d_env_marg); cudaFree(ctx->d_env_cond);
     cudaFree(ctx->st_sigma); cudaFree(ctx->st_albedo); cudaFree(ctx->st_image);
     cudaFree(ctx->st_gimage); cudaFree(ctx->st_dsigma); cudaFree(ctx->st_dalbedo);
@@ -554,6 +556,22 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
         P.desc = ctx->desc;
         P.desc_cap = ctx->props.max_depth + 1;
         P.neelog = ctx->neelog;
+#if UIVR_DSIGMA_TILED
+        {
+            P.tile_x = (P.res[0] + 1) >> 1;
+            P.tile_y = (P.res[1] + 1) >> 1;
+            const size_t tiles = (size_t) 4 * P.res[2] * P.tile_y * P.tile_x;
+            if (ctx->dsigma4_tiles < tiles) {
+                cudaFree(ctx->dsigma4);
+                ctx->dsigma4 = nullptr;
+                ctx->dsigma4_tiles = 0;
+                UIVR_CUDA(ctx, cudaMalloc(&ctx->dsigma4, tiles * sizeof(float4)));
+                ctx->dsigma4_tiles = tiles;
+            }
+            UIVR_CUDA(ctx, cudaMemsetAsync(ctx->dsigma4, 0, tiles * sizeof(float4), st));
+            P.dsigma4 = ctx->dsigma4;
+        }
+#endif
 #if UIVR_DALBEDO_V4
         if (ctx->dalbedo4_vox < vox) {
             cudaFree(ctx->dalbedo4);
@@ -574,6 +592,10 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             if ((rc = launch_pool(ctx->num_sms, KIND_DRT, ctx->counting != 0, P, st))) return fail(ctx, rc, "pool kernel launch failed");
             ctx->launches += 1;
         }
+#if UIVR_DSIGMA_TILED
+        k_tiles_to_dsigma<<<ctx->num_sms * 8, kBlock, 0, st>>>(ctx->dsigma4, d_dsigma_t, P.res[0], P.res[1], P.res[2], P.tile_x, P.tile_y);
+        ctx->launches += 1;
+#endif
 #if UIVR_DALBEDO_V4
         k_rgba_to_rgb<<<ctx->num_sms * 8, kBlock, 0, st>>>(ctx->dalbedo4, d_dalbedo, vox);
         ctx->launches += 1;

@@ -71,6 +71,8 @@ struct Params {
     float* dsigma;            // [Z,Y,X]
     float* dalbedo;           // [Z,Y,X,3]
     float4* dalbedo4;         // (UIVR_DALBEDO_V4 builds) RGBA-padded accumulation buffer, else NULL
+    float4* dsigma4;          // (UIVR_DSIGMA_TILED builds) 2x2 (x, y) tiles of d sigma_t, four copies by the parity of the
+    int   tile_x, tile_y;     // tile origin: [copy][z][tile_y][tile_x] float4; else NULL
     unsigned long long* counters;
     unsigned int* work_counter;
     uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
@@ -319,6 +321,9 @@ UIVR_DEV void albedo_tap(const Params& P, float px, float py, float pz, float a[
 #ifndef UIVR_DSIGMA_V2
 #define UIVR_DSIGMA_V2 1   // the two x-neighbours of a d sigma_t scatter go out as ONE red.global.add.v2.f32 when they
 #endif                     // are adjacent and 8-byte aligned (about half of the scatters)
+#ifndef UIVR_DSIGMA_TILED
+#define UIVR_DSIGMA_TILED 1 // d sigma_t is accumulated in 2 x 2 (x, y) tiles (Params::dsigma4): the four voxels a scatter touches
+#endif                      // in one z plane are ONE red.global.add.v4.f32 (2 REDs per scatter instead of 8)
 #ifndef UIVR_DALBEDO_V4
 #define UIVR_DALBEDO_V4 1
 #endif
@@ -350,6 +355,28 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
     const float gs = P.scale * g;
     const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
     const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
+#if UIVR_DSIGMA_TILED && !UIVR_SCATTER_MATCH
+    if (P.dsigma4) {
+        // tile (x0 >> 1, y0 >> 1) of the copy picked by the parities of (x0, y0) holds (x0, y0), (x0+1, y0), (x0, y0+1),
+        // (x0+1, y0+1) contiguously; a clamped neighbour (x1 == x0 at the border) folds into the slot of x0
+        const int sx = c.x1 - c.x0, sy1 = c.y1 - c.y0;
+        const size_t tile = ((size_t) (((c.x0 & 1) | ((c.y0 & 1) << 1)) * P.res[2]) * P.tile_y + (c.y0 >> 1)) * P.tile_x + (c.x0 >> 1);
+        const size_t plane = (size_t) P.tile_y * P.tile_x;
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+            const float wz = kz ? c.wz : uz;
+            const float v00 = gs * ((ux * uy) * wz), v10 = gs * ((c.wx * uy) * wz);
+            const float v01 = gs * ((ux * c.wy) * wz), v11 = gs * ((c.wx * c.wy) * wz);
+            float t0 = v00, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;   // slots (0,0) (1,0) (0,1) (1,1)
+            if (sx) t1 = v10; else t0 += v10;
+            if (sy1) { t2 = v01; if (sx) t3 = v11; else t2 += v11; }
+            else { t0 += v01; if (sx) t1 += v11; else t0 += v11; }
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.dsigma4 + tile + (size_t) (kz ? c.z1 : c.z0) * plane),
+                         "f"(t0), "f"(t1), "f"(t2), "f"(t3) : "memory");
+        }
+        return;
+    }
+#endif
 #if UIVR_DSIGMA_V2 && !UIVR_SCATTER_MATCH
     const bool adjacent = c.x1 == c.x0 + 1;
 #pragma unroll

@@ -124,6 +124,26 @@ __global__ void __launch_bounds__(kBlock) k_build_walk_table(const float* __rest
     }
 }
 
+// (UIVR_DSIGMA_TILED builds) fold the four tile copies into the caller's (Z,Y,X) gradient: voxel (x, y) lies in
+// tile ((x - px) >> 1, (y - py) >> 1), slot ((x - px) & 1) + 2 ((y - py) & 1) of the copy with tile origin (px, py)
+__global__ void __launch_bounds__(kBlock) k_tiles_to_dsigma(const float4* __restrict__ tiles, float* __restrict__ out, int rx,
+                                                            int ry, int rz, int tx, int ty) {
+    const size_t n = (size_t) rx * ry * rz;
+    const float* t = reinterpret_cast<const float*>(tiles);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int x = (int) (i % rx), y = (int) ((i / rx) % ry), z = (int) (i / ((size_t) rx * ry));
+        float acc = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int px = p & 1, py = p >> 1;
+            if (x < px || y < py) continue;
+            const int X = (x - px) >> 1, Y = (y - py) >> 1, slot = ((x - px) & 1) + 2 * ((y - py) & 1);
+            acc += t[((((size_t) p * rz + z) * ty + Y) * tx + X) * 4 + slot];
+        }
+        out[i] += acc;
+    }
+}
+
 // (UIVR_DALBEDO_V4 builds) fold the RGBA-padded accumulation buffer into the caller's (Z,Y,X,3) gradient
 __global__ void __launch_bounds__(kBlock) k_rgba_to_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
