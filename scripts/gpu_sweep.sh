@@ -10,7 +10,7 @@ tail -8 gpurun_out/pytest_gpu_$TAG.log
 timeout 120 python scripts/quick_bench.py variant=3 reps=3 > gpurun_out/quick_default_$TAG.log 2>&1; tail -4 gpurun_out/quick_default_$TAG.log
 SWEEP_VARIANT=3 timeout 900 bash scripts/sweep_pool.sh run counters=0 2>&1 | tee gpurun_out/sweep_$TAG.log
 if [ -z "$NO_NCU" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pool -s 4 -c 4 -f -o gpurun_out/prof_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pool -s 3 -c 3 -f -o gpurun_out/prof_$TAG \
     python scripts/profile_step.py variant=3 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
 fi

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/kernel_constants.json from an ncu report of ONE config-3 step (scripts/profile_step.py variant=3,
-`ncu --set full -k regex:k_pool -s 4 -c 4`): warp instructions, lanes per instruction and DRAM bytes of the four
-slot-pool launches (forward, primal replay, adjoint, DRT), stamped with the fingerprint of the kernel sources.
+`ncu --set full -k regex:k_pool -s 3 -c 3`): warp instructions, lanes per instruction and DRAM bytes of the three
+slot-pool launches (forward, adjoint, DRT), stamped with the fingerprint of the kernel sources.
 bench.py reads it for `roofline.traffic` / `roofline.issue` and refuses it when the sources have changed.
 
     python scripts/ncu_constants.py gpurun_out/prof.ncu-rep "r02 gpurun call A"
@@ -44,23 +44,23 @@ def main():
             "l1_hit_pct": val(d, "l1tex__t_sector_hit_rate.pct"),
             "regs": val(d, "launch__registers_per_thread"),
         })
-    if len(launches) != 4:
-        raise SystemExit(f"expected the 4 slot-pool launches of one step, found {len(launches)}")
-    fwd, rep_, adj, drt = launches
-    wi_b = rep_["warp_inst"] + adj["warp_inst"] + drt["warp_inst"]
+    if len(launches) != 3 or "k_pool<0" not in launches[0]["kernel"].replace("(int)", ""):
+        raise SystemExit(f"expected the 3 slot-pool launches of one step (forward first), found "
+                         f"{[l['kernel'][:40] for l in launches]}")
+    fwd, adj, drt = launches
+    wi_b = adj["warp_inst"] + drt["warp_inst"]
     out = {
         "source_sha": bench.kernel_source_sha(),
         "captured": captured,
         "what": "one step of bench.py's config 3 (256^3, 512x512x64 spp) under `ncu --set full --clock-control none`: "
-                "launches = forward, primal replay, adjoint replay, DRT",
+                "launches = forward, adjoint replay (gathers L itself), DRT",
         "fwd_warp_inst_per_step": fwd["warp_inst"],
         "bwd_pipeline_warp_inst_per_step": wi_b,
         "fwd_dram_bytes_per_launch": fwd["dram_bytes"],
-        "bwd_pipeline_dram_bytes_per_step": rep_["dram_bytes"] + adj["dram_bytes"] + drt["dram_bytes"],
+        "bwd_pipeline_dram_bytes_per_step": adj["dram_bytes"] + drt["dram_bytes"],
         "lanes_per_instruction": {
             "forward": fwd["lanes_per_inst"],
-            "backward_pipeline": (rep_["lanes_per_inst"] * rep_["warp_inst"] + adj["lanes_per_inst"] * adj["warp_inst"] +
-                                  drt["lanes_per_inst"] * drt["warp_inst"]) / wi_b},
+            "backward_pipeline": (adj["lanes_per_inst"] * adj["warp_inst"] + drt["lanes_per_inst"] * drt["warp_inst"]) / wi_b},
         "launches": launches,
     }
     path = os.path.join(ROOT, "profiles", "kernel_constants.json")

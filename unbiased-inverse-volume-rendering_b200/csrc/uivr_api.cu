@@ -38,7 +38,7 @@ struct uivr_ctx {
     size_t records_cap = 0;
     uint4* desc = nullptr;          // vertex descriptors of the adjoint launch: [SM][slot][max_depth + 1][4]
     size_t desc_vecs = 0;
-    float2* neelog = nullptr;       // NEE collision log of the adjoint launch: [SM][slot][kNeeLog]
+    float2* neelog = nullptr;       // NEE collision log of the adjoint launch: [SM][slot][kNeeLog + 1]
     float4* dalbedo4 = nullptr;     // (UIVR_DALBEDO_V4 builds) RGBA-padded d albedo
     size_t dalbedo4_vox = 0;
     float4* dsigma4 = nullptr;      // (UIVR_DSIGMA_TILED builds) d sigma_t in 2 x 2 tiles, four copies
@@ -552,7 +552,7 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             ctx->desc_vecs = desc_vecs;
         }
         if (!ctx->neelog)
-            UIVR_CUDA(ctx, cudaMalloc(&ctx->neelog, (size_t) ctx->num_sms * UIVR_POOL_SLOTS_ADJ * kNeeLog * sizeof(float2)));
+            UIVR_CUDA(ctx, cudaMalloc(&ctx->neelog, (size_t) ctx->num_sms * UIVR_POOL_SLOTS_ADJ * kNeeLogStride * sizeof(float2)));
         P.desc = ctx->desc;
         P.desc_cap = ctx->props.max_depth + 1;
         P.neelog = ctx->neelog;
@@ -560,7 +560,13 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
         {
             P.tile_x = (P.res[0] + 1) >> 1;
             P.tile_y = (P.res[1] + 1) >> 1;
+#if UIVR_DSIGMA_TILED == 2
+            P.tile_z = (P.res[2] + 1) >> 1;
+            const size_t tiles = (size_t) 16 * P.tile_z * P.tile_y * P.tile_x;
+#else
+            P.tile_z = P.res[2];
             const size_t tiles = (size_t) 4 * P.res[2] * P.tile_y * P.tile_x;
+#endif
             if (ctx->dsigma4_tiles < tiles) {
                 cudaFree(ctx->dsigma4);
                 ctx->dsigma4 = nullptr;
@@ -593,7 +599,11 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
             ctx->launches += 1;
         }
 #if UIVR_DSIGMA_TILED
+#if UIVR_DSIGMA_TILED == 2
+        k_tiles3_to_dsigma<<<ctx->num_sms * 8, kBlock, 0, st>>>(ctx->dsigma4, d_dsigma_t, P.res[0], P.res[1], P.res[2], P.tile_x, P.tile_y, P.tile_z);
+#else
         k_tiles_to_dsigma<<<ctx->num_sms * 8, kBlock, 0, st>>>(ctx->dsigma4, d_dsigma_t, P.res[0], P.res[1], P.res[2], P.tile_x, P.tile_y);
+#endif
         ctx->launches += 1;
 #endif
 #if UIVR_DALBEDO_V4

@@ -72,7 +72,7 @@ struct Params {
     float* dalbedo;           // [Z,Y,X,3]
     float4* dalbedo4;         // (UIVR_DALBEDO_V4 builds) RGBA-padded accumulation buffer, else NULL
     float4* dsigma4;          // (UIVR_DSIGMA_TILED builds) 2x2 (x, y) tiles of d sigma_t, four copies by the parity of the
-    int   tile_x, tile_y;     // tile origin: [copy][z][tile_y][tile_x] float4; else NULL
+    int   tile_x, tile_y, tile_z; // tile origin: [copy][z][tile_y][tile_x] float4; else NULL
     unsigned long long* counters;
     unsigned int* work_counter;
     uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
@@ -360,8 +360,14 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
         // tile (x0 >> 1, y0 >> 1) of the copy picked by the parities of (x0, y0) holds (x0, y0), (x0+1, y0), (x0, y0+1),
         // (x0+1, y0+1) contiguously; a clamped neighbour (x1 == x0 at the border) folds into the slot of x0
         const int sx = c.x1 - c.x0, sy1 = c.y1 - c.y0;
+#if UIVR_DSIGMA_TILED == 2
+        // 2 x 2 x 2 tiles, eight copies: both z planes of a scatter lie in ONE 32-byte sector
+        const size_t tile = (((size_t) (((c.x0 & 1) | ((c.y0 & 1) << 1) | ((c.z0 & 1) << 2)) * P.tile_z + (c.z0 >> 1)) * P.tile_y + (c.y0 >> 1)) * P.tile_x + (c.x0 >> 1)) * 2;
+        const int sz1 = c.z1 - c.z0;
+#else
         const size_t tile = ((size_t) (((c.x0 & 1) | ((c.y0 & 1) << 1)) * P.res[2]) * P.tile_y + (c.y0 >> 1)) * P.tile_x + (c.x0 >> 1);
         const size_t plane = (size_t) P.tile_y * P.tile_x;
+#endif
 #pragma unroll
         for (int kz = 0; kz < 2; ++kz) {
             const float wz = kz ? c.wz : uz;
@@ -371,7 +377,12 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
             if (sx) t1 = v10; else t0 += v10;
             if (sy1) { t2 = v01; if (sx) t3 = v11; else t2 += v11; }
             else { t0 += v01; if (sx) t1 += v11; else t0 += v11; }
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.dsigma4 + tile + (size_t) (kz ? c.z1 : c.z0) * plane),
+#if UIVR_DSIGMA_TILED == 2
+            float4* dst = P.dsigma4 + tile + (kz ? sz1 : 0);
+#else
+            float4* dst = P.dsigma4 + tile + (size_t) (kz ? c.z1 : c.z0) * plane;
+#endif
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
                          "f"(t0), "f"(t1), "f"(t2), "f"(t3) : "memory");
         }
         return;

@@ -144,6 +144,26 @@ __global__ void __launch_bounds__(kBlock) k_tiles_to_dsigma(const float4* __rest
     }
 }
 
+// same for 2 x 2 x 2 tiles (UIVR_DSIGMA_TILED == 2): eight copies, two float4 (z slot 0 / 1) per tile
+__global__ void __launch_bounds__(kBlock) k_tiles3_to_dsigma(const float4* __restrict__ tiles, float* __restrict__ out, int rx,
+                                                             int ry, int rz, int tx, int ty, int tz) {
+    const size_t n = (size_t) rx * ry * rz;
+    const float* t = reinterpret_cast<const float*>(tiles);
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const int x = (int) (i % rx), y = (int) ((i / rx) % ry), z = (int) (i / ((size_t) rx * ry));
+        float acc = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int px = p & 1, py = (p >> 1) & 1, pz = p >> 2;
+            if (x < px || y < py || z < pz) continue;
+            const int X = (x - px) >> 1, Y = (y - py) >> 1, Z = (z - pz) >> 1;
+            const int slot = ((x - px) & 1) + 2 * ((y - py) & 1) + 4 * ((z - pz) & 1);
+            acc += t[((((size_t) p * tz + Z) * ty + Y) * tx + X) * 8 + slot];
+        }
+        out[i] += acc;
+    }
+}
+
 // (UIVR_DALBEDO_V4 builds) fold the RGBA-padded accumulation buffer into the caller's (Z,Y,X,3) gradient
 __global__ void __launch_bounds__(kBlock) k_rgba_to_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {

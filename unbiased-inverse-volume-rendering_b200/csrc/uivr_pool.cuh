@@ -41,7 +41,7 @@ namespace uivr {
 #define UIVR_POOL_HANDLERS_ADJ 12
 #endif
 #ifndef UIVR_POOL_SLOTS_ADJ
-#define UIVR_POOL_SLOTS_ADJ 832
+#define UIVR_POOL_SLOTS_ADJ 1088
 #endif
 #ifndef UIVR_POOL_BLOCK_DRT
 #define UIVR_POOL_BLOCK_DRT 896
@@ -50,7 +50,7 @@ namespace uivr {
 #define UIVR_POOL_HANDLERS_DRT 12
 #endif
 #ifndef UIVR_POOL_SLOTS_DRT
-#define UIVR_POOL_SLOTS_DRT 832
+#define UIVR_POOL_SLOTS_DRT 928
 #endif
 #ifndef UIVR_POOL_BLOCK_FWD
 #define UIVR_POOL_BLOCK_FWD 896
@@ -81,6 +81,9 @@ namespace uivr {
 #endif
 #ifndef UIVR_POOL_FOCUS
 #define UIVR_POOL_FOCUS 1          // 1: the handler warps of a CTA prefer to serve the same queue (instruction cache)
+#endif
+#ifndef UIVR_POOL_AFFINITY
+#define UIVR_POOL_AFFINITY 0       // 1 (A/B build): handler warps of one SM sub-partition prefer one queue (L0 instruction cache)
 #endif
 #ifndef UIVR_POOL_SMEMTAB
 #define UIVR_POOL_SMEMTAB 0   // 1 (A/B build): the whole walk table lives in shared memory, loaded once per CTA with
@@ -127,19 +130,27 @@ enum : int {
     F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ,
     F_B0, F_B1, F_B2, F_R0, F_R1, F_R2, F_TS, F_FLAGS, F_DEPTH,
     F_NUM_FWD,
-    // adjoint-only state
-    F_ALT_LO = F_NUM_FWD, F_ALT_HI, F_ASEQ,
-    F_DL0, F_DL1, F_DL2,
-    F_RSW0, F_RSW1, F_RSW2, F_RSC0, F_RSC1, F_RSC2,
-    F_RSOX, F_RSOY, F_RSOZ, F_RSDX, F_RSDY, F_RSDZ, F_RSTMAX,
-    F_CLONE_LO, F_CLONE_HI, F_DRT_ST,
-    F_NUM_BWD,
+    // state of both backward kernels: dL of the pixel, reservoir weight sums (adjoint) | Li of the DRT vertex (DRT),
+    // logged collisions of the current NEE walk (adjoint) | sigma_t at the DRT vertex (DRT)
+    F_DL0 = F_NUM_FWD, F_DL1, F_DL2,
+    F_RSW0, F_RSW1, F_RSW2,
+    F_DRT_ST,
+    // alt sampler (adjoint) | albedo of the DRT vertex (DRT)
+    F_ALT_LO, F_ALT_HI, F_ASEQ,
+    F_NUM_ADJ,
+    // DRT kernel only: the reservoir segment, DRT distance-sampling sums
+    F_RSOX = F_NUM_ADJ, F_RSOY, F_RSOZ, F_RSDX, F_RSDY, F_RSDZ, F_DRT_D, F_DRT_T,
+    F_NUM_DRT,
     // aliases
     F_ST = F_TS, F_T = F_TS, F_ASUM = F_TS,
-    F_LI0 = F_RSW0, F_LI1 = F_RSW1, F_LI2 = F_RSW2, F_AL0 = F_RSC0, F_AL1 = F_RSC1, F_AL2 = F_RSC2,
-    F_T2 = F_CLONE_LO, F_DRT_D = F_CLONE_LO, F_DRT_T = F_CLONE_HI,
-    F_NLOG = F_DRT_ST   // adjoint kernel: tentative collisions of the current NEE walk (F_DRT_ST lives in the DRT kernel)
+    F_LI0 = F_RSW0, F_LI1 = F_RSW1, F_LI2 = F_RSW2, F_AL0 = F_ALT_LO, F_AL1 = F_ALT_HI, F_AL2 = F_ASEQ,
+    F_NLOG = F_DRT_ST,  // adjoint kernel: tentative collisions of the current NEE walk
+    F_T2 = F_DRT_ST     // adjoint kernel: T of the NEE replay walk (log overflow only; the log count is consumed by then)
 };
+// The adjoint kernel keeps what is touched once or twice per path OUT of shared memory (every word per slot is
+// in-flight samples lost): the reservoir's candidate (weight, segment) is the vertex descriptor of the depth the
+// reservoir picked + a fifth vector written when a candidate is accepted; the sampler clone of the NEE replay lives in
+// the slot's collision log (entry kNeeLog).
 
 // The CONTINUATION of the free-flight walk is a 12-word record per slot (array of structures, 48 bytes): a
 // walker lane picks it up with three 128-bit loads (conflict-free for any 8 slots per phase: the stride of 12
@@ -225,20 +236,33 @@ constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) a
 //   {alt state lo, hi, sigma_t at the collision (0: the segment escaped), interval} {o.xyz, d.x} {d.yz, c.xy}
 //   {c.z, albedo.xyz}    c = contribution of the next-event estimation that follows this vertex (written by the
 //                        NEE handler; 0 without one): what the reference subtracts from L after the vertex (:214)
-constexpr int kDescVec = 4;
+//   {reservoir weight.xyz, t_exit of the segment}   (only written when the reservoir accepts the vertex, :745-753)
+constexpr int kDescVec = 5;
 // NEE adjoint (volpathsimple.py:393-401, :483-492): the reference walks every shadow segment a second time, from a
 // cloned sampler, to scatter -sum(adjoint)/sigma_n at each tentative collision once the contribution is known.
 // The adjoint kernel instead LOGS the tentative collisions of the first walk (t, sigma_n; kNeeLog per slot, global
 // memory) and scatters from the log at the NEE end: same positions, same values, no second walk.  A shadow walk
 // with more collisions than the log holds falls back to the replay walk.
 constexpr int kNeeLog = 32;
+constexpr int kNeeLogStride = kNeeLog + 1;  // + the sampler clone (:383) for the fall-back
 
 // ENV (envmap emitter, uivr_env.cuh): three more fields per slot hold the NEE weight
 // throughput * phase * mis * Le / pdf of the direction sampled at Q_SPAWN until Q_NEE_END
-template <bool BWD, int NSLOT, bool ENV = false>
+__host__ __device__ constexpr int pool_fields(int kind) { return kind == 0 ? F_NUM_FWD : kind == 2 ? F_NUM_ADJ : F_NUM_DRT; }
+template <int KIND, int NSLOT, bool ENV = false>
 constexpr size_t pool_smem_bytes() {
     return 128 + (size_t) Q_NUM * NSLOT * sizeof(uint16_t) +
-           (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0) + C_WORDS) * NSLOT * sizeof(uint32_t);
+           (size_t) (pool_fields(KIND) + (ENV ? 3 : 0) + C_WORDS) * NSLOT * sizeof(uint32_t);
+}
+// The envmap instances carry three more words per slot: as many slots as fit the footprint of the constant-emitter
+// instance (the shared-memory carve-out moves in steps; one step more halves the L1 that is left)
+template <int KIND, int NSLOT>
+constexpr int pool_env_slots() {
+    int n = NSLOT;
+    while (n > 256 && 128 + (size_t) n * (Q_NUM * sizeof(uint16_t) + (pool_fields(KIND) + 3 + C_WORDS) * sizeof(uint32_t)) >
+                          pool_smem_bytes<KIND, NSLOT, false>())
+        n -= 32;
+    return n;
 }
 
 // BLOCK threads per CTA (one CTA per SM), of which HANDLERS warps serve the transition queues and the
@@ -246,7 +270,7 @@ constexpr size_t pool_smem_bytes() {
 template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS, bool ENV = false>
 __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     constexpr bool BWD = KIND != KIND_FWD;               // any gradient work
-    constexpr int F_NW0 = BWD ? F_NUM_BWD : F_NUM_FWD;   // ENV only: NEE weight (3 words)
+    constexpr int F_NW0 = pool_fields(KIND);             // ENV only: NEE weight (3 words)
     constexpr bool HAS_ADJ = KIND == KIND_ADJ;           // adjoint replay (reservoir, NEE adjoint)
     constexpr bool HAS_DRT = KIND == KIND_DRT;           // DRT walk, DRT vertex, recursive path
     constexpr int kPoolBlock = BLOCK;
@@ -262,7 +286,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     volatile uint16_t* const ring = reinterpret_cast<volatile uint16_t*>(smem_raw + 128);
     uint32_t* const pool = reinterpret_cast<uint32_t*>(smem_raw + 128 + Q_NUM * NSLOT * sizeof(uint16_t));
     static_assert(NSLOT < 65535 && (Q_NUM * NSLOT * sizeof(uint16_t)) % 16 == 0, "16-bit slot ids; the pool stays 16-byte aligned");
-    uint32_t* const cont = pool + (size_t) ((BWD ? F_NUM_BWD : F_NUM_FWD) + (ENV ? 3 : 0)) * NSLOT;  // [slot][C_WORDS]
+    uint32_t* const cont = pool + (size_t) (pool_fields(KIND) + (ENV ? 3 : 0)) * NSLOT;  // [slot][C_WORDS]
     static_assert(NSLOT % 4 == 0, "the continuation records must stay 16-byte aligned");
 #if UIVR_POOL_SMEMTAB
     // walk table in shared memory (+ its slack on either side): one elected thread issues TMA bulk copies, the bytes
@@ -587,6 +611,23 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 best = __shfl_sync(FULL, best, 0);
 #if UIVR_POOL_FOCUS
                 const int focus = __shfl_sync(FULL, *((volatile int*) &ctl->focus), 0) & 7;
+#endif
+#if UIVR_POOL_AFFINITY
+                // Queue affinity by scheduler (warp_id & 3 = the SM sub-partition a warp lives on, each with its own
+                // L0 instruction cache): the handler warps of one sub-partition prefer one handler body.
+                const int wq = warp_id & 3;
+                const int pref0 = wq == 0 ? Q_TAP : wq == 1 ? Q_FREE : wq == 2 ? (HAS_ADJ ? Q_VERTEX_ADJ : Q_VERTEX) : Q_PATH_END;
+                const int pref1 = wq == 3 ? (HAS_ADJ ? Q_SCATTER : Q_NEE_END) : pref0;
+                const int pref2 = wq == 3 ? Q_NEE_END : pref0;
+                if (__shfl_sync(FULL, cnt, pref0) >= 32) {
+                    work = pref0;
+                } else if (__shfl_sync(FULL, cnt, pref1) >= 32) {
+                    work = pref1;
+                } else if (__shfl_sync(FULL, cnt, pref2) >= 32) {
+                    work = pref2;
+                } else
+#endif
+#if UIVR_POOL_FOCUS
                 if (__shfl_sync(FULL, cnt, focus) >= 32) {
                     work = focus;
                 } else if ((best >> 3) >= 32) {
@@ -690,7 +731,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             // log the collision for the NEE adjoint (scattered at the NEE end, when its weight is known)
                             const unsigned nl = PU(F_NLOG, s);
                             if (nl < (unsigned) kNeeLog)
-                                __stcg(P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLog + nl, make_float2(wt, sn));
+                                __stcg(P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLogStride + nl, make_float2(wt, sn));
                             PU(F_NLOG, s) = nl + 1u;
                         }
                         // ratio tracking (:461-502) / running transmittance of the DRT walk
@@ -765,10 +806,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     const bool is_drt = HAS_DRT && ((fl & FL_MODE_MASK) >> FL_MODE_SHIFT) == (unsigned) PM_DRT;
                     const bool ds = is_drt ? (fl & FL_DRT_FOUND) != 0u : (fl & FL_DID_SCATTER) != 0u;
                     // vertex position: on the stored reservoir segment for DRT, else on the current segment
-                    const int fo = is_drt ? F_RSOX : F_OX, fd = is_drt ? F_RSDX : F_DX;
+                    const int fo = (HAS_DRT && is_drt) ? F_RSOX : F_OX, fd = (HAS_DRT && is_drt) ? F_RSDX : F_DX;
                     const float sox = PF(fo, s), soy = PF(fo + 1, s), soz = PF(fo + 2, s);
                     const float sdx = PF(fd, s), sdy = PF(fd + 1, s), sdz = PF(fd + 2, s);
-                    const float swt = is_drt ? PF(F_DRT_T, s) : CF(C_WT, s);
+                    const float swt = (HAS_DRT && is_drt) ? PF(F_DRT_T, s) : CF(C_WT, s);
                     const float vx = fmaf(swt, sdx, sox), vy = fmaf(swt, sdy, soy), vz = fmaf(swt, sdz, soz);
                     float albedo[3] = {1.0f, 1.0f, 1.0f};
                     if (ds) {
@@ -777,7 +818,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         // the vertex becomes the origin of whatever leaves it (NEE segment, then the phase-sampled one)
                         PSET(F_OX, s, vx); PSET(F_OY, s, vy); PSET(F_OZ, s, vz);
                     }
-                    if (is_drt) {
+                    if (HAS_DRT && is_drt) {
                         if (ds) {
                             PSET(F_AL0, s, albedo[0]); PSET(F_AL1, s, albedo[1]); PSET(F_AL2, s, albedo[2]);
                             PSET(F_LI0, s, 0.0f); PSET(F_LI1, s, 0.0f); PSET(F_LI2, s, 0.0f);
@@ -804,6 +845,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 const float u = draw(alt, K);
                                 float wsum[3] = {PF(F_RSW0, s), PF(F_RSW1, s), PF(F_RSW2, s)};
                                 float ratio[3];
+                                bool took = false;
 #pragma unroll
                                 for (int c = 0; c < 3; ++c) {
                                     wsum[c] += beta[c];
@@ -811,13 +853,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 }
                                 PSET(F_RSW0, s, wsum[0]); PSET(F_RSW1, s, wsum[1]); PSET(F_RSW2, s, wsum[2]);
                                 if (u <= mean3(ratio)) {
-                                    PSET(F_RSC0, s, beta[0]); PSET(F_RSC1, s, beta[1]); PSET(F_RSC2, s, beta[2]);
-                                    PSET(F_RSOX, s, sox); PSET(F_RSOY, s, soy); PSET(F_RSOZ, s, soz);
-                                    PSET(F_RSDX, s, sdx); PSET(F_RSDY, s, sdy); PSET(F_RSDZ, s, sdz);
-                                    PSET(F_RSTMAX, s, stmax);
+                                    // the candidate IS this vertex's descriptor (segment) + its fifth vector
+                                    took = true;
                                     PU(F_DEPTH, s) = (dw & 0xFFFFu) | ((unsigned) depth << 16);
                                     fl |= FL_RS_VALID;
                                 }
+                                if (took)
+                                    __stcg(P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + depth) * kDescVec + 4,
+                                           make_uint4(__float_as_uint(beta[0]), __float_as_uint(beta[1]), __float_as_uint(beta[2]),
+                                                      __float_as_uint(stmax)));
                             }
                             // The free-flight (:152-172) and transmittance (:181-189) gradients of this segment need
                             // the radiance the path gathers from here on, Li = L - (what was gathered before).  The
@@ -894,8 +938,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 // more collisions than the log holds: walk the segment again (:393-401)
                                 nee_n = 0u;
                                 PSET(F_ASUM, s, a);
-                                PU(F_RNG_LO, s) = PU(F_CLONE_LO, s);  // the replay consumes exactly the same draws again
-                                PU(F_RNG_HI, s) = PU(F_CLONE_HI, s);
+                                // the replay consumes exactly the same draws again
+                                const float2 cl = __ldcg(P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLogStride + kNeeLog);
+                                PU(F_RNG_LO, s) = __float_as_uint(cl.x);
+                                PU(F_RNG_HI, s) = __float_as_uint(cl.y);
                                 fl = (fl & ~FL_MODE_MASK) | ((unsigned) PM_NEE_ADJ << FL_MODE_SHIFT);
                                 next = Q_WALK;
                             } else {
@@ -913,6 +959,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             } else if (work == Q_PATH_END) {
                 bool want_rec = false;
                 float wdl[3] = {0.0f, 0.0f, 0.0f};  // reservoir weight * dL: the adjoint handed to the DRT pass
+                uint4 rs1 = make_uint4(0u, 0u, 0u, 0u), rs2 = rs1, rs4 = rs1;  // descriptor of the reservoir's vertex
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
                     const int pass = (int) (fl & FL_PASS_MASK);
@@ -961,7 +1008,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                         if (use_rsv && (fl & FL_RS_VALID)) {
                             // DRTReservoir.get (:756-760) and adjoint = weight * dL (:255)
-                            const float wcur[3] = {PF(F_RSC0, s), PF(F_RSC1, s), PF(F_RSC2, s)};
+                            const uint4* dsc = P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + (dw >> 16)) * kDescVec;
+                            rs1 = __ldcg(dsc + 1); rs2 = __ldcg(dsc + 2); rs4 = __ldcg(dsc + 4);
+                            const float wcur[3] = {__uint_as_float(rs4.x), __uint_as_float(rs4.y), __uint_as_float(rs4.z)};
                             const float wsum[3] = {PF(F_RSW0, s), PF(F_RSW1, s), PF(F_RSW2, s)};
                             const float d = mean3(wcur), ws = mean3(wsum);
 #pragma unroll
@@ -1006,8 +1055,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         if (want_rec) {
                             uint32_t* rec = P.records + (size_t) (base + __popc(m & lt_mask)) * kRecWords;
                             uint4* r4 = reinterpret_cast<uint4*>(rec);
-                            r4[0] = make_uint4(PU(F_RSOX, s), PU(F_RSOY, s), PU(F_RSOZ, s), PU(F_RSDX, s));
-                            r4[1] = make_uint4(PU(F_RSDY, s), PU(F_RSDZ, s), PU(F_RSTMAX, s), __float_as_uint(wdl[0]));
+                            r4[0] = rs1;  // o.xyz, d.x
+                            r4[1] = make_uint4(rs2.x, rs2.y, rs4.w, __float_as_uint(wdl[0]));  // d.yz, t_exit
                             r4[2] = make_uint4(__float_as_uint(wdl[1]), __float_as_uint(wdl[2]), PU(F_ALT_LO, s), PU(F_ALT_HI, s));
                             r4[3] = make_uint4(PU(F_ASEQ, s), PU(F_DEPTH, s) >> 16, 0u, 0u);
                         }
@@ -1080,7 +1129,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             for (int c = 0; c < 3; ++c) {
                                 PSET(F_DL0 + c, s, ldg_tap(P.grad_image + 3 * (size_t) pix + c) * P.inv_spp);
                                 PSET(F_RSW0 + c, s, 0.0f);
-                                PSET(F_RSC0 + c, s, 0.0f);
                                 PSET(F_R0 + c, s, 0.0f);  // the replay gathers the primal radiance itself
                             }
                         } else {
@@ -1152,7 +1200,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(FULL, n_max, o));
                 if (n_max) {
-                    const float2* lg = P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLog;
+                    const float2* lg = P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLogStride;
                     const float ox = nee_n ? PF(F_OX, s) : 0.0f, oy = nee_n ? PF(F_OY, s) : 0.0f, oz = nee_n ? PF(F_OZ, s) : 0.0f;
                     const float dx = nee_n ? PF(F_DX, s) : 0.0f, dy = nee_n ? PF(F_DY, s) : 0.0f, dz = nee_n ? PF(F_DZ, s) : 0.0f;
 #pragma unroll 1
@@ -1202,8 +1250,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (!phase) {
                         if (HAS_ADJ && (fl & FL_PASS_MASK) == (unsigned) PP_ADJ) {
                             // sampler.clone() position for the adjoint replay (:383)
-                            PU(F_CLONE_LO, s) = (uint32_t) r.state;
-                            PU(F_CLONE_HI, s) = (uint32_t) (r.state >> 32);
+                            __stcg(P.neelog + ((size_t) blockIdx.x * NSLOT + s) * kNeeLogStride + kNeeLog,
+                                   make_float2(__uint_as_float((uint32_t) r.state), __uint_as_float((uint32_t) (r.state >> 32))));
                             PU(F_NLOG, s) = 0u;
                         }
                         fl = ok ? (fl | FL_NEE_VALID) : (fl & ~FL_NEE_VALID);
@@ -1338,15 +1386,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     K.flush(P.counters);
 }
 
-// NSLOT: in-flight samples per CTA (one CTA per SM).  Per slot: 41 (backward) / 19 (forward) pool words + the 12-word
-// continuation record + 8 16-bit ring cells; what is left of the 227 KB is L1 for the walk table and the taps.
+// NSLOT: in-flight samples per CTA (one CTA per SM).  Per slot: 19 (forward) / 29 (adjoint) / 37 (DRT) pool words + the
+// 12-word continuation record + 8 16-bit ring cells.  The pools are sized to the 196 KB step of the shared-memory
+// carve-out (199 680 bytes usable): one step more leaves 28 instead of 60 KB of L1 for the walk table and the taps.
 // kind: KIND_FWD / KIND_ADJ / KIND_DRT
 inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
     const bool env = P.env_data != nullptr;
 #define UIVR_POOL_LAUNCH(KD, C, N, T, H, E)                                                             \
     do {                                                                                                \
-        const size_t smem = pool_smem_bytes<(KD) != KIND_FWD, N, E>() +                                 \
+        const size_t smem = pool_smem_bytes<KD, N, E>() +                                               \
                             (UIVR_POOL_SMEMTAB ? (size_t) P.wtab_words * 4 : 0);                        \
         if (smem > 232448) return -4; /* the walk table does not fit next to the pool */                \
         e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
@@ -1362,7 +1411,8 @@ inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cu
 #define UIVR_POOL_LAUNCH2(KD, N, T, H)                                                                  \
     do {                                                                                                \
         if (env) {                                                                                      \
-            if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H, true); else UIVR_POOL_LAUNCH(KD, false, N, T, H, true); \
+            constexpr int NE = pool_env_slots<KD, N>();                                                 \
+            if (counting) UIVR_POOL_LAUNCH(KD, true, NE, T, H, true); else UIVR_POOL_LAUNCH(KD, false, NE, T, H, true); \
         } else {                                                                                        \
             if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H, false); else UIVR_POOL_LAUNCH(KD, false, N, T, H, false); \
         }                                                                                               \
