@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
                     [--workload config3|dense|config5] [--scaling weak|strong] [--no-extras]
 
-A "step" = one forward render at `seed` + one DRT backward at `seed_grad` (primal replay +
-path-replay adjoint + DRT) of ONE view, i.e. what `mi.render` + `dr.backward(loss)` execute
+A "step" = one forward render at `seed` + one DRT backward at `seed_grad` (path-replay adjoint,
+which gathers the primal radiance itself, + DRT) of ONE view, i.e. what `mi.render` + `dr.backward(loss)` execute
 per view in the reference (optimize.py:345-350).  Default workload: BASELINE.json configs[2]
 (the configuration the metric is quoted on): 256^3 sigma_t + albedo grids, 512x512x64 spp,
 `volpathsimple-drt` flags, max_depth 64, supergrid factor 8.  At N>1 the pixels are sharded
@@ -244,7 +244,7 @@ def workload_config(name: str, n_gpus: int, spp: int, scaling: str, extra=None):
                        f"pixel-sharded x{n_gpus} (pixels interleaved across ranks), {scaling} scaling "
                        f"(spp {spp} in total), NCCL grad all-reduce in step",
         "l2_policy": f"inputs larger than L2 (sigma_t octets {oct_mb:.0f} MB + albedo {n ** 3 * 12 / 1e6:.0f} MB + "
-                     f"gradients {n ** 3 * 16 / 1e6:.0f} MB vs 126 MB L2); gradient buffers re-zeroed every step; "
+                     f"gradient accumulation tiles {n ** 3 * 32 / 1e6:.0f} MB vs 126 MB L2); gradient buffers re-zeroed every step; "
                      "seeds change every step",
     }
     if extra:
@@ -430,8 +430,8 @@ class Job:
         achieved = bytes_b / (t["bwd_ms"] * 1e-3) / 1e9
         out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                "traffic": None, "peak_source": peak_src,
-               "kernel": "backward pipeline, rank 0: k_pool<FWD> primal replay -> k_pool<ADJ> adjoint replay -> "
-                         "k_pool<DRT> (three slot-pool launches timed as one bracket)",
+               "kernel": "backward pipeline, rank 0: k_pool<ADJ> adjoint replay (gathers L itself) -> k_pool<DRT> -> folds "
+                         "of the gradient tiles (two slot-pool launches + two streaming folds timed as one bracket)",
                "kernel_ms": t["bwd_ms"], "algorithmic_bytes_per_launch": bytes_b,
                "bytes_per_sample": bytes_b / my_samples,
                "forward_kernel": {"kernel_ms": t["fwd_ms"], "algorithmic_bytes_per_launch": bytes_f,
