@@ -484,6 +484,9 @@ def run_native(args):
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION (the image's default) prints a banner on stdout; stdout carries ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
