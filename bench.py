@@ -229,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -484,9 +484,6 @@ def run_native(args):
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION (the image's default) prints a banner on stdout; stdout carries ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -638,11 +635,33 @@ def run_native(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
             line["parity"] = parity_in_child()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: native libraries that print there (NCCL's version banner under
+    NCCL_DEBUG=VERSION) are sent to stderr for the rest of the process; emit() writes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -660,10 +679,13 @@ def main():
     if args.warmup < 3 and args.impl == "native":
         print(f"note: warmup {args.warmup} < 3 breaks the timing rules; use only for profiling runs", file=sys.stderr)
     if args.parity_only:
-        print(json.dumps(parity_check()), flush=True)
+        _claim_stdout()
+        emit(parity_check())
         return 0
     if args.impl == "reference":
         return run_reference(args)
+    if "RANK" in os.environ or args.gpus <= 1:
+        _claim_stdout()
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch ourselves under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
