@@ -82,6 +82,19 @@ namespace uivr {
 #ifndef UIVR_POOL_FOCUS
 #define UIVR_POOL_FOCUS 1          // 1: the handler warps of a CTA prefer to serve the same queue (instruction cache)
 #endif
+// work items a CTA reserves from the global queue at a time (0: one global atomic per batch of 32).  Measured (profiles/
+// r02_history.md, call V): the forward kernel gains 5 % at 2048, the backward kernels lose 2 % at any size -- their
+// handler warps are the bottleneck, and a visit that finds the reservation empty while another warp refills it is a
+// wasted visit
+#ifndef UIVR_POOL_CHUNK_FWD
+#define UIVR_POOL_CHUNK_FWD 2048
+#endif
+#ifndef UIVR_POOL_CHUNK_ADJ
+#define UIVR_POOL_CHUNK_ADJ 0
+#endif
+#ifndef UIVR_POOL_CHUNK_DRT
+#define UIVR_POOL_CHUNK_DRT 0
+#endif
 #ifndef UIVR_POOL_AFFINITY
 #define UIVR_POOL_AFFINITY 0       // 1 (A/B build): handler warps of one SM sub-partition prefer one queue (L0 instruction cache)
 #endif
@@ -181,7 +194,11 @@ struct PoolCtl {
     int exhausted;   // the global sample queue is empty
     int abort;       // watchdog tripped: every warp leaves
     int focus;       // (UIVR_POOL_FOCUS) queue the handler warps currently prefer
+    unsigned long long chunk;  // (UIVR_POOL_CHUNK) the CTA's reservation from the global queue: next item << 24 | items left
+    int refill;      // lock: one warp at a time reserves the next chunk
 };
+static_assert(UIVR_POOL_CHUNK_FWD < (1 << 24) && UIVR_POOL_CHUNK_ADJ < (1 << 24) && UIVR_POOL_CHUNK_DRT < (1 << 24),
+              "24 bits count the items left of a chunk");
 
 // One decision of the supergrid DDA: the axis whose boundary the ray crosses first (ties: x before y before z, as
 // in the oracle's walk_next), the time of that crossing (= when the ray leaves the current cell) and the cell
@@ -273,6 +290,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     constexpr int F_NW0 = pool_fields(KIND);             // ENV only: NEE weight (3 words)
     constexpr bool HAS_ADJ = KIND == KIND_ADJ;           // adjoint replay (reservoir, NEE adjoint)
     constexpr bool HAS_DRT = KIND == KIND_DRT;           // DRT walk, DRT vertex, recursive path
+    // (the shared-memory-table A/B build keeps its mbarrier where the chunk lock lives)
+    constexpr unsigned kPoolChunk = UIVR_POOL_SMEMTAB ? 0u : (unsigned) (KIND == KIND_FWD ? UIVR_POOL_CHUNK_FWD : KIND == KIND_ADJ ? UIVR_POOL_CHUNK_ADJ : UIVR_POOL_CHUNK_DRT);
     constexpr int kPoolBlock = BLOCK;
     constexpr int kPoolHandlerWarps = HANDLERS;
     static_assert(NSLOT > (Q_NUM - 1) * 31 && NSLOT % 32 == 0, "pool too small for the full-batch scheduling rule");
@@ -321,7 +340,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         ctl->tail[threadIdx.x] = threadIdx.x == Q_FREE ? (unsigned) NSLOT : 0u;
         ctl->count[threadIdx.x] = threadIdx.x == Q_FREE ? NSLOT : 0;
     }
-    if (threadIdx.x == 0) { ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; ctl->focus = Q_FREE; }
+    if (threadIdx.x == 0) {
+        ctl->live = NSLOT; ctl->exhausted = 0; ctl->abort = 0; ctl->focus = Q_FREE;
+        ctl->chunk = 0ull; ctl->refill = 0;
+    }
 #if UIVR_POOL_SMEMTAB
     {
         const uint32_t mb = (uint32_t) __cvta_generic_to_shared(mbar);
@@ -1069,7 +1091,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 const unsigned fresh = __ballot_sync(FULL, act);
                 uint64_t item = 0;
                 bool mine = false;
-                if (exh == 0 && fresh) {
+                if (kPoolChunk == 0u && exh == 0 && fresh) {
                     const int leader = __ffs(fresh) - 1;
                     unsigned base = 0;
                     if ((int) lane == leader) base = atomicAdd(P.work_counter, (unsigned) __popc(fresh));
@@ -1079,8 +1101,52 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     if (mine) none_left = false;
                     if ((uint64_t) base + __popc(fresh) >= total && (int) lane == leader) ctl->exhausted = 1;
                 }
+                if constexpr (kPoolChunk != 0u) if (exh == 0 && fresh) {
+                    // The CTA reserves kPoolChunk items at a time (one global round trip per chunk instead of per
+                    // batch) and its warps take from the reservation with a shared-memory compare-and-swap.
+                    const int leader = __ffs(fresh) - 1;
+                    const unsigned n = (unsigned) __popc(fresh);
+                    unsigned base = 0, cnt = 0;
+                    if ((int) lane == leader) {
+                        for (;;) {
+                            unsigned long long cs = *((volatile unsigned long long*) &ctl->chunk);
+                            const unsigned left = (unsigned) (cs & 0xFFFFFFull);
+                            if (left) {
+                                const unsigned take = left < n ? left : n;
+                                const unsigned long long ns = (((cs >> 24) + take) << 24) | (unsigned long long) (left - take);
+                                if (atomicCAS(&ctl->chunk, cs, ns) == cs) { base = (unsigned) (cs >> 24); cnt = take; break; }
+                                continue;
+                            }
+                            // empty: one warp reserves the next chunk; the others come back later (their slots stay free)
+                            if (atomicCAS(&ctl->refill, 0, 1) != 0) break;
+                            cs = *((volatile unsigned long long*) &ctl->chunk);
+                            if (cs & 0xFFFFFFull) { atomicExch(&ctl->refill, 0); continue; }
+                            const unsigned gb = atomicAdd(P.work_counter, kPoolChunk);
+                            const uint64_t avail = (uint64_t) gb < total ? (total - gb < kPoolChunk ? total - gb : (uint64_t) kPoolChunk) : 0ull;
+                            if (avail == 0ull) {
+                                ctl->exhausted = 1;  // the global queue is empty: from now on free slots retire
+                            } else {
+                                cnt = avail < n ? (unsigned) avail : n;
+                                base = gb;
+                                if (avail > cnt)
+                                    *((volatile unsigned long long*) &ctl->chunk) =
+                                        ((unsigned long long) (gb + cnt) << 24) | (unsigned long long) (avail - cnt);
+                            }
+                            __threadfence_block();
+                            atomicExch(&ctl->refill, 0);
+                            break;
+                        }
+                    }
+                    base = __shfl_sync(FULL, base, leader);
+                    cnt = __shfl_sync(FULL, cnt, leader);
+                    const unsigned r = (unsigned) __popc(fresh & lt_mask);
+                    mine = act && r < cnt;
+                    item = (uint64_t) base + r;
+                    if (mine) none_left = false;
+                    else if (act) next = Q_FREE;  // nothing reserved right now: the slot stays free
+                }
                 // no more work items: the slot retires
-                const unsigned retire = __ballot_sync(FULL, act && none_left);
+                const unsigned retire = __ballot_sync(FULL, act && none_left && (kPoolChunk == 0u || exh != 0));
                 if (retire && lane == 0) atomicSub(&ctl->live, __popc(retire));
                 if (KIND == KIND_DRT) {
                     // DRT launch: the work items are the reservoir records of the adjoint launch
