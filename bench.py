@@ -119,12 +119,24 @@ class ClockSampler:
         self.path = f"/tmp/uivr_clocks_{os.getpid()}.csv"
 
     def start(self):
+        """Launch `nvidia-smi -lms 25` and wait for its first sample (start-up can take longer than a short timed
+        region); mark() then sets the beginning of the window whose samples count."""
+        self.offset = 0
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "25", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        t0 = time.time()
+        while time.time() - t0 < 3.0 and os.path.getsize(self.path) == 0:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples written from now on lie in the timed region."""
+        if self.proc is not None:
+            self.offset = os.path.getsize(self.path)
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -139,6 +151,7 @@ class ClockSampler:
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as f:
+            f.seek(self.offset)
             for line in f:
                 c = [x.strip() for x in line.split(",")]
                 if len(c) < 9:
@@ -370,11 +383,13 @@ class Job:
         """W untimed + K timed steps, CUDA events on the launching stream, max over ranks."""
         torch = self.torch
         import torch.distributed as dist
+        if clocks is not None:
+            clocks.start()   # running before the warm-up: its start-up is not part of the timed region
         for it in range(warmup):
             self.step(it)
         barrier()
         if clocks is not None:
-            clocks.start()
+            clocks.mark()
         l0 = self.ctx.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k_fwd, k_bwd = [], []
@@ -667,8 +682,8 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config3")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
