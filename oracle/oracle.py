@@ -291,6 +291,18 @@ def set_exit_mask(enable: bool) -> None:
     lib().uivr_oracle_set_exit_mask(1 if enable else 0)
 
 
+def set_nee_log_capacity(capacity: int) -> None:
+    """Counters only: model a collision log of `capacity` entries per NEE shadow walk (the CUDA adjoint kernel's
+    kNeeLog): walks with more tentative collisions are walked twice there as well.  0 = unlimited (default)."""
+    lib().uivr_oracle_set_nee_log_capacity(int(capacity))
+
+
+def nee_log_overflows() -> int:
+    f = lib().uivr_oracle_nee_log_overflows
+    f.restype = C.c_uint64
+    return int(f())
+
+
 def set_remaining_by_difference(enable: bool) -> None:
     """Test hook: Li of the adjoint as L - gathered (the CUDA pipeline's form) instead of the running subtraction."""
     lib().uivr_oracle_set_remaining_by_difference(1 if enable else 0)

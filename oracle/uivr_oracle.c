@@ -655,10 +655,11 @@ static int walk_next(const ctx_t* C, counters_t* K, walk_t* w, float u, float* t
 /* ------------------------------------------------------------------------------------ */
 
 static float ratio_track(const ctx_t* C, counters_t* K, const seg_t* s, rng_t* rng,
-                         const float* adjoint) {
+                         const float* adjoint, int* n_null) {
     walk_t w;
     walk_init(C, K, s, &w);
     float T = 1.0f;
+    int nn = 0; /* tentative collisions with sigma_n > 0: the ones the adjoint scatters at */
     for (;;) {
         float t, sb, p[3];
         if (!walk_next(C, K, &w, rng_f(rng), &t, &sb)) break;
@@ -666,6 +667,7 @@ static float ratio_track(const ctx_t* C, counters_t* K, const seg_t* s, rng_t* r
         float st = eval_sigma_t(C, K, p);
         float sn = sb - st;
         float tr = sn / sb; /* sb > 0 whenever a collision is returned */
+        if (tr > 0.0f) nn += 1;
         if (adjoint && tr > 0.0f) {
             float asum = (adjoint[0] + adjoint[1]) + adjoint[2];
             scatter_sigma(C, K, p, -asum / sn);
@@ -673,8 +675,18 @@ static float ratio_track(const ctx_t* C, counters_t* K, const seg_t* s, rng_t* r
         T *= tr;
         if (T == 0.0f) break;
     }
+    if (n_null) *n_null = nn;
     return T;
 }
+
+/* Test hook for the event counters only (results are unaffected): the CUDA adjoint kernel logs up to `capacity`
+ * tentative collisions of a shadow walk and scatters the NEE adjoint from the log; a walk with more collisions is
+ * walked a second time like here.  With a capacity set, only the second walks the CUDA path really skips are
+ * booked as "replay" events; 0 (default) books all of them. */
+static int g_nee_log_capacity = 0;
+static uint64_t g_nee_log_overflows = 0;
+void uivr_oracle_set_nee_log_capacity(int capacity) { g_nee_log_capacity = capacity; g_nee_log_overflows = 0; }
+uint64_t uivr_oracle_nee_log_overflows(void) { return g_nee_log_overflows; }
 
 /* sample_emitter_for_nee + sample_emitter (volpathsimple.py:380-433, a5/a6) for a constant
  * emitter and isotropic phase: contribution = beta * phase(1/4pi) * mis(1/2) * (Le*4pi) * T,
@@ -699,17 +711,22 @@ static void nee(const ctx_t* C, counters_t* K, const float p[3], const float bet
     seg_t s;
     int valid = worked && make_segment(C, p, w, &s);
     rng_t clone = *rng;
-    float T = valid ? ratio_track(C, K, &s, rng, NULL) : 0.0f;
+    float T = valid ? ratio_track(C, K, &s, rng, NULL, NULL) : 0.0f;
     for (int c = 0; c < 3; ++c) contrib[c] = wgt[c] * T;
     if (dL && valid) {
         float adj[3];
         for (int c = 0; c < 3; ++c) adj[c] = dL[c] * contrib[c];
         uint64_t d0 = clone.draws;
         counters_t before = *K;
-        ratio_track(C, K, &s, &clone, adj);
+        int n_null = 0;
+        ratio_track(C, K, &s, &clone, adj, &n_null);
         rng->draws += clone.draws - d0; /* the replay consumes (cloned) draws too */
-        for (int k = 0; k < UIVR_ORC_NUM_COUNTERS; ++k) K->r[k] += K->c[k] - before.c[k];
-        K->r[UIVR_ORC_RNG_DRAWS] += clone.draws - d0;
+        if (g_nee_log_capacity > 0 && n_null > g_nee_log_capacity) {
+            __atomic_fetch_add(&g_nee_log_overflows, 1, __ATOMIC_RELAXED);
+        } else {
+            for (int k = 0; k < UIVR_ORC_NUM_COUNTERS; ++k) K->r[k] += K->c[k] - before.c[k];
+            K->r[UIVR_ORC_RNG_DRAWS] += clone.draws - d0;
+        }
     }
 }
 

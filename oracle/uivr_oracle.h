@@ -129,6 +129,10 @@ void  uivr_oracle_build_majorant(const float* sigma_t, const int32_t res[3], flo
 void  uivr_oracle_build_exit_mask(const float* majorant, const int32_t mres[3], uint8_t* out);
 void  uivr_oracle_set_exit_mask(int enable);  /* test hook (default on) */
 void  uivr_oracle_set_remaining_by_difference(int enable);  /* test hook (default off), see path_loop */
+/* counters only: book as "replay" events just the second shadow walks a collision log of this capacity makes
+ * unnecessary (0: all of them); _overflows = shadow walks of the last backward calls that exceeded it */
+void  uivr_oracle_set_nee_log_capacity(int capacity);
+uint64_t uivr_oracle_nee_log_overflows(void);
 
 /* events of the primal pass inside the most recent backward call (they are part of its `counters`) */
 void  uivr_oracle_last_backward_primal_counters(uint64_t* out);

@@ -257,6 +257,64 @@ def test_backward_config1_homogeneous(uivr, oracle, dev, variant):
     assert rel_linf(da_g, da_o) < GRAD_TOL
 
 
+def _spiky_grids(n=16, seed=5):
+    """A thin medium under a high majorant: one dense voxel per supergrid cell lifts sigma_bar far above sigma_t, so
+    shadow walks see dozens of NULL collisions (sigma_n / sigma_bar ~ 0.98) without losing their transmittance."""
+    rng = np.random.default_rng(seed)
+    sig = (0.01 + 0.02 * rng.random((n, n, n, 1))).astype(np.float32)
+    sig[n // 2, n // 2, n // 2, 0] = 1.0
+    alb = (0.3 + 0.6 * rng.random((n, n, n, 3))).astype(np.float32)
+    return sig, alb
+
+
+NEE_LOG_CAPACITY = 32   # kNeeLog of csrc/uivr_pool.cuh
+
+
+def test_nee_collision_log_overflow_falls_back_to_the_second_walk(uivr, oracle, dev):
+    """The adjoint kernel scatters the NEE adjoint (:393-401, :483-492) from a log of the shadow walk's tentative
+    collisions; a walk with more collisions than the log holds must take the reference's route (walk the segment
+    again from the cloned sampler).  Scene: ~60 null collisions per crossing, so most shadow walks overflow."""
+    sig, alb = _spiky_grids()
+    vol = uivr.benchmark_scene(16, 24, 20, scale=60.0, majorant_resolution_factor=16)
+    props = dict(max_depth=6)
+    spp = 4
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 91, spp)
+    gimg = loss_grad(img)
+    sg = uivr.tea32(91, 1)
+    oracle.set_nee_log_capacity(NEE_LOG_CAPACITY)
+    try:
+        ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, spp, want_samples=True)
+        overflows = oracle.nee_log_overflows()
+        cnt_o = _pipeline_counters(oracle, cnt_o, 3, props)
+    finally:
+        oracle.set_nee_log_capacity(0)
+    assert overflows > 100, "the scene must exercise the fall-back"
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, sg, spp, dev, 3)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == cnt_o
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
+def test_backward_with_more_than_255_vertices_allowed(uivr, oracle, dev):
+    """Vertex descriptors of the slot-pool adjoint are indexed with 8 + 8 bits; a backward with max_depth > 255 is
+    routed to the one-sample-per-lane kernels (primal pass + adjoint replay, like the reference) -- same results."""
+    sig, alb = hetero_grids(12)
+    alb[...] = 0.97   # long paths
+    vol = uivr.benchmark_scene(12, 20, 16, scale=30.0, majorant_resolution_factor=4)
+    props = dict(max_depth=300)
+    spp = 4
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 5, spp)
+    gimg = loss_grad(img)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 6, spp, want_samples=True)
+    assert cnt_o["real_collisions"] > 5 * cnt_o["camera_hits"]   # the paths ARE long
+    ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, 6, spp, dev, 3)
+    assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))
+    assert cnt_g == _pipeline_counters(oracle, cnt_o, 3, props)
+    assert rel_linf(ds_g, ds_o) < GRAD_TOL
+    assert rel_linf(da_g, da_o) < GRAD_TOL
+
+
 # ---------------------------------------------------------------------------------------
 # sharding, autograd plumbing, host entry points, errors
 # ---------------------------------------------------------------------------------------

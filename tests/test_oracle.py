@@ -278,6 +278,33 @@ def test_ka3_white_furnace(uivr, oracle):
     assert np.abs(ds.sum()) < 0.03 * np.abs(ds2.sum())
 
 
+def test_nee_log_capacity_only_moves_event_counts(oracle, uivr):
+    """The collision-log model (uivr_oracle_set_nee_log_capacity) is bookkeeping for the parity tests of the CUDA
+    adjoint kernel: shadow walks with more tentative collisions than the log holds keep their second walk in the
+    main counters; results do not change."""
+    rng = np.random.default_rng(5)
+    n = 16
+    sig = (0.01 + 0.02 * rng.random((n, n, n, 1))).astype(np.float32)
+    sig[n // 2, n // 2, n // 2, 0] = 1.0
+    alb = (0.3 + 0.6 * rng.random((n, n, n, 3))).astype(np.float32)
+    vol = uivr.benchmark_scene(n, 24, 20, scale=60.0, majorant_resolution_factor=16)
+    props = dict(max_depth=6)
+    img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 91, 4)
+    gimg = loss_grad(img)
+    ds0, da0, _, cnt0 = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 7, 4, want_samples=True)
+    rep0 = oracle.last_backward_replay_counters()
+    oracle.set_nee_log_capacity(32)
+    try:
+        ds1, da1, _, cnt1 = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 7, 4, want_samples=True)
+        rep1 = oracle.last_backward_replay_counters()
+        over = oracle.nee_log_overflows()
+    finally:
+        oracle.set_nee_log_capacity(0)
+    assert cnt0 == cnt1 and rel_linf(ds1, ds0) < 1e-5 and rel_linf(da1, da0) < 1e-5
+    assert over > 100
+    assert 0 < rep1["sigma_taps"] < rep0["sigma_taps"] and rep1["rng_draws"] < rep0["rng_draws"]
+
+
 def test_radiance_still_to_come_must_be_subtracted_in_path_order(oracle, uivr):
     """Why the CUDA adjoint (which gathers L itself instead of running the reference's primal pass first) keeps the
     reference's ORDER of subtractions (volpathsimple.py:214) when it scatters the vertex gradients afterwards:
