@@ -66,6 +66,8 @@ struct uivr_ctx {
     float* st_dalbedo = nullptr;
     size_t st_vox = 0, st_pix = 0;
     bool st_params_valid = false;  // st_sigma / st_albedo hold the parameters of the last *_host call
+    cudaStream_t copy_stream = nullptr;   // *_host: the albedo upload runs beside the supergrid rebuild
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     // CUDA events bracketing the most recent path kernel: [0] forward, [1] backward
     cudaEvent_t ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     bool ev_valid[2] = {false, false};
@@ -225,6 +227,36 @@ int ensure_staging(uivr_ctx* ctx) {
 
 }  // namespace
 
+extern "C" int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream);
+
+namespace {
+
+// Upload of the parameters for the *_host entry points: sigma_t first, then the rebuild of everything derived from
+// it (corner octets, majorant supergrid, walk table) on the caller's stream WHILE the albedo, three times the bytes,
+// is still crossing the link on a second stream.
+int stage_params(uivr_ctx* ctx, const float* h_sigma_t, const float* h_albedo, cudaStream_t st) {
+    if (!ctx->copy_stream) {
+        UIVR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        UIVR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[0], cudaEventDisableTiming));
+        UIVR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[1], cudaEventDisableTiming));
+    }
+    ctx->st_params_valid = false;
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
+    // the albedo copy follows the sigma_t copy (and whatever the caller's stream still does with the staging buffer)
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], st));
+    UIVR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                                   ctx->copy_stream));
+    UIVR_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+    const int rc = uivr_update_medium(ctx, ctx->st_sigma, (void*) st);
+    UIVR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[1], 0));
+    if (rc) return rc;
+    ctx->st_params_valid = true;
+    return UIVR_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int uivr_version(void) { return 100; }
@@ -263,6 +295,9 @@ int uivr_destroy(uivr_ctx* ctx) {
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j)
             if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return UIVR_OK;
 }
@@ -732,11 +767,7 @@ int uivr_render_forward_host(uivr_ctx* ctx, const float* h_sigma_t, const float*
     cudaStream_t st = (cudaStream_t) stream;
     int rc = ensure_staging(ctx);
     if (rc) return rc;
-    ctx->st_params_valid = false;
-    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
-    UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
-    ctx->st_params_valid = true;
+    if ((rc = stage_params(ctx, h_sigma_t, h_albedo, st))) return rc;
     if ((rc = uivr_render_forward(ctx, ctx->st_albedo, seed, spp, shard, ctx->st_image, nullptr, stream))) return rc;
     UIVR_CUDA(ctx, cudaMemcpyAsync(h_image, ctx->st_image, ctx->st_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     UIVR_CUDA(ctx, cudaStreamSynchronize(st));
@@ -755,11 +786,7 @@ int uivr_render_backward_host(uivr_ctx* ctx, const float* h_sigma_t, const float
     int rc = ensure_staging(ctx);
     if (rc) return rc;
     if (h_sigma_t) {
-        ctx->st_params_valid = false;
-        UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_sigma, h_sigma_t, ctx->st_vox * sizeof(float), cudaMemcpyHostToDevice, st));
-        UIVR_CUDA(ctx, cudaMemcpyAsync(ctx->st_albedo, h_albedo, ctx->st_vox * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-        if ((rc = uivr_update_medium(ctx, ctx->st_sigma, stream))) return rc;
-        ctx->st_params_valid = true;
+        if ((rc = stage_params(ctx, h_sigma_t, h_albedo, st))) return rc;
     } else if (!ctx->st_params_valid || old_vox != ctx->st_vox || !ctx->have_medium) {
         return fail(ctx, UIVR_ERR_STATE, "no staged parameters: pass h_sigma_t / h_albedo, or call uivr_render_forward_host first");
     }
