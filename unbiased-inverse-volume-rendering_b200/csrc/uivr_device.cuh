@@ -349,6 +349,9 @@ UIVR_DEV void red_add(float* base, size_t idx, float v) {
     atomicAdd(base + idx, v);
 }
 
+// ACC: the caller guarantees the accumulation buffers (Params::dsigma4 / dalbedo4; the slot-pool backward always has
+// them), so only that path is compiled in -- the scatter is inlined at three sites of the adjoint kernel
+template <bool ACC = false>
 UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float g) {
     GridCell c;
     if (!grid_cell(P, px, py, pz, c)) return;
@@ -356,7 +359,7 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
     const size_t sy = (size_t) P.res[0], sz = (size_t) P.res[0] * P.res[1];
     const float ux = 1.0f - c.wx, uy = 1.0f - c.wy, uz = 1.0f - c.wz;
 #if UIVR_DSIGMA_TILED && !UIVR_SCATTER_MATCH
-    if (P.dsigma4) {
+    if (ACC || P.dsigma4) {
         // tile (x0 >> 1, y0 >> 1) of the copy picked by the parities of (x0, y0) holds (x0, y0), (x0+1, y0), (x0, y0+1),
         // (x0+1, y0+1) contiguously; a clamped neighbour (x1 == x0 at the border) folds into the slot of x0
         const int sx = c.x1 - c.x0, sy1 = c.y1 - c.y0;
@@ -387,6 +390,7 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
         }
         return;
     }
+    if (ACC) return;
 #endif
 #if UIVR_DSIGMA_V2 && !UIVR_SCATTER_MATCH
     const bool adjacent = c.x1 == c.x0 + 1;
@@ -415,6 +419,7 @@ UIVR_DEV void scatter_sigma(const Params& P, float px, float py, float pz, float
 #endif
 }
 
+template <bool ACC = false>
 UIVR_DEV void scatter_albedo(const Params& P, float px, float py, float pz, const float g[3]) {
     GridCell c;
     if (!grid_cell(P, px, py, pz, c)) return;
@@ -425,11 +430,12 @@ UIVR_DEV void scatter_albedo(const Params& P, float px, float py, float pz, cons
         const int x = (k & 1) ? c.x1 : c.x0, y = (k & 2) ? c.y1 : c.y0, z = (k & 4) ? c.z1 : c.z0;
         const float w = (((k & 1) ? c.wx : ux) * ((k & 2) ? c.wy : uy)) * ((k & 4) ? c.wz : uz);
 #if UIVR_DALBEDO_V4
-        if (P.dalbedo4) {
+        if (ACC || P.dalbedo4) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.dalbedo4 + (z * sz + y * sy + x)),
                          "f"(g[0] * w), "f"(g[1] * w), "f"(g[2] * w), "f"(0.0f) : "memory");
             continue;
         }
+        if (ACC) continue;
 #endif
         float* dst = P.dalbedo + 3 * (z * sz + y * sy + x);
         atomicAdd(dst + 0, g[0] * w);

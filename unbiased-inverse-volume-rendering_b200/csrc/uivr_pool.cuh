@@ -220,7 +220,24 @@ UIVR_DEV void walk_decide(float& tnx, float& tny, float& tnz, float adx, float a
 // and FETCH / ray-batch generation need them at several places (instruction-cache footprint of the handlers)
 __device__ __noinline__ void pool_seed_sampler(Rng& r, uint32_t seed, uint32_t idx) { r.seed_sampler(seed, idx); }
 
-UIVR_DEV void batch_film_position(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v) {
+// the slot-pool backward always scatters into the accumulation buffers (uivr_api.cu sets them up with the launch)
+#ifndef UIVR_POOL_ACC
+#define UIVR_POOL_ACC 1   // 0 (A/B build): keep the scalar / v2 fall-back paths of the scatter in the pool kernels
+#endif
+constexpr bool kPoolAcc = UIVR_POOL_ACC && UIVR_DSIGMA_TILED && UIVR_DALBEDO_V4 && !UIVR_SCATTER_MATCH;
+#ifndef UIVR_POOL_COLD_NOINLINE
+#define UIVR_POOL_COLD_NOINLINE 0   // 1 (A/B build): ray-batch ray generation and the log-overflow scatter out of line
+#endif
+#if UIVR_POOL_COLD_NOINLINE
+__device__ __noinline__ void pool_scatter_sigma_cold(const Params& P, float px, float py, float pz, float g) {
+    scatter_sigma<kPoolAcc>(P, px, py, pz, g);
+}
+__device__ __noinline__
+#else
+UIVR_DEV void pool_scatter_sigma_cold(const Params& P, float px, float py, float pz, float g) { scatter_sigma<kPoolAcc>(P, px, py, pz, g); }
+UIVR_DEV
+#endif
+void batch_film_position(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v) {
     batch_film_position_t(P, b, idx, F, u, v, [](Rng& r, uint32_t sd, uint32_t i) { pool_seed_sampler(r, sd, i); });
 }
 
@@ -747,7 +764,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             }
                         } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
                             // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)   [replay walk: log overflow only]
-                            scatter_sigma(P, px, py, pz, -PF(F_ASUM, s) / sn);
+                            pool_scatter_sigma_cold(P, px, py, pz, -PF(F_ASUM, s) / sn);
                             K.add(C_SSCAT, 1);
                         } else if (HAS_ADJ && mode == PM_NEE && q > 0.0f) {
                             // log the collision for the NEE adjoint (scattered at the NEE end, when its weight is known)
@@ -1273,7 +1290,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     for (unsigned i = 0; i < n_max; ++i) {
                         if (i < nee_n) {
                             const float2 e = __ldcg(lg + i);
-                            scatter_sigma(P, fmaf(e.x, dx, ox), fmaf(e.x, dy, oy), fmaf(e.x, dz, oz), -nee_a / e.y);
+                            scatter_sigma<kPoolAcc>(P, fmaf(e.x, dx, ox), fmaf(e.x, dy, oy), fmaf(e.x, dz, oz), -nee_a / e.y);
                             K.add(C_SSCAT, 1);
                         }
                     }
@@ -1368,10 +1385,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             px = fmaf(tk, sc_dx, sc_ox); py = fmaf(tk, sc_dy, sc_oy); pz = fmaf(tk, sc_dz, sc_oz);
                             g = sc_g;
                         }
-                        scatter_sigma(P, px, py, pz, g);
+                        scatter_sigma<kPoolAcc>(P, px, py, pz, g);
                         K.add(C_SSCAT, 1);
                         if (k == 4) {
-                            scatter_albedo(P, px, py, pz, sc_ga);
+                            scatter_albedo<kPoolAcc>(P, px, py, pz, sc_ga);
                             K.add(C_ASCAT, 1);
                         }
                     }
