@@ -228,10 +228,16 @@ int uivr_check_watchdog(uivr_ctx* ctx, uint32_t out[64], void* stream);
 int uivr_get_launch_count(const uivr_ctx* ctx, uint64_t* out);
 /* kernel variant: 3 (default) = persistent slot-pool kernels (CTA-wide compaction of live rays through
  * shared-memory queues; walker warps run the supergrid DDA, handler warps everything else in full batches;
- * the backward runs as primal replay -> adjoint replay -> DRT launches that hand per-sample state through
- * context-owned HBM scratch); 1 = one sample per lane, run to completion (in-GPU cross-check, and the
- * O(n^2) `use_drt_subsampling = False` mode).  Other values: UIVR_ERR_INVALID. */
+ * the backward runs as adjoint replay (which gathers the primal radiance itself: no primal pass) -> DRT launch,
+ * handing per-sample state through context-owned HBM scratch); 1 = one sample per lane, run to completion
+ * (in-GPU cross-check, the O(n^2) `use_drt_subsampling = False` mode, and backward calls with max_depth > 255).
+ * Other values: UIVR_ERR_INVALID. */
 int uivr_set_variant(uivr_ctx* ctx, int variant);
+/* Test hook for the watchdog of the slot-pool kernels: a walker warp that steps more than `limit` supergrid cells
+ * in one go trips it (default 2^24: never on a sane scene; limit <= 0 restores the default).  With a tiny limit
+ * every render call aborts in bounded time and uivr_check_watchdog returns UIVR_ERR_WATCHDOG -- which is what
+ * tests/test_gpu_parity.py checks: a scheduling bug must end as an error, not as a hung GPU. */
+int uivr_debug_set_walk_limit(uivr_ctx* ctx, int limit);
 
 /* ---- device primitives exposed for bit-exactness tests (all arrays are DEVICE pointers) ---- */
 /* out[0:n] = -ln(1-u);  s,c = sin/cos(2 pi x);  sampler floats of stream (seed, idx) */

@@ -315,6 +315,30 @@ def test_backward_with_more_than_255_vertices_allowed(uivr, oracle, dev):
     assert rel_linf(da_g, da_o) < GRAD_TOL
 
 
+def test_watchdog_ends_a_runaway_kernel_as_an_error(uivr, oracle, dev):
+    """A scheduling bug of the persistent kernels must end as UIVR_ERR_WATCHDOG, not as a hung GPU.  The test hook
+    makes every longer walk look like a runaway one: the launch aborts (all warps leave through the abort flag,
+    spin loops through their own limits), uivr_check_watchdog reports it, and the context works again afterwards."""
+    sig, alb = hetero_grids(16)
+    vol = uivr.benchmark_scene(16, 48, 32, scale=8.0, majorant_resolution_factor=2)
+    props = dict(max_depth=16)
+    scene = uivr.Scene(vol, device=0)
+    integ = uivr.VolpathSimpleIntegrator(props)
+    params = {"m.sigma_t.data": _gpu(sig, dev), "m.albedo.data": _gpu(alb, dev)}
+    scene.ctx.debug_set_walk_limit(1)
+    integ.render(scene, params, seed=3, spp=8)
+    with pytest.raises(uivr.NativeError, match="watchdog|-5"):
+        scene.ctx.check_watchdog()
+    integ.render_backward(scene, params, _gpu(np.full((32, 48, 3), 1e-3, np.float32), dev), seed=4, spp=4)
+    with pytest.raises(uivr.NativeError, match="watchdog|-5"):
+        scene.ctx.check_watchdog()
+    scene.ctx.debug_set_walk_limit(0)
+    img = integ.render(scene, params, seed=3, spp=8)
+    scene.ctx.check_watchdog()   # silent again
+    img_o, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 3, 8)
+    assert np.abs(img.cpu().numpy() - img_o).max() < IMAGE_TOL
+
+
 # ---------------------------------------------------------------------------------------
 # sharding, autograd plumbing, host entry points, errors
 # ---------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ EXPORTS = [
     "uivr_set_integrator", "uivr_update_medium", "uivr_render_forward", "uivr_render_backward",
     "uivr_render_forward_host", "uivr_render_backward_host", "uivr_set_counting",
     "uivr_reset_counters", "uivr_get_counters", "uivr_get_kernel_ms", "uivr_get_launch_count",
-    "uivr_set_variant", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
+    "uivr_set_variant", "uivr_debug_set_walk_limit", "uivr_check_watchdog", "uivr_adam_step", "uivr_set_batch", "uivr_upsample2x",
     "uivr_test_neg_log1m", "uivr_test_sincos2pi", "uivr_test_sampler", "uivr_test_sigma_lookup",
     "uivr_get_majorant", "uivr_get_walk_table", "uivr_tea32", "uivr_alt_seed", "uivr_alt_seed_batch",
     "uivr_nerf_forward", "uivr_nerf_backward", "uivr_test_exp", "uivr_set_envmap", "uivr_test_atan2_turns",
@@ -112,6 +112,7 @@ def lib():
         "uivr_get_kernel_ms": ([vp, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "uivr_get_launch_count": ([vp, C.POINTER(C.c_uint64)], C.c_int),
         "uivr_set_variant": ([vp, C.c_int], C.c_int),
+        "uivr_debug_set_walk_limit": ([vp, C.c_int], C.c_int),
         "uivr_check_watchdog": ([vp, C.POINTER(C.c_uint32), vp], C.c_int),
         "uivr_adam_step": ([vp, fp, fp, fp, fp, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float, i32,
                             C.c_float, C.c_float, vp], C.c_int),
@@ -224,6 +225,10 @@ class Context:
 
     def set_variant(self, variant: int):
         self._check(self._L.uivr_set_variant(self._h, int(variant)), "uivr_set_variant")
+
+    def debug_set_walk_limit(self, limit: int):
+        """Test hook: trip the slot-pool watchdog after `limit` supergrid cells per walk quantum (<= 0: default)."""
+        self._check(self._L.uivr_debug_set_walk_limit(self._h, int(limit)), "uivr_debug_set_walk_limit")
 
     def set_counting(self, enable: bool):
         self._check(self._L.uivr_set_counting(self._h, int(bool(enable))), "uivr_set_counting")

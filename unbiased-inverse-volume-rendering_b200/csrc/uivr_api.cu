@@ -33,6 +33,7 @@ struct uivr_ctx {
     unsigned long long* counters = nullptr;
     unsigned int* work_counter = nullptr;
     unsigned int* debug = nullptr;  // [64] watchdog record of the slot-pool kernel
+    int walk_limit = kPoolWalkLimit;  // (uivr_debug_set_walk_limit)
     // scratch of the backward pipeline: the reservoir records handed from the adjoint launch to the DRT launch
     uint32_t* records = nullptr;
     size_t records_cap = 0;
@@ -188,6 +189,7 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.counters = ctx->counters;
     P.work_counter = ctx->work_counter;
     P.debug = ctx->debug;
+    P.walk_limit = ctx->walk_limit;
     return UIVR_OK;
 }
 
@@ -382,6 +384,12 @@ int uivr_set_integrator(uivr_ctx* ctx, const uivr_integrator_props* props) {
 int uivr_set_counting(uivr_ctx* ctx, int enable) {
     if (!ctx) return UIVR_ERR_INVALID;
     ctx->counting = enable ? 1 : 0;
+    return UIVR_OK;
+}
+
+int uivr_debug_set_walk_limit(uivr_ctx* ctx, int limit) {
+    if (!ctx) return UIVR_ERR_INVALID;
+    ctx->walk_limit = limit > 0 ? limit : kPoolWalkLimit;
     return UIVR_OK;
 }
 

@@ -95,9 +95,6 @@ namespace uivr {
 #ifndef UIVR_POOL_CHUNK_DRT
 #define UIVR_POOL_CHUNK_DRT 0
 #endif
-#ifndef UIVR_POOL_AFFINITY
-#define UIVR_POOL_AFFINITY 0       // 1 (A/B build): handler warps of one SM sub-partition prefer one queue (L0 instruction cache)
-#endif
 #ifndef UIVR_POOL_SMEMTAB
 #define UIVR_POOL_SMEMTAB 0   // 1 (A/B build): the whole walk table lives in shared memory, loaded once per CTA with
 #endif                        //    cp.async.bulk (TMA bulk copy) + mbarrier; needs small pools (the table is 166 KB at 256^3 / 8)
@@ -218,44 +215,52 @@ UIVR_DEV void walk_decide(float& tnx, float& tny, float& tnz, float adx, float a
 
 // sampler.seed(seed, wavefront) for one lane, out of line: TEA + the PCG32 seeding sequence are ~150 instructions
 // and FETCH / ray-batch generation need them at several places (instruction-cache footprint of the handlers)
+#ifndef UIVR_POOL_SEED_INLINE
+#define UIVR_POOL_SEED_INLINE 1   // (the out-of-line call cost 1.5 %: call AC)
+#endif
+#if UIVR_POOL_SEED_INLINE
+UIVR_DEV void pool_seed_sampler(Rng& r, uint32_t seed, uint32_t idx) { r.seed_sampler(seed, idx); }
+#else
 __device__ __noinline__ void pool_seed_sampler(Rng& r, uint32_t seed, uint32_t idx) { r.seed_sampler(seed, idx); }
+#endif
 
 // the slot-pool backward always scatters into the accumulation buffers (uivr_api.cu sets them up with the launch)
 #ifndef UIVR_POOL_ACC
 #define UIVR_POOL_ACC 1   // 0 (A/B build): keep the scalar / v2 fall-back paths of the scatter in the pool kernels
 #endif
 constexpr bool kPoolAcc = UIVR_POOL_ACC && UIVR_DSIGMA_TILED && UIVR_DALBEDO_V4 && !UIVR_SCATTER_MATCH;
-#ifndef UIVR_POOL_COLD_NOINLINE
-#define UIVR_POOL_COLD_NOINLINE 0   // 1 (A/B build): ray-batch ray generation and the log-overflow scatter out of line
-#endif
-#if UIVR_POOL_COLD_NOINLINE
-__device__ __noinline__ void pool_scatter_sigma_cold(const Params& P, float px, float py, float pz, float g) {
-    scatter_sigma<kPoolAcc>(P, px, py, pz, g);
-}
-__device__ __noinline__
-#else
-UIVR_DEV void pool_scatter_sigma_cold(const Params& P, float px, float py, float pz, float g) { scatter_sigma<kPoolAcc>(P, px, py, pz, g); }
-UIVR_DEV
-#endif
-void batch_film_position(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v) {
+UIVR_DEV void batch_film_position(const Params& P, uint32_t b, uint32_t idx, float F[15], float& u, float& v) {
     batch_film_position_t(P, b, idx, F, u, v, [](Rng& r, uint32_t sd, uint32_t i) { pool_seed_sampler(r, sd, i); });
 }
 
-// watchdog record (cold code, kept out of line): reason + queue state; every warp of the CTA leaves
-__device__ __noinline__ void pool_trip(PoolCtl* ctl, unsigned* debug, unsigned why) {
+// Watchdog record: the thread that trips a limit raises the CTA's abort flag and leaves its reason in the debug buffer;
+// the queue state is dumped at the end of the kernel by the CTA that tripped first.  Out of line by measurement
+// (call AG: 786 vs 775 Msamples/s inline), like the sampler seeding is inline by measurement -- at this code size
+// either choice moves the register allocation and the layout of the handler bodies by a percent.
+#ifndef UIVR_POOL_TRIP_INLINE
+#define UIVR_POOL_TRIP_INLINE 0
+#endif
+#if UIVR_POOL_TRIP_INLINE
+UIVR_DEV
+#else
+__device__ __noinline__
+#endif
+void pool_trip(PoolCtl* ctl, unsigned* debug, unsigned why) {
     if (atomicExch(&ctl->abort, 1) == 0 && debug) {
         if (atomicExch(&debug[0], why) == 0u) {
             debug[1] = blockIdx.x;
             debug[2] = threadIdx.x;
-            for (int q = 0; q < Q_NUM; ++q) {
-                debug[4 + 3 * q] = ctl->head[q];
-                debug[5 + 3 * q] = ctl->tail[q];
-                debug[6 + 3 * q] = (unsigned) ctl->count[q];
-            }
-            debug[4 + 3 * Q_NUM] = (unsigned) ctl->live;
-            debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
         }
     }
+}
+__device__ __noinline__ void pool_trip_dump(const PoolCtl* ctl, unsigned* debug) {
+    for (int q = 0; q < Q_NUM; ++q) {
+        debug[4 + 3 * q] = ctl->head[q];
+        debug[5 + 3 * q] = ctl->tail[q];
+        debug[6 + 3 * q] = (unsigned) ctl->count[q];
+    }
+    debug[4 + 3 * Q_NUM] = (unsigned) ctl->live;
+    debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
 }
 
 // kernel kinds: the forward / primal kernel and the two halves of the backward pipeline, which runs the
@@ -301,7 +306,9 @@ constexpr int pool_env_slots() {
 
 // BLOCK threads per CTA (one CTA per SM), of which HANDLERS warps serve the transition queues and the
 // rest walk
-template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS, bool ENV = false>
+// BATCH: ray-batch mode (uivr_set_batch): its ray generation is compiled into its own instances, the sensor-mode
+// kernels do not carry it (every instruction of the handler bodies counts: profiles/r02_history.md, call AB)
+template <int KIND, bool COUNT, int NSLOT, int BLOCK, int HANDLERS, bool ENV = false, bool BATCH = false>
 __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
     constexpr bool BWD = KIND != KIND_FWD;               // any gradient work
     constexpr int F_NW0 = pool_fields(KIND);             // ENV only: NEE weight (3 words)
@@ -580,7 +587,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                 n_walk = __popc(__ballot_sync(FULL, wst == W_WALKING));
                 if (n_walk <= n_stop) { wphase = 0; break; }
                 if ((it & 3) == 0) {
-                    if (it > kPoolWalkLimit) { trip(0x400u); wst = W_END; wphase = 0; break; }
+                    if (it > P.walk_limit) { trip(0x400u); wst = W_END; wphase = 0; break; }
                     // a warp that started short of lanes leaves as soon as the queue can fill them
                     if (short_handed &&
                         __shfl_sync(FULL, (lane == 0) ? *((volatile int*) &ctl->count[Q_WALK]) : 0, 0) >= kWalkQuantum) {
@@ -632,44 +639,34 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
         int last_work = Q_FREE;
         unsigned idle_ns = 32;
         for (;;) {
-            if (__shfl_sync(FULL, *((volatile int*) &ctl->abort), 0)) break;
-            // per-queue fill levels, one queue per lane
-            const int cnt_all = (lane < Q_NUM) ? *((volatile int*) &ctl->count[lane]) : 0;
+            // one shared-memory read per lane: the fill level of queue `lane` (lanes 0..7), the queue the handler warps
+            // currently prefer (lane 8), the abort flag (lane 9)
+            const int* cw = lane < Q_NUM ? &ctl->count[lane] : (lane == 8 ? &ctl->focus : &ctl->abort);
+            const int cv = lane <= 9 ? *((volatile const int*) cw) : 0;
+            if (__shfl_sync(FULL, cv, 9)) break;
+            const int cnt_all = (lane < Q_NUM) ? cv : 0;
             const int cnt = (lane != Q_WALK) ? cnt_all : 0;
-            // the walkers are running dry: accept smaller batches rather than let them idle
-            const int min_batch = __shfl_sync(FULL, cnt_all, Q_WALK) < kPoolStarveBelow ? kPoolMinBatch : 32;
             int work = -1;
             bool exact = true;
+#if UIVR_POOL_FOCUS
+            // Fast path (two dependent shuffles): the preferred queue still holds a full batch.  All handler warps of
+            // the CTA on the same handler body is what the instruction caches like (profiles/r02_history.md).
+            const int focus = __shfl_sync(FULL, cv, 8) & 7;
+            if (__shfl_sync(FULL, cnt, focus) >= 32) {
+                work = focus;
+            } else
+#endif
             {
-                // Stay on the queue served last while it still holds a full batch (its handler code is
-                // hot in the instruction caches), else take the fullest queue.
+                // the walkers are running dry: accept smaller batches rather than let them idle
+                const int min_batch = __shfl_sync(FULL, cnt_all, Q_WALK) < kPoolStarveBelow ? kPoolMinBatch : 32;
+                // else the fullest queue (which becomes the preferred one), else the queue served last
                 const int c_last = __shfl_sync(FULL, cnt, last_work & 31);
                 int best = (cnt << 3) | (int) lane;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
                 best = __shfl_sync(FULL, best, 0);
 #if UIVR_POOL_FOCUS
-                const int focus = __shfl_sync(FULL, *((volatile int*) &ctl->focus), 0) & 7;
-#endif
-#if UIVR_POOL_AFFINITY
-                // Queue affinity by scheduler (warp_id & 3 = the SM sub-partition a warp lives on, each with its own
-                // L0 instruction cache): the handler warps of one sub-partition prefer one handler body.
-                const int wq = warp_id & 3;
-                const int pref0 = wq == 0 ? Q_TAP : wq == 1 ? Q_FREE : wq == 2 ? (HAS_ADJ ? Q_VERTEX_ADJ : Q_VERTEX) : Q_PATH_END;
-                const int pref1 = wq == 3 ? (HAS_ADJ ? Q_SCATTER : Q_NEE_END) : pref0;
-                const int pref2 = wq == 3 ? Q_NEE_END : pref0;
-                if (__shfl_sync(FULL, cnt, pref0) >= 32) {
-                    work = pref0;
-                } else if (__shfl_sync(FULL, cnt, pref1) >= 32) {
-                    work = pref1;
-                } else if (__shfl_sync(FULL, cnt, pref2) >= 32) {
-                    work = pref2;
-                } else
-#endif
-#if UIVR_POOL_FOCUS
-                if (__shfl_sync(FULL, cnt, focus) >= 32) {
-                    work = focus;
-                } else if ((best >> 3) >= 32) {
+                if ((best >> 3) >= 32) {
                     work = best & 7;
                     if (lane == 0) ctl->focus = work;
                 } else
@@ -700,7 +697,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             int next = -1;
             bool resume = false;  // next == Q_WALK continues a walk after a null collision (no set-up)
             // gradient scatter request of the handlers (executed at one site below)
-            bool sc_taps = false, sc_ff = false;
+            bool sc_taps = false, sc_ff = false, sc_alb = true;  // sc_alb: the vertex request also scatters d albedo
             float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
             float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
             float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
@@ -763,9 +760,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                                 fl |= FL_DRT_FOUND;
                             }
                         } else if (HAS_ADJ && mode == PM_NEE_ADJ && q > 0.0f) {
-                            // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)   [replay walk: log overflow only]
-                            pool_scatter_sigma_cold(P, px, py, pz, -PF(F_ASUM, s) / sn);
-                            K.add(C_SSCAT, 1);
+                            // ratio tracking adjoint: -sum(adj)/sigma_n (:483-492)   [replay walk: log overflow only;
+                            // executed at the scatter site below, which keeps this rare route out of the tap handler]
+                            sc_vx = px; sc_vy = py; sc_vz = pz;
+                            sc_gs = -PF(F_ASUM, s) / sn;
+                            sc_ff = true;
+                            sc_alb = false;
                         } else if (HAS_ADJ && mode == PM_NEE && q > 0.0f) {
                             // log the collision for the NEE adjoint (scattered at the NEE end, when its weight is known)
                             const unsigned nl = PU(F_NLOG, s);
@@ -1219,7 +1219,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                         Seg sg;
                         float F[15], fu, fv;
-                        if (P.sensors) {
+                        if (BATCH) {
                             // ray-batch mode: "pix" is the batch element; the path sampler draws no jitter (batched.py:390)
                             batch_film_position(P, pix, idx, F, fu, fv);
                         } else {
@@ -1387,7 +1387,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                         scatter_sigma<kPoolAcc>(P, px, py, pz, g);
                         K.add(C_SSCAT, 1);
-                        if (k == 4) {
+                        if (k == 4 && sc_alb) {
                             scatter_albedo<kPoolAcc>(P, px, py, pz, sc_ga);
                             K.add(C_ASCAT, 1);
                         }
@@ -1466,6 +1466,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 #undef CU
 #undef CF
 #undef CSET
+    // (after an abort) the thread that recorded the reason dumps the queue state of its CTA
+    if (*((volatile int*) &ctl->abort) && P.debug && P.debug[1] == blockIdx.x && P.debug[2] == threadIdx.x && P.debug[0] != 0u)
+        pool_trip_dump(ctl, P.debug);
     K.flush(P.counters);
 }
 
@@ -1476,28 +1479,33 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
 inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cudaStream_t st) {
     cudaError_t e;
     const bool env = P.env_data != nullptr;
-#define UIVR_POOL_LAUNCH(KD, C, N, T, H, E)                                                             \
+    const bool batch = P.sensors != nullptr;
+#define UIVR_POOL_LAUNCH(KD, C, N, T, H, E, B)                                                          \
     do {                                                                                                \
         const size_t smem = pool_smem_bytes<KD, N, E>() +                                               \
                             (UIVR_POOL_SMEMTAB ? (size_t) P.wtab_words * 4 : 0);                        \
         if (smem > 232448) return -4; /* the walk table does not fit next to the pool */                \
-        e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        e = cudaFuncSetAttribute(k_pool<KD, C, N, T, H, E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
         if (e != cudaSuccess) return -2;                                                                \
         if (UIVR_POOL_SETMAXNREG) {                                                                     \
             /* setmaxnreg.inc waits for registers of the CTA's pool: the pool must be what the budget assumes */ \
             cudaFuncAttributes fa;                                                                      \
-            if (cudaFuncGetAttributes(&fa, k_pool<KD, C, N, T, H, E>) != cudaSuccess ||                 \
+            if (cudaFuncGetAttributes(&fa, k_pool<KD, C, N, T, H, E, B>) != cudaSuccess ||              \
                 fa.numRegs != (65536 / (T)) / 8 * 8) return -3;                                         \
         }                                                                                               \
-        k_pool<KD, C, N, T, H, E><<<num_sms, T, smem, st>>>(P);                                         \
+        k_pool<KD, C, N, T, H, E, B><<<num_sms, T, smem, st>>>(P);                                      \
+    } while (0)
+#define UIVR_POOL_LAUNCH3(KD, C, N, T, H, E)                                                            \
+    do {                                                                                                \
+        if (batch) UIVR_POOL_LAUNCH(KD, C, N, T, H, E, true); else UIVR_POOL_LAUNCH(KD, C, N, T, H, E, false); \
     } while (0)
 #define UIVR_POOL_LAUNCH2(KD, N, T, H)                                                                  \
     do {                                                                                                \
         if (env) {                                                                                      \
             constexpr int NE = pool_env_slots<KD, N>();                                                 \
-            if (counting) UIVR_POOL_LAUNCH(KD, true, NE, T, H, true); else UIVR_POOL_LAUNCH(KD, false, NE, T, H, true); \
+            if (counting) UIVR_POOL_LAUNCH3(KD, true, NE, T, H, true); else UIVR_POOL_LAUNCH3(KD, false, NE, T, H, true); \
         } else {                                                                                        \
-            if (counting) UIVR_POOL_LAUNCH(KD, true, N, T, H, false); else UIVR_POOL_LAUNCH(KD, false, N, T, H, false); \
+            if (counting) UIVR_POOL_LAUNCH3(KD, true, N, T, H, false); else UIVR_POOL_LAUNCH3(KD, false, N, T, H, false); \
         }                                                                                               \
     } while (0)
     switch (kind) {
@@ -1507,6 +1515,7 @@ inline int launch_pool(int num_sms, int kind, bool counting, const Params& P, cu
         default: return -1;
     }
 #undef UIVR_POOL_LAUNCH2
+#undef UIVR_POOL_LAUNCH3
 #undef UIVR_POOL_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
