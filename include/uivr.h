@@ -150,8 +150,9 @@ int uivr_update_medium(uivr_ctx* ctx, const float* d_sigma_t, void* stream);
 int uivr_render_forward(uivr_ctx* ctx, const float* d_albedo, uint32_t seed, int32_t spp,
                         const uivr_shard* shard, float* d_image, float* d_sample_L, void* stream);
 
-/* dr.backward(loss) -> RBIntegrator.render_backward (batched.py:212-326): primal replay at
- * seed_grad, then the path-replay adjoint with the three gradient estimators + DRT.
+/* dr.backward(loss) -> RBIntegrator.render_backward (batched.py:212-326): the primal radiance at
+ * seed_grad (gathered inside the adjoint replay by the slot-pool kernels, a separate primal pass in the
+ * one-sample-per-lane kernels), the path-replay adjoint with the three gradient estimators, then DRT.
  * d_dsigma_t [Z,Y,X] and d_dalbedo [Z,Y,X,3] are OVERWRITTEN with this call's gradients. */
 int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_grad_image,
                          uint32_t seed_grad, int32_t spp_grad, const uivr_shard* shard,

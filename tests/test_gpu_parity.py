@@ -859,7 +859,7 @@ def test_upsample_grid_matches_scipy_zoom(uivr, dev, shape):
 
 def test_upsample_params_in_the_loop(uivr, dev):
     """optimize.py:228-252 inside a short optimisation: grids double, Adam state of the re-sized
-    tensors starts over, the supergrid factor is re-derived, rendering continues at the new resolution."""
+    tensors starts over, the medium is rebuilt, rendering continues at the new resolution."""
     n, w, h, spp = 8, 24, 24, 16
     sig_t, alb_t = hetero_grids(16, seed=4)
     vol = uivr.benchmark_scene(n, w, h, scale=6.0, majorant_resolution_factor=uivr.adjust_majorant_res_factor(8, (n, n, n, 1)))
@@ -876,7 +876,8 @@ def test_upsample_params_in_the_loop(uivr, dev):
         uivr.optimization_step(scene, integ, opt, sensors, refs, it, spp)
     shapes = uivr.upsample_params(scene, opt, 8)
     assert shapes["m.sigma_t.data"] == (16, 16, 16, 1) and shapes["m.albedo.data"] == (16, 16, 16, 3)
-    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 4
+    # optimize.py:249-250: after the step the medium is back on the CONFIGURED factor (keep_adjusted=True: 4)
+    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 8
     assert set(opt.t.values()) == {0} and float(opt.m["m.sigma_t.data"].abs().max()) == 0.0
     losses = [uivr.optimization_step(scene, integ, opt, sensors, refs, 3 + it, spp) for it in range(3)]
     scene.ctx.check_watchdog()

@@ -264,6 +264,14 @@ def test_optimization_config_matches_reference(uivr):
         assert sorted(cfg.upsample_at) == list(g[f"upsample_at/{i}"])
         assert np.array_equal(np.array([cfg.should_upsample(it) for it in range(n_iter)]), g[f"should_upsample/{i}"])
     d = uivr.OptimizationConfig("x", spp=4, n_iter=10, lr=1.0)
+    # positional construction binds the reference's fields (opt_config.py:14-37, in this order)
+    import dataclasses
+    assert [f.name for f in dataclasses.fields(uivr.OptimizationConfig)] == [
+        "name", "spp", "n_iter", "lr", "primal_spp_factor", "batch_size", "lr_schedule", "upsample", "base_seed",
+        "render_initial", "render_final", "preview_stride", "checkpoint_initial", "checkpoint_final", "checkpoint_stride",
+        "preview_spp", "opt_type", "opt_args", "loss"]
+    pos = uivr.OptimizationConfig("x", 4, 100, 1.0, 64, None, uivr.Schedule.Last25, [0.5])
+    assert pos.lr_schedule == uivr.Schedule.Last25 and pos.upsample == [0.5] and pos.base_seed == 988378
     assert (d.primal_spp_factor, d.batch_size, d.base_seed, d.preview_stride, d.checkpoint_stride, d.opt_type) == \
         (64, None, 988378, 100, 1000, "adam")
     assert d.loss is uivr.losses.l1 and d.render_initial and d.render_final and d.checkpoint_initial and d.checkpoint_final
@@ -505,7 +513,8 @@ def test_run_optimization_control_flow_with_a_stand_in_renderer(uivr, tmp_path, 
     shapes = [c[1][0] for c in calls if c[0] == "update_medium"]
     assert shapes == [4, 4, 8, 8, 16, 16, 16, 16]
     assert [c[1] for c in calls if c[0] == "reshape"] == [(8, 8, 8, 1), (16, 16, 16, 1)]
-    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 4
+    # optimize.py:249-250: an upsampling step leaves the medium on the CONFIGURED supergrid factor
+    assert scene.volume.res == (16, 16, 16) and scene.volume.majorant_resolution_factor == 8
     assert sorted(os.listdir(os.path.join(out, "params"))) == ["final-medium1_albedo.vol", "final-medium1_sigma_t.vol"]
     assert sorted(f for f in os.listdir(out) if f.endswith(".exr")) == ["ref_0002.exr"]
     with pytest.raises(ValueError, match="Initial resolution not supported"):

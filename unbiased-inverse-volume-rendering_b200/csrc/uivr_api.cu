@@ -190,6 +190,14 @@ int fill_params(uivr_ctx* ctx, Params& P, const uivr_shard* shard, uint32_t seed
     P.work_counter = ctx->work_counter;
     P.debug = ctx->debug;
     P.walk_limit = ctx->walk_limit;
+    {
+        // chunked work fetch of the forward kernel: at least ~32 chunks per SM, so that the last chunk of the slowest
+        // SM stays a small share of a short launch
+        const uint64_t total = (uint64_t) P.n_slots * (uint64_t) P.spp;
+        uint64_t c = total / ((uint64_t) ctx->num_sms * 32u);
+        c = c / 32u * 32u;
+        P.fetch_chunk = (int) (c < 32u ? 32u : (c > (uint64_t) UIVR_POOL_CHUNK_FWD ? (uint64_t) UIVR_POOL_CHUNK_FWD : c));
+    }
     return UIVR_OK;
 }
 
@@ -554,8 +562,6 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     P.dalbedo = d_dalbedo;
     P.sample_L = d_sample_L;
     const size_t vox = (size_t) P.res[0] * P.res[1] * P.res[2];
-    UIVR_CUDA(ctx, cudaMemsetAsync(d_dsigma_t, 0, vox * sizeof(float), st));
-    UIVR_CUDA(ctx, cudaMemsetAsync(d_dalbedo, 0, vox * 3 * sizeof(float), st));
     UIVR_CUDA(ctx, cudaMemsetAsync(ctx->work_counter, 0, sizeof(unsigned int) * 4, st));
     int grid = 0;
     // the O(n^2) mode (use_drt_subsampling = False) nests sub-paths: served by variant 1
@@ -566,7 +572,14 @@ int uivr_render_backward(uivr_ctx* ctx, const float* d_albedo, const float* d_gr
     UIVR_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], st));
     // (the slot-pool adjoint keeps max_depth + 1 vertex descriptors per in-flight sample: deeper paths than 255
     // vertices go to the one-sample-per-lane kernels)
-    if (quadratic || !pool_ok(ctx) || ctx->props.max_depth > 255) {
+    // The slot-pool kernels scatter into accumulation buffers of their own (tiles / RGBA) that are folded into the
+    // caller's tensors at the end: nothing else writes those, so they need no zeroing there.
+    const bool pool_path = !(quadratic || !pool_ok(ctx) || ctx->props.max_depth > 255);
+    const bool sigma_folded = pool_path && UIVR_DSIGMA_TILED && !UIVR_SCATTER_MATCH;
+    const bool albedo_folded = pool_path && UIVR_DALBEDO_V4;
+    if (!sigma_folded) UIVR_CUDA(ctx, cudaMemsetAsync(d_dsigma_t, 0, vox * sizeof(float), st));
+    if (!albedo_folded) UIVR_CUDA(ctx, cudaMemsetAsync(d_dalbedo, 0, vox * 3 * sizeof(float), st));
+    if (!pool_path) {
         if (ctx->counting) {
             if ((rc = persistent_grid(ctx, k_backward_v1<true>, kBlock, &grid))) return rc;
             k_backward_v1<true><<<grid, kBlock, 0, st>>>(P);

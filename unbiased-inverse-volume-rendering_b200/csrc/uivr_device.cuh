@@ -75,6 +75,7 @@ struct Params {
     int   tile_x, tile_y, tile_z; // tile origin: [copy][z][tile_y][tile_x] float4; else NULL
     unsigned long long* counters;
     unsigned int* work_counter;
+    int fetch_chunk;          // work items a CTA of the forward kernel reserves at a time (uivr_pool.cuh, UIVR_POOL_CHUNK_FWD)
     int walk_limit;           // watchdog: supergrid cells a walker warp may step in one go (uivr_debug_set_walk_limit)
     uint4* desc;              // adjoint launch: vertex descriptors, [CTA][slot][desc_cap][4] (uivr_pool.cuh)
     int desc_cap;             // descriptors per slot = max_depth + 1

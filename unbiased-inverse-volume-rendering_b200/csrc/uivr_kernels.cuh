@@ -124,23 +124,43 @@ __global__ void __launch_bounds__(kBlock) k_build_walk_table(const float* __rest
     }
 }
 
-// (UIVR_DSIGMA_TILED builds) fold the four tile copies into the caller's (Z,Y,X) gradient: voxel (x, y) lies in
-// tile ((x - px) >> 1, (y - py) >> 1), slot ((x - px) & 1) + 2 ((y - py) & 1) of the copy with tile origin (px, py)
+// (UIVR_DSIGMA_TILED builds) fold the four tile copies into the caller's (Z,Y,X) gradient (overwritten).  One thread
+// per 2 x 2 block of voxels (x = 2X, 2X+1; y = 2Y, 2Y+1): the block IS tile (X, Y) of copy (0, 0), it straddles two
+// tiles of the copies whose origin is odd in one axis and four of the copy that is odd in both -- nine aligned
+// 16-byte loads, neighbours in a warp read neighbouring tiles.  Copy p = px + 2 py holds the tiles with origin
+// (2 Xt + px, 2 Yt + py); slot = (x - origin) + 2 (y - origin).  Sum order per voxel: copy 0, 1, 2, 3.
 __global__ void __launch_bounds__(kBlock) k_tiles_to_dsigma(const float4* __restrict__ tiles, float* __restrict__ out, int rx,
                                                             int ry, int rz, int tx, int ty) {
-    const size_t n = (size_t) rx * ry * rz;
-    const float* t = reinterpret_cast<const float*>(tiles);
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-        const int x = (int) (i % rx), y = (int) ((i / rx) % ry), z = (int) (i / ((size_t) rx * ry));
-        float acc = 0.0f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int px = p & 1, py = p >> 1;
-            if (x < px || y < py) continue;
-            const int X = (x - px) >> 1, Y = (y - py) >> 1, slot = ((x - px) & 1) + 2 * ((y - py) & 1);
-            acc += t[((((size_t) p * rz + z) * ty + Y) * tx + X) * 4 + slot];
+    const size_t plane = (size_t) tx * ty, nblk = plane * rz;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nblk; i += (size_t) gridDim.x * blockDim.x) {
+        const int X = (int) (i % tx), Y = (int) ((i / tx) % ty), z = (int) (i / plane);
+        auto T = [&](int p, int Xt, int Yt) { return __ldg(tiles + ((size_t) p * rz + z) * plane + (size_t) Yt * tx + Xt); };
+        const float4 c0 = T(0, X, Y);
+        float a00 = c0.x, a10 = c0.y, a01 = c0.z, a11 = c0.w;   // a<x offset><y offset>
+        {   // copy 1: origin odd in x
+            const float4 r = T(1, X, Y);
+            a10 += r.x; a11 += r.z;
+            if (X > 0) { const float4 l = T(1, X - 1, Y); a00 += l.y; a01 += l.w; }
         }
-        out[i] += acc;
+        {   // copy 2: origin odd in y
+            const float4 u = T(2, X, Y);
+            a01 += u.x; a11 += u.y;
+            if (Y > 0) { const float4 d = T(2, X, Y - 1); a00 += d.z; a10 += d.w; }
+        }
+        {   // copy 3: origin odd in both
+            a11 += T(3, X, Y).x;
+            if (X > 0) a01 += T(3, X - 1, Y).y;
+            if (Y > 0) a10 += T(3, X, Y - 1).z;
+            if (X > 0 && Y > 0) a00 += T(3, X - 1, Y - 1).w;
+        }
+        const int x0 = 2 * X, y0 = 2 * Y;
+        float* o = out + ((size_t) z * ry + y0) * rx + x0;
+        o[0] = a00;
+        if (x0 + 1 < rx) o[1] = a10;
+        if (y0 + 1 < ry) {
+            o[rx] = a01;
+            if (x0 + 1 < rx) o[rx + 1] = a11;
+        }
     }
 }
 
@@ -160,17 +180,17 @@ __global__ void __launch_bounds__(kBlock) k_tiles3_to_dsigma(const float4* __res
             const int slot = ((x - px) & 1) + 2 * ((y - py) & 1) + 4 * ((z - pz) & 1);
             acc += t[((((size_t) p * tz + Z) * ty + Y) * tx + X) * 8 + slot];
         }
-        out[i] += acc;
+        out[i] = acc;
     }
 }
 
-// (UIVR_DALBEDO_V4 builds) fold the RGBA-padded accumulation buffer into the caller's (Z,Y,X,3) gradient
+// (UIVR_DALBEDO_V4 builds) fold the RGBA-padded accumulation buffer into the caller's (Z,Y,X,3) gradient (overwritten)
 __global__ void __launch_bounds__(kBlock) k_rgba_to_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
         const float4 v = in[i];
-        out[3 * i + 0] += v.x;
-        out[3 * i + 1] += v.y;
-        out[3 * i + 2] += v.z;
+        out[3 * i + 0] = v.x;
+        out[3 * i + 1] = v.y;
+        out[3 * i + 2] = v.z;
     }
 }
 

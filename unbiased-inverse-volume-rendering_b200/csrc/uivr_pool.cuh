@@ -1138,8 +1138,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             if (atomicCAS(&ctl->refill, 0, 1) != 0) break;
                             cs = *((volatile unsigned long long*) &ctl->chunk);
                             if (cs & 0xFFFFFFull) { atomicExch(&ctl->refill, 0); continue; }
-                            const unsigned gb = atomicAdd(P.work_counter, kPoolChunk);
-                            const uint64_t avail = (uint64_t) gb < total ? (total - gb < kPoolChunk ? total - gb : (uint64_t) kPoolChunk) : 0ull;
+                            const unsigned chunk = (unsigned) P.fetch_chunk;  // <= kPoolChunk: smaller for small launches (load balance)
+                            const unsigned gb = atomicAdd(P.work_counter, chunk);
+                            const uint64_t avail = (uint64_t) gb < total ? (total - gb < chunk ? total - gb : (uint64_t) chunk) : 0ull;
                             if (avail == 0ull) {
                                 ctl->exhausted = 1;  // the global queue is empty: from now on free slots retire
                             } else {

@@ -51,6 +51,7 @@ class Scene:
         self._medium_key = None
         self._scene_key = None
         self._props_key = None
+        self._env_ref = None
 
     # mi.traverse(scene) equivalent for the two optimised grids
     def check_params(self, params: Dict[str, torch.Tensor],
@@ -72,11 +73,15 @@ class Scene:
         desc = vol.as_dict()
         env_keys = ("env_data", "env_marg", "env_cond")  # big tables: keyed by identity of the EnvMap object
         key = tuple((k, tuple(map(float, v.reshape(-1))) if hasattr(v, "reshape") else v)
-                    for k, v in sorted(desc.items()) if k not in env_keys) + (id(vol.envmap),)
+                    for k, v in sorted(desc.items()) if k not in env_keys)
         if key != self._scene_key:
             old_medium_inputs = None if self._scene_key is None else self._medium_inputs
             self.ctx.set_scene(desc)
-            self.ctx.set_envmap(desc)
+            # The environment map has its own key: a sensor change (one per iteration in the optimisation loop) must
+            # not re-upload tens of MB of tables.  The strong reference keeps id() from being recycled.
+            if self._env_ref is not vol.envmap or self._scene_key is None:
+                self.ctx.set_envmap(desc)
+                self._env_ref = vol.envmap
             self._scene_key = key
             self._medium_inputs = (desc["res"], float(desc["scale"]), desc["majorant_factor"])
             if old_medium_inputs != self._medium_inputs:

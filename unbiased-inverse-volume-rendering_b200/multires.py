@@ -62,13 +62,17 @@ def upsample_iterations(upsample: Iterable[float], n_iter: int) -> Set[int]:
     return out
 
 
-def upsample_params(scene: Scene, opt, majorant_resolution_factor: int) -> Dict[str, Tuple[int, ...]]:
-    """optimize.py:228-252: double the resolution of every optimised grid, re-derive the supergrid
-    factor for the new density resolution, rebuild the medium.  `opt` is an optimize.Adam: the
-    state of a re-shaped parameter starts over, as mi.ad.Optimizer does when a parameter changes
-    size.  Returns the new shapes."""
+def upsample_params(scene: Scene, opt, majorant_resolution_factor: int, keep_adjusted: bool = False) -> Dict[str, Tuple[int, ...]]:
+    """optimize.py:228-252: double the resolution of every optimised grid and rebuild the medium.  `opt` is an
+    optimize.Adam: the state of a re-shaped parameter starts over, as mi.ad.Optimizer does when a parameter changes
+    size.  Returns the new shapes.
+
+    Supergrid factor: the reference re-derives it for the new density resolution inside the loop (:245-246) and then
+    sets the medium back to the CONFIGURED factor (:249-250), so after an upsampling step the configured factor is
+    what renders -- mirrored here, because the tentative collisions (and with them the sample streams) depend on it.
+    `keep_adjusted=True` keeps the re-derived factor instead (a supergrid of at least 4 cells per side)."""
     new_shapes = {}
-    factor = majorant_resolution_factor
+    adjusted = majorant_resolution_factor
     k_sig = None
     for k in list(opt.params.keys()):
         v = opt.params[k]
@@ -80,9 +84,9 @@ def upsample_params(scene: Scene, opt, majorant_resolution_factor: int) -> Dict[
         new_shapes[k] = new_res
         if k.endswith(SIGMA_T_SUFFIX):
             k_sig = k
-            factor = adjust_majorant_res_factor(majorant_resolution_factor, new_res)
+            adjusted = adjust_majorant_res_factor(majorant_resolution_factor, new_res)
     z, y, x = new_shapes[k_sig][:3]
-    scene.volume = scene.volume.with_resolution((x, y, z), factor)
+    scene.volume = scene.volume.with_resolution((x, y, z), adjusted if keep_adjusted else majorant_resolution_factor)
     scene.update_medium_after_reshape(opt.params[k_sig])
     return new_shapes
 

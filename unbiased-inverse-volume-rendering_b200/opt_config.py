@@ -33,24 +33,23 @@ class OptimizationConfig:
     spp: int                                       # samples per pixel of the adjoint pass
     n_iter: int
     lr: float
-    # sampling
+    # defaults, in the reference's positional order as well (opt_config.py:19-37): reference-style positional
+    # construction binds the same fields
     primal_spp_factor: int = 64                    # primal spp = spp x this
     batch_size: Optional[int] = None               # None: one random sensor per iteration; else rays per batch
-    base_seed: int = 988378
-    # schedule
     lr_schedule: Optional[Schedule] = None
     upsample: Optional[List[float]] = None         # fractions of the run at which the grids double
-    opt_type: str = "adam"                         # "adam" | "sgd"
-    opt_args: Optional[Dict[str, Any]] = None
-    loss: Callable = losses.l1
-    # outputs
-    checkpoint_initial: bool = True
-    checkpoint_final: bool = True
-    checkpoint_stride: Optional[int] = 1000        # None / 0: no intermediate checkpoints
+    base_seed: int = 988378
     render_initial: bool = True
     render_final: bool = True
     preview_stride: int = 100
+    checkpoint_initial: bool = True
+    checkpoint_final: bool = True
+    checkpoint_stride: Optional[int] = 1000        # None / 0: no intermediate checkpoints
     preview_spp: Optional[int] = None              # None: spp
+    opt_type: str = "adam"                         # "adam" | "sgd"
+    opt_args: Optional[Dict[str, Any]] = None
+    loss: Callable = losses.l1
 
     def __post_init__(self):
         from .multires import upsample_iterations

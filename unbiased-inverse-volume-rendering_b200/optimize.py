@@ -230,9 +230,9 @@ def _grid_shape(volume, key: str) -> Tuple[int, int, int, int]:
     return (z, y, x, 1 if key.endswith(SIGMA_T_SUFFIX) else 3)
 
 
-def _bound_scene(volume, sigma_t_shape, device) -> Scene:
+def _bound_scene(volume, sigma_t_shape, device, factor: Optional[int] = None) -> Scene:
     z, y, x = sigma_t_shape[:3]
-    return Scene(volume.with_resolution((x, y, z), volume.majorant_resolution_factor), device)
+    return Scene(volume.with_resolution((x, y, z), volume.majorant_resolution_factor if factor is None else factor), device)
 
 
 def reference_pass_plan(film_size: Tuple[int, int], ref_spp: int, max_rays_per_pass: int) -> Tuple[int, int]:
@@ -253,7 +253,8 @@ def render_reference_image(scene_config, to_render: Dict[int, str], seed: int = 
     dev = _cuda_device(device)
     params = {k: _as_grid(v, dev) for k, v in scene_config.ref_params.items()}
     k_sig = next(k for k in params if k.endswith(SIGMA_T_SUFFIX))
-    scene = _bound_scene(scene_config.ref_volume, params[k_sig].shape, dev.index)
+    # the reference loads its scene file with the configuration's supergrid factor (scene_config.py:36, scene vars)
+    scene = _bound_scene(scene_config.ref_volume, params[k_sig].shape, dev.index, scene_config.majorant_resolution_factor)
     integrator = load_dict({"type": scene_config.ref_integrator, "max_depth": scene_config.max_depth})
     for s, fname in to_render.items():
         sensor = scene_config.scene_sensors[s]
