@@ -86,6 +86,9 @@ namespace uivr {
 // r02_history.md, call V): the forward kernel gains 5 % at 2048, the backward kernels lose 2 % at any size -- their
 // handler warps are the bottleneck, and a visit that finds the reservation empty while another warp refills it is a
 // wasted visit
+#ifndef UIVR_POOL_SCATTER_AT_END
+#define UIVR_POOL_SCATTER_AT_END 1   // the path-end handler scatters the first described vertex itself (one queue hop less per path)
+#endif
 #ifndef UIVR_POOL_CHUNK_FWD
 #define UIVR_POOL_CHUNK_FWD 2048
 #endif
@@ -698,6 +701,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
             bool resume = false;  // next == Q_WALK continues a walk after a null collision (no set-up)
             // gradient scatter request of the handlers (executed at one site below)
             bool sc_taps = false, sc_ff = false, sc_alb = true;  // sc_alb: the vertex request also scatters d albedo
+            bool scatter_now = false;  // (adjoint kernel) the path has just ended: its first described vertex is due
             float sc_g = 0.0f, sc_int = 0.0f, sc_gs = 0.0f, sc_ga[3] = {0.0f, 0.0f, 0.0f};
             float sc_ox = 0.0f, sc_oy = 0.0f, sc_oz = 0.0f, sc_dx = 0.0f, sc_dy = 0.0f, sc_dz = 0.0f;
             float sc_vx = 0.0f, sc_vy = 0.0f, sc_vz = 0.0f;
@@ -789,53 +793,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                     PU(F_RNG_HI, s) = (uint32_t) (r.state >> 32);
                     PU(F_FLAGS, s) = fl;
                 }
-            } else if (HAS_ADJ && work == Q_SCATTER) {
-                // ---- deferred gradients of one described vertex of a finished path (see the vertex handler) ----
-                if (act) {
-                    // vertices in path order: F_R holds L minus the NEE contributions of the vertices before this one,
-                    // subtracted one by one exactly like the reference's replay does (:214)
-                    const unsigned tw = PU(F_TS, s), k = tw & 0xFFFFu, n_desc = tw >> 16;
-                    PU(F_TS, s) = tw + 1u;
-                    const uint4* dsc = P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + k) * kDescVec;
-                    const uint4 d0 = __ldcg(dsc + 0), d1 = __ldcg(dsc + 1), d2 = __ldcg(dsc + 2), d3 = __ldcg(dsc + 3);
-                    alt.state = (uint64_t) d0.x | ((uint64_t) d0.y << 32);
-                    alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
-                    const float st = __uint_as_float(d0.z);
-                    const bool ds = d0.z != 0u;
-                    sc_int = __uint_as_float(d0.w);
-                    sc_ox = __uint_as_float(d1.x); sc_oy = __uint_as_float(d1.y); sc_oz = __uint_as_float(d1.z);
-                    sc_dx = __uint_as_float(d1.w); sc_dy = __uint_as_float(d2.x); sc_dz = __uint_as_float(d2.y);
-                    const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
-                    const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
-                    PSET(F_R0, s, R[0] - __uint_as_float(d2.z));
-                    PSET(F_R1, s, R[1] - __uint_as_float(d2.w));
-                    PSET(F_R2, s, R[2] - __uint_as_float(d3.x));
-                    const float albedo[3] = {__uint_as_float(d3.y), __uint_as_float(d3.z), __uint_as_float(d3.w)};
-                    next = k + 1u < n_desc ? Q_SCATTER : Q_FREE;
-                    // :152-172 free-flight scattering gradient
-                    if ((!P.use_drt || P.use_drt_mis) && ds) {
-                        float m = 1.0f;
-                        if (P.use_drt && P.use_drt_mis) {
-                            const float s2 = st * st;
-                            m = s2 / (1.0f + s2);
-                        }
-                        const float inv_pdf = 1.0f / st;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float Li = R[c] / (albedo[c] > 1e-8f ? albedo[c] : 1e-8f);
-                            const float term = ((m * dL[c]) * Li) * inv_pdf;
-                            sc_gs = fmaf(term, albedo[c], sc_gs);
-                            sc_ga[c] = term * st;
-                        }
-                        sc_ff = true;
-                        sc_vx = fmaf(sc_int, sc_dx, sc_ox); sc_vy = fmaf(sc_int, sc_dy, sc_oy); sc_vz = fmaf(sc_int, sc_dz, sc_oz);
-                    }
-                    // :181-189, :584-607 transmittance gradient: 4 uniform taps on the segment
-                    const float aw = fmaf(dL[2], R[2], fmaf(dL[1], R[1], dL[0] * R[0]));
-                    sc_g = -(aw * (sc_int * 0.25f));
-                    sc_taps = true;
-                }
-            } else if (work == Q_VERTEX || work == Q_VERTEX_ADJ) {
+            } else if ((!HAS_ADJ && work == Q_VERTEX) || work == Q_VERTEX_ADJ) {   // (adjoint kernel: Q_VERTEX is Q_SCATTER)
                 // ---- end of a delta-tracking segment (:130-245) or of the DRT walk (:550-558) ----
                 if (act) {
                     unsigned fl = PU(F_FLAGS, s);
@@ -1064,7 +1022,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         if (n_desc) {
                             PSET(F_R0, s, R[0]); PSET(F_R1, s, R[1]); PSET(F_R2, s, R[2]);
                             PU(F_TS, s) = n_desc << 16;  // next vertex to scatter (low half) of n_desc (high half)
+#if UIVR_POOL_SCATTER_AT_END
+                            scatter_now = true;          // the first one in this very visit (below)
+#else
                             next = Q_SCATTER;
+#endif
                         }
                     } else if (HAS_DRT) {  // PP_REC: Li complete -> DRT gradient (:571-581)
                         const float dst = PF(F_DRT_ST, s), dD = PF(F_DRT_D, s), dt = PF(F_DRT_T, s);
@@ -1275,6 +1237,55 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                         }
                         PU(F_FLAGS, s) = fl;
                     }
+                }
+            }
+
+            // ---- deferred gradients of one described vertex of a finished path (see the vertex handler): for the
+            //      batch of Q_SCATTER and, without a queue hop, for the first vertex of the paths that have just ended ----
+            if (HAS_ADJ && __ballot_sync(FULL, act && (work == Q_SCATTER || scatter_now))) {
+                if (act && (work == Q_SCATTER || scatter_now)) {
+                    // vertices in path order: F_R holds L minus the NEE contributions of the vertices before this one,
+                    // subtracted one by one exactly like the reference's replay does (:214)
+                    const unsigned tw = PU(F_TS, s), k = tw & 0xFFFFu, n_desc = tw >> 16;
+                    PU(F_TS, s) = tw + 1u;
+                    const uint4* dsc = P.desc + (((size_t) blockIdx.x * NSLOT + s) * P.desc_cap + k) * kDescVec;
+                    const uint4 d0 = __ldcg(dsc + 0), d1 = __ldcg(dsc + 1), d2 = __ldcg(dsc + 2), d3 = __ldcg(dsc + 3);
+                    alt.state = (uint64_t) d0.x | ((uint64_t) d0.y << 32);
+                    alt.inc = ((uint64_t) PU(F_ASEQ, s) << 1) | 1ull;
+                    const float st = __uint_as_float(d0.z);
+                    const bool ds = d0.z != 0u;
+                    sc_int = __uint_as_float(d0.w);
+                    sc_ox = __uint_as_float(d1.x); sc_oy = __uint_as_float(d1.y); sc_oz = __uint_as_float(d1.z);
+                    sc_dx = __uint_as_float(d1.w); sc_dy = __uint_as_float(d2.x); sc_dz = __uint_as_float(d2.y);
+                    const float dL[3] = {PF(F_DL0, s), PF(F_DL1, s), PF(F_DL2, s)};
+                    const float R[3] = {PF(F_R0, s), PF(F_R1, s), PF(F_R2, s)};
+                    PSET(F_R0, s, R[0] - __uint_as_float(d2.z));
+                    PSET(F_R1, s, R[1] - __uint_as_float(d2.w));
+                    PSET(F_R2, s, R[2] - __uint_as_float(d3.x));
+                    const float albedo[3] = {__uint_as_float(d3.y), __uint_as_float(d3.z), __uint_as_float(d3.w)};
+                    next = k + 1u < n_desc ? Q_SCATTER : Q_FREE;
+                    // :152-172 free-flight scattering gradient
+                    if ((!P.use_drt || P.use_drt_mis) && ds) {
+                        float m = 1.0f;
+                        if (P.use_drt && P.use_drt_mis) {
+                            const float s2 = st * st;
+                            m = s2 / (1.0f + s2);
+                        }
+                        const float inv_pdf = 1.0f / st;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float Li = R[c] / (albedo[c] > 1e-8f ? albedo[c] : 1e-8f);
+                            const float term = ((m * dL[c]) * Li) * inv_pdf;
+                            sc_gs = fmaf(term, albedo[c], sc_gs);
+                            sc_ga[c] = term * st;
+                        }
+                        sc_ff = true;
+                        sc_vx = fmaf(sc_int, sc_dx, sc_ox); sc_vy = fmaf(sc_int, sc_dy, sc_oy); sc_vz = fmaf(sc_int, sc_dz, sc_oz);
+                    }
+                    // :181-189, :584-607 transmittance gradient: 4 uniform taps on the segment
+                    const float aw = fmaf(dL[2], R[2], fmaf(dL[1], R[1], dL[0] * R[0]));
+                    sc_g = -(aw * (sc_int * 0.25f));
+                    sc_taps = true;
                 }
             }
 
