@@ -11,10 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "unbiased-inverse-volume-rendering_b200", "csrc", "uivr_pool.cuh")
 MARKS = [("w-top", "WALKER WARPS:"), ("pickup", "1. idle lanes pick up"), ("w-idle", "const unsigned m_walk ="),
          ("DDA-loop", "for (int it = 1;; ++it)"), ("flush", "3. hand finished lanes on"),
-         ("h-sched+pop", "HANDLER WARPS:"), ("TAP", "if (work == Q_TAP)"), ("SCATTER-stage", "} else if (HAS_ADJ && work == Q_SCATTER)"),
-         ("VERTEX", "} else if (work == Q_VERTEX"),
+         ("h-sched+pop", "HANDLER WARPS:"), ("TAP", "if (work == Q_TAP)"),
+         ("VERTEX", "} else if ((!HAS_ADJ && work == Q_VERTEX)"),
          ("NEE_END", "} else if (work == Q_NEE_END)"), ("PATH_END", "} else if (work == Q_PATH_END)"),
-         ("FETCH", "Q_FREE: next work item"), ("SPAWN", "one code site: for the batch of"),
+         ("FETCH", "Q_FREE: next work item"), ("SCATTER-stage", "deferred gradients of one described vertex of a finished path"),
+         ("NEE-log", "NEE adjoint from the collision log"), ("SPAWN", "one code site: for the batch of"),
          ("scatter", "gradient scatter of the batch"), ("walk-setup", "set-up of a new free-flight walk"),
          ("end", "#undef PU")]
 
