@@ -218,7 +218,7 @@ int uivr_set_counting(uivr_ctx* ctx, int enable);
 int uivr_reset_counters(uivr_ctx* ctx, void* stream);
 int uivr_get_counters(uivr_ctx* ctx, uint64_t out[UIVR_NUM_COUNTERS], void* stream); /* synchronises */
 /* CUDA-event duration (ms) of the most recent path megakernel launched by this context:
- * which = 0 forward (sample(Primal) kernel), 1 backward (primal replay + adjoint + DRT kernel).
+ * which = 0 forward (sample(Primal) kernel), 1 backward (adjoint replay + DRT launches + gradient folds; the one-sample-per-lane route: its single kernel).
  * Events are recorded on the stream the kernel was launched on; synchronises on the end event. */
 int uivr_get_kernel_ms(uivr_ctx* ctx, int which, float* ms);
 /* Synchronises `stream` and reports whether a persistent path kernel launched by this context

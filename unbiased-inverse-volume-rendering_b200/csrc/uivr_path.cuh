@@ -1,8 +1,8 @@
 // uivr_path.cuh -- per-sample path logic (variant 1: one sample per lane, run to completion).
 //
 // Follows python/integrators/volpathsimple.py; every function cites the lines it replaces.
-// The persistent lane-refill megakernel (uivr_mega.cuh) re-expresses the same logic as a
-// state machine and must produce identical per-sample results.
+// The persistent slot-pool kernels (uivr_pool.cuh) re-express the same logic as a state machine
+// and must produce identical per-sample results.
 #pragma once
 
 #include "uivr_device.cuh"

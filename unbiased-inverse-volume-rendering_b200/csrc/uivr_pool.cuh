@@ -8,11 +8,11 @@
 //                                         -> Q_VERTEX / Q_NEE_END / Q_SPAWN (segment end) ... -> Q_PATH_END -> Q_FREE
 //
 // Warps are specialised.  WALKER warps run ONLY the supergrid DDA of the free-flight walk (Medium::
-// sample_interaction and its ratio-tracking / DRT siblings): ~30 instructions per cell, no RNG, no taps, no
+// sample_interaction and its ratio-tracking / DRT siblings): ~48 instructions per cell, no RNG, no taps, no
 // divisions.  The walk is a CONTINUATION stored in the pool (next-boundary times, their increments, cell
 // index, remaining optical depth tau, position t): a walker lane picks one up with a dozen shared-memory
 // loads, steps cells until the walk ends or tau is used up inside a cell, and hands the slot on -- on a
-// tentative collision it first saves the six words that changed.  Everything else runs in HANDLER warps,
+// tentative collision it first saves the eight words that changed.  Everything else runs in HANDLER warps,
 // which pop FULL batches of 32 slots of one queue, so that the expensive code (ray generation, the walk
 // set-up with its divisions, the sigma_t tap + accept/reject decision, vertices, emitter / phase sampling,
 // gradient scatter) always runs with all lanes: compaction of live rays across the whole CTA.
@@ -266,13 +266,13 @@ __device__ __noinline__ void pool_trip_dump(const PoolCtl* ctl, unsigned* debug)
     debug[5 + 3 * Q_NUM] = (unsigned) ctl->exhausted;
 }
 
-// kernel kinds: the forward / primal kernel and the two halves of the backward pipeline, which runs the
-// primal replay with the forward kernel (per-sample radiance to HBM), then the adjoint replay (reservoir
-// records to HBM), then the DRT pass.  Splitting trades ~1.3 GB of coalesced HBM traffic (the path is at
-// < 15 % of the HBM roofline) for three lean kernels with fewer live modes each.
+// kernel kinds: the forward / primal kernel and the two halves of the backward pipeline -- the adjoint replay
+// (gathers the primal radiance itself, scatters the free-flight / transmittance / NEE gradients, hands one
+// reservoir record per sample to HBM), then the DRT pass on those records.  Splitting trades ~1 GB of coalesced
+// HBM traffic (the path is at < 15 % of the HBM roofline) for lean kernels with fewer live modes each.
 enum : int { KIND_FWD = 0, KIND_ADJ = 2, KIND_DRT = 3 };
 constexpr int kRecWords = 16;  // reservoir record: seg(7) dL'(3) alt state(2) alt seq(1) depth(1) pad(2)
-// Vertex descriptor of the adjoint kernel (4 x uint4, global memory, one area of max_depth + 1 descriptors per
+// Vertex descriptor of the adjoint kernel (5 x uint4, global memory, one area of max_depth + 1 descriptors per
 // slot): what the free-flight (:152-172) and transmittance (:181-189) gradients of one path segment need apart from
 // the radiance that is still to come -- which is only known when the path has ended.
 //   {alt state lo, hi, sigma_t at the collision (0: the segment escaped), interval} {o.xyz, d.x} {d.yz, c.xy}
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_pool(const Params P) {
                             P.sample_L[3 * (size_t) idx + 1] = R[1];
                             P.sample_L[3 * (size_t) idx + 2] = R[2];
                         }
-                        if (P.image) {  // (null when this launch is the primal replay of the backward)
+                        if (P.image) {
                             atomicAdd(P.image + 3 * (size_t) pix + 0, R[0]);
                             atomicAdd(P.image + 3 * (size_t) pix + 1, R[1]);
                             atomicAdd(P.image + 3 * (size_t) pix + 2, R[2]);
