@@ -1,6 +1,8 @@
-"""GPU-vs-GPU stress of the slot-pool kernel (variant 2) against the lane-refill megakernel
-(variant 0) at sizes where every pool slot is recycled many times (the oracle would take too
-long here; variant 0 itself is pinned to the oracle by tests/test_gpu_parity.py)."""
+"""GPU-vs-GPU stress of the slot-pool kernels (variant 3) against the one-sample-per-lane kernels
+(variant 1) at sizes where every pool slot is recycled many times (the oracle would take too
+long here; variant 1 itself is pinned to the oracle by tests/test_gpu_parity.py).
+
+    python scripts/stress_pool.py [n=64 w=256 h=256 spp=16 factor=8]      # drt, basic and no-MIS flag sets"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -34,8 +36,16 @@ def run(variant, n, w, h, spp, factor, combo="volpathsimple-drt", max_depth=64):
 
 
 def main(n=64, w=256, h=256, spp=16, factor=8):
-    ref = run(0, n, w, h, spp, factor)
-    new = run(int(os.environ.get("UIVR_STRESS_VARIANT", "3")), n, w, h, spp, factor)
+    rc = 0
+    for combo, depth in (("volpathsimple-drt", 64), ("volpathsimple-basic", 64), ("volpathsimple-drt", 3)):
+        print(f"== {combo}, max_depth {depth}")
+        rc |= compare(n, w, h, spp, factor, combo, depth)
+    return rc
+
+
+def compare(n, w, h, spp, factor, combo, depth):
+    ref = run(1, n, w, h, spp, factor, combo, depth)
+    new = run(3, n, w, h, spp, factor, combo, depth)
     ok = True
     for name, a, b in zip(("image", "samples_fwd", "samples_bwd"), ref[:3], new[:3]):
         same = torch.equal(a.view(torch.int32), b.view(torch.int32)) if name != "image" else float((a - b).abs().max()) < 1e-5
