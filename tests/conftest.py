@@ -24,8 +24,15 @@ def uivr():
     return importlib.import_module("uivr_b200")
 
 
+NEE_LOG_CAPACITY = 32   # kNeeLog of csrc/uivr_pool.cuh
+
+
 @pytest.fixture(scope="session")
 def oracle():
+    """The checker.  Its EVENT COUNTERS model the collision log of the CUDA adjoint kernel (shadow walks with more
+    tentative collisions than the log holds are walked twice there, like in the reference): results are unaffected,
+    but `fused_backward_counters` must book exactly the second walks the kernel really skips."""
     from oracle import oracle as O
     O.build()
+    O.set_nee_log_capacity(NEE_LOG_CAPACITY)
     return O

@@ -267,7 +267,7 @@ def _spiky_grids(n=16, seed=5):
     return sig, alb
 
 
-NEE_LOG_CAPACITY = 32   # kNeeLog of csrc/uivr_pool.cuh
+from conftest import NEE_LOG_CAPACITY   # kNeeLog of csrc/uivr_pool.cuh
 
 
 def test_nee_collision_log_overflow_falls_back_to_the_second_walk(uivr, oracle, dev):
@@ -281,13 +281,10 @@ def test_nee_collision_log_overflow_falls_back_to_the_second_walk(uivr, oracle, 
     img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 91, spp)
     gimg = loss_grad(img)
     sg = uivr.tea32(91, 1)
-    oracle.set_nee_log_capacity(NEE_LOG_CAPACITY)
-    try:
-        ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, spp, want_samples=True)
-        overflows = oracle.nee_log_overflows()
-        cnt_o = _pipeline_counters(oracle, cnt_o, 3, props)
-    finally:
-        oracle.set_nee_log_capacity(0)
+    oracle.set_nee_log_capacity(NEE_LOG_CAPACITY)   # (the session default of conftest.py; resets the overflow count)
+    ds_o, da_o, smp_o, cnt_o = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, sg, spp, want_samples=True)
+    overflows = oracle.nee_log_overflows()
+    cnt_o = _pipeline_counters(oracle, cnt_o, 3, props)
     assert overflows > 100, "the scene must exercise the fall-back"
     ds_g, da_g, smp_g, cnt_g = _run_backward(uivr, vol, props, sig, alb, gimg, sg, spp, dev, 3)
     assert np.array_equal(smp_g.view(np.uint32), smp_o.view(np.uint32))

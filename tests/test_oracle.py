@@ -291,15 +291,17 @@ def test_nee_log_capacity_only_moves_event_counts(oracle, uivr):
     props = dict(max_depth=6)
     img, _, _ = oracle.render_forward(vol.as_dict(), props, sig, alb, 91, 4)
     gimg = loss_grad(img)
-    ds0, da0, _, cnt0 = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 7, 4, want_samples=True)
-    rep0 = oracle.last_backward_replay_counters()
-    oracle.set_nee_log_capacity(32)
+    from conftest import NEE_LOG_CAPACITY
     try:
+        oracle.set_nee_log_capacity(0)       # unlimited: every second walk is booked as skipped
+        ds0, da0, _, cnt0 = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 7, 4, want_samples=True)
+        rep0 = oracle.last_backward_replay_counters()
+        oracle.set_nee_log_capacity(32)
         ds1, da1, _, cnt1 = oracle.render_backward(vol.as_dict(), props, sig, alb, gimg, 7, 4, want_samples=True)
         rep1 = oracle.last_backward_replay_counters()
         over = oracle.nee_log_overflows()
     finally:
-        oracle.set_nee_log_capacity(0)
+        oracle.set_nee_log_capacity(NEE_LOG_CAPACITY)   # the session default (conftest.py)
     assert cnt0 == cnt1 and rel_linf(ds1, ds0) < 1e-5 and rel_linf(da1, da0) < 1e-5
     assert over > 100
     assert 0 < rep1["sigma_taps"] < rep0["sigma_taps"] and rep1["rng_draws"] < rep0["rng_draws"]
