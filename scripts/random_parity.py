@@ -46,7 +46,7 @@ def main(first=16, count=300, variant=3):
         if not ok:
             bad += 1
             print("MISMATCH case", case, props, "grad errors", es, ea, flush=True)
-    print(f"{count} random cases (seeds {first}..{first + count - 1}), slot-pool kernels vs oracle: {bad} mismatches; "
+    print(f"{count} random cases (seeds {first}..{first + count - 1}), kernel variant {variant} vs oracle: {bad} mismatches; "
           f"worst gradient relative L-inf {worst_s:.2e} (sigma_t) / {worst_a:.2e} (albedo)")
     return 1 if bad else 0
 
