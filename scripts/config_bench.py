@@ -58,6 +58,15 @@ def config4(reps=2, views=32, spp=32):
     print(json.dumps({"config": f"4: 256^3, {views} views x 512x512x{spp}spp, render + L1 + backward per view, Adam + clamp + supergrid rebuild",
                       "ms_per_step": ms, "steps_per_s": 1e3 / ms, "msamples_per_s": views * w * h * spp / ms / 1e3,
                       "losses": losses}))
+    # the same with the views alternating between two contexts / streams (the drain of one view's launches overlaps
+    # the other view's kernels)
+    for n_lanes in (2, 3):
+        lanes = u.make_view_lanes(scene, params, n_lanes)
+        losses2 = []
+        ms2 = timed(lambda: losses2.append(u.optimization_step(scene, integ, opt, sensors, refs, next(it), spp, grads=grads, lanes=lanes)), reps)
+        print(json.dumps({"config": f"4 with {n_lanes} view lanes: 256^3, {views} views x 512x512x{spp}spp", "ms_per_step": ms2,
+                          "steps_per_s": 1e3 / ms2, "msamples_per_s": views * w * h * spp / ms2 / 1e3, "losses": losses2}))
+        del lanes
 
 
 def config3_envmap(reps=3):

@@ -663,6 +663,38 @@ def test_optimization_step_multiview(uivr, dev):
     assert set(opt.t.values()) == {12}
 
 
+def test_optimization_step_with_view_lanes_is_the_same_step(uivr, dev):
+    """optimization_step(lanes=...): the views alternate between two contexts / CUDA streams.  Same seeds, same
+    samples: the losses are identical and the updated parameters agree to the order of the gradient sums."""
+    n, w, h, spp = 12, 24, 20, 16
+    sig_t, alb_t = hetero_grids(n, seed=5)
+    vol = uivr.benchmark_scene(n, w, h, scale=6.0, majorant_resolution_factor=4)
+    integ = uivr.get_int_config("volpathsimple-drt").create(max_depth=12)
+    sensors = uivr.circle_sensors(5, w, h)   # odd: the lanes get 3 and 2 views
+    target = {"m.sigma_t.data": _gpu(sig_t, dev), "m.albedo.data": _gpu(alb_t, dev)}
+    ref_scene = uivr.Scene(vol, device=0)
+    refs = [integ.render(ref_scene, target, sensor=s, seed=70 + i, spp=128).clone() for i, s in enumerate(sensors)]
+    out = []
+    for use_lanes in (False, True):
+        scene = uivr.Scene(vol, device=0)
+        params = {"m.sigma_t.data": torch.full((n, n, n, 1), 0.3, device=dev),
+                  "m.albedo.data": torch.full((n, n, n, 3), 0.6, device=dev)}
+        opt = uivr.Adam(lr=1e-2, params=params)
+        lanes = uivr.make_view_lanes(scene, params, 2) if use_lanes else None
+        losses = [uivr.optimization_step(scene, integ, opt, sensors, refs, it, spp, lanes=lanes) for it in range(3)]
+        torch.cuda.synchronize()
+        for lane in lanes or []:
+            lane.scene.ctx.check_watchdog()
+        scene.ctx.check_watchdog()
+        out.append((losses, params["m.sigma_t.data"].cpu().numpy(), params["m.albedo.data"].cpu().numpy()))
+    (l0, s0, a0), (l1, s1, a1) = out
+    assert np.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
+    # Adam normalises the gradient: a sum that differs in the last bits can move a voxel whose gradient is ~0 by up
+    # to one learning-rate step per iteration; everywhere else the parameters agree closely
+    assert np.abs(s1 - s0).max() <= 3 * 1e-2 + 1e-6 and np.median(np.abs(s1 - s0)) < 1e-5
+    assert np.abs(a1 - a0).max() <= 3 * 2e-2 + 1e-6 and np.median(np.abs(a1 - a0)) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------
 # ragged shapes: anisotropic grid resolution, non-square film, supergrid factor that does
 # not divide the resolution, anisotropic medium box, odd spp

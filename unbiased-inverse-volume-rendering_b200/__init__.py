@@ -14,7 +14,7 @@ from .multires import (adjust_majorant_res_factor, read_vol, save_params, upsamp
 from .fd import fd_gradients
 from .optimize import (PCG32, SGD, Adam, checkpoint_prefix, create_checkpoint, get_reference_image_paths,
                        initial_resolution, initialize_scene, l1_loss_grad, learning_rates, load_reference_images,
-                       optimization_step, param_bounds, preview_suffix, reference_pass_plan, render_previews,
+                       make_view_lanes, optimization_step, param_bounds, preview_suffix, reference_pass_plan, render_previews,
                        render_reference_image, run_optimization)
 from .scene import (EnvMap, Sensor, VolumeScene, benchmark_scene, circle_sensors, cube_test_grids,
                     cube_test_scene, look_at, synthetic_grids)
@@ -31,5 +31,5 @@ __all__ = [
     "read_exr", "write_exr", "read_hdr", "write_hdr", "EnvMap", "PCG32", "SGD", "checkpoint_prefix", "create_checkpoint", "get_reference_image_paths",
     "initial_resolution", "initialize_scene", "load_reference_images", "preview_suffix", "reference_pass_plan",
     "render_previews", "render_reference_image", "run_optimization",
-    "fd_gradients", "Adam", "l1_loss_grad", "learning_rates", "optimization_step", "param_bounds",
+    "fd_gradients", "Adam", "l1_loss_grad", "learning_rates", "make_view_lanes", "optimization_step", "param_bounds",
 ]
